@@ -1,0 +1,198 @@
+/*
+ * rnad_b200.h - C ABI of the B200-native R-NaD self-play hot path.
+ *
+ * The reference (baskuit/R-NaD) has no FFI of its own: its hot path is Python
+ * calling ATen.  Each entry point below replaces the group of ATen calls the
+ * cited reference lines issue, and is what a reference-side binding (ctypes,
+ * see INTEGRATION.md) loads from librnad_b200.so.
+ *
+ * Conventions (all entry points)
+ *   - every pointer is a DEVICE pointer into caller-owned memory unless the
+ *     parameter says "host"; nothing is allocated, freed or retained;
+ *   - work is enqueued on `stream` (a cudaStream_t passed as void*; NULL =
+ *     the legacy default stream) and the call returns without synchronising;
+ *   - the return value is 0 on success, a negative RNAD_E* code otherwise;
+ *     rnad_last_error() gives the message for the calling thread;
+ *   - time-major trajectory tensors are laid out (T, B, ...) contiguous,
+ *     exactly like the reference's `Episodes` members (episode.py:218-227).
+ */
+#ifndef RNAD_B200_H
+#define RNAD_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define RNAD_API __attribute__((visibility("default")))
+#else
+#define RNAD_API
+#endif
+
+#define RNAD_OK 0
+#define RNAD_EINVAL (-1)      /* bad argument (shape, null pointer, unsupported size) */
+#define RNAD_ECUDA (-2)       /* CUDA runtime / launch error */
+#define RNAD_EUNSUPPORTED (-3) /* valid request the selected kernel variant cannot serve */
+
+/* precision / engine selector of the fused rollout */
+#define RNAD_PREC_FP32 0 /* FFMA on the CUDA cores, fp32 throughout (validation build) */
+#define RNAD_PREC_TF32 1 /* first layer on tcgen05 tensor cores, kind::tf32, fp32 accumulate in TMEM */
+
+#define RNAD_MAX_ACTIONS 8
+#define RNAD_MAX_TRANSITIONS 8
+
+RNAD_API const char* rnad_last_error(void);
+/* version of this ABI (major*100 + minor) */
+RNAD_API int rnad_version(void);
+/* number of SMs of the current device (host value), <0 on error */
+RNAD_API int rnad_device_sm_count(void);
+
+/* ------------------------------------------------------------------------
+ * Packed node tables (replaces the 5 per-node tensors of tree.py:125-140 as
+ * kernel input; built once per tree by Tree.packed()).
+ *
+ *   ev_tab : S x ev_stride 32-bit words.  words [0, A*A) = expected_value[s,0,r,c]
+ *            (f32, row-major), word A*A = rows | cols << 8 where the legal mask
+ *            of node s is the prefix rectangle r < rows, c < cols (tree.py:133).
+ *   tr_tab : S x A*A x tr_stride words, entry (s, r, c) =
+ *            [chance[s,0..C-1,r,c] f32 | index[s,0..C-1,r,c] as int32 | value[s,0..C-1,r,c] f32 | pad]
+ *   ev_stride = round_up(A*A + 1, 4), tr_stride = round_up(3*C, 4)  (16-byte rows).
+ * ------------------------------------------------------------------------ */
+RNAD_API int rnad_packed_strides(int A, int C, int* ev_stride, int* tr_stride);
+
+/* index (S,C,A,A) i64, value/chance (S,C,A,A) f32, expected_value/legal (S,1,A,A) f32.
+ * bad_flag (device int32, caller zeroes it): set to 1 if some legal mask is not a prefix
+ * rectangle, 2 if a child id does not fit int32 or is out of [0,S). */
+RNAD_API int rnad_tree_pack(const int64_t* index, const float* value, const float* chance,
+                   const float* expected_value, const float* legal,
+                   int64_t S, int C, int A,
+                   uint32_t* ev_tab, uint32_t* tr_tab, int32_t* bad_flag, void* stream);
+
+/* ------------------------------------------------------------------------
+ * K1a  States.observations (episode.py:46-68): obs (B,2,A,A) f32 for the side
+ * to move (`turn` 0 = row, 1 = column; all games share it, episode.py:96-98)
+ * and the mover's legal-action mask obs[:,1,:,0] (B,A) f32 (may be NULL).
+ * ------------------------------------------------------------------------ */
+RNAD_API int rnad_observe(const uint32_t* ev_tab, int A, const int32_t* idx, int turn, int64_t B,
+                 float* obs, float* mask, void* stream);
+
+/* ------------------------------------------------------------------------
+ * K1b  the transition half of States.step (episode.py:102-124).
+ * idx (B) int32 in/out; row_actions/col_actions (B) int64 in [0,A).
+ * Chance draw: inverse CDF of chance[s,:,r,c] at u, u = u_chance[b] if
+ * u_chance != NULL else Philox4x32-10(key=seed, ctr=(game_offset+b, t, 0)) word 1.
+ * reward (B) f32 = value[s,k,r,c] * (s' == 0).  alive (device int32, caller
+ * zeroes): incremented by the number of games with s' != 0 (episode.py:124).
+ * ------------------------------------------------------------------------ */
+RNAD_API int rnad_step(const uint32_t* tr_tab, int A, int C, int32_t* idx,
+              const int64_t* row_actions, const int64_t* col_actions,
+              const float* u_chance, uint64_t seed, int t, int64_t game_offset,
+              int64_t B, float* reward, int32_t* alive, void* stream);
+
+/* Categorical draw replacing torch.multinomial(p, 1) (net.py:49): p (B,N) f32,
+ * out (B) int64; u = u_in[b] if u_in != NULL else Philox word 0 of (seed, game, t). */
+RNAD_API int rnad_sample_categorical(const float* p, int64_t B, int N, const float* u_in,
+                            uint64_t seed, int t, int64_t game_offset, int64_t* out, void* stream);
+
+/* ------------------------------------------------------------------------
+ * K2  Episodes.generate (episode.py:175-230) fused with MLP.forward
+ * (net.py:37-51): B games from the root for exactly T half-moves.
+ * Weights are the reference nn.Linear tensors, fp32, row-major:
+ *   value_fc0.weight (W,2A^2) .bias (W) ; value_fc1.weight (1,W) .bias (1)
+ *   policy_fc0.weight (W,2A^2) .bias (W); policy_fc1.weight (A,W) .bias (A)
+ * uniforms: NULL, or (T,B,2) f32 with [..,0] the action and [..,1] the chance
+ * uniform (parity / replay mode).
+ * Outputs, all (T,B,...) contiguous, reference dtypes (episode.py:218-225):
+ *   indices i64, turns i64, observations f32 (T,B,2,A,A), policy f32 (T,B,A),
+ *   actions f32 one-hot (T,B,A), rewards f32, values f32, masks f32 (T,B,A).
+ * t_last (device int32, caller sets to -1): max over games of the last
+ * half-move at which the game was not yet on the absorbing node (= t_eff).
+ * ------------------------------------------------------------------------ */
+typedef struct rnad_mlp_weights {
+    const float* value_fc0_w; const float* value_fc0_b;
+    const float* value_fc1_w; const float* value_fc1_b;
+    const float* policy_fc0_w; const float* policy_fc0_b;
+    const float* policy_fc1_w; const float* policy_fc1_b;
+    int width;
+} rnad_mlp_weights;
+
+typedef struct rnad_trajectory {
+    int64_t* indices; int64_t* turns; float* observations; float* policy;
+    float* actions; float* rewards; float* values; float* masks;
+} rnad_trajectory;
+
+RNAD_API int rnad_rollout(const uint32_t* ev_tab, const uint32_t* tr_tab, int A, int C,
+                 const rnad_mlp_weights* w /* host struct of device pointers */,
+                 int64_t B, int T, uint64_t seed, int64_t game_offset, const float* uniforms,
+                 int precision, const rnad_trajectory* out /* host struct of device pointers */,
+                 int32_t* t_last, void* stream);
+
+/* 1 if the RNAD_PREC_TF32 engine serves this net shape (width == 256, 2 <= A <= 4), else 0 */
+RNAD_API int rnad_rollout_tc_supported(int A, int width);
+
+/* ------------------------------------------------------------------------
+ * K3  learn/vtrace.py + learn/rnad.py:368-425
+ * ------------------------------------------------------------------------ */
+
+/* vtrace.process_policy (vtrace.py:24-55) on n_rows = T*B rows of A entries. */
+RNAD_API int rnad_process_policy(const float* policy, const float* mask, int64_t n_rows, int A,
+                        int n_disc, float eps_threshold, float* out, void* stream);
+
+/* vtrace.v_trace for ONE player, reference signature (vtrace.py:207-352):
+ * v (T,B,1), valid (T,B) f32, player_id (T,B) i64, acting/merged policy and
+ * merged_log_policy / actions_oh (T,B,A), player_others (T,B,1), reward (T,B).
+ * Outputs v_target (T,B,1) f32, has_played (T,B) i64, learning_output (T,B,A). */
+RNAD_API int rnad_vtrace(const float* v, const float* valid, const int64_t* player_id,
+                const float* acting_policy, const float* merged_policy, const float* merged_log_policy,
+                const float* player_others, const float* actions_oh, const float* reward, int player,
+                float eta, float lambda_, float c, float rho, float gamma,
+                int T, int64_t B, int A,
+                float* v_target, int64_t* has_played, float* learning_output, void* stream);
+
+/* Fused learner targets: everything RNaD.__learn computes between the four
+ * forward_batch calls and loss.backward() (rnad.py:365-425), both players in
+ * one reverse pass over time, plus the analytic gradients of
+ *   loss = value_weight*loss_v + neurd_weight*loss_nerd
+ * with respect to the learner net's `logit` and `v` outputs.
+ * Inputs (T,B,...): indices i64 (valid = indices != 0), turns i64, mu = the
+ * acting policy, actions_oh, rewards (player 0's; player 1 gets the negation),
+ * masks, and from the nets: logit/pi/log_pi/v (learner), v_target_net
+ * (target), log_pi_reg, log_pi_reg_ (regularisation nets).
+ * Outputs: d_logit (T,B,A), d_v (T,B) required; the rest may be NULL:
+ * pi_processed (T,B,A), v_target[2] (T,B), has_played[2] (T,B) i64,
+ * learning_output[2] (T,B,A).  losses: device float[2] = {loss_v, loss_nerd};
+ * counts: device int32[2] = {N_0, N_1} (sum of has_played).
+ * workspace: device scratch of rnad_learner_targets_workspace(T,B) bytes. */
+typedef struct rnad_learner_io {
+    const int64_t* indices; const int64_t* turns; const float* mu; const float* actions_oh;
+    const float* rewards; const float* masks;
+    const float* logit; const float* pi; const float* log_pi; const float* v;
+    const float* v_target_net; const float* log_pi_reg; const float* log_pi_reg_;
+    float* d_logit; float* d_v;
+    float* pi_processed; float* v_target[2]; int64_t* has_played[2]; float* learning_output[2];
+    float* losses; int32_t* counts;
+    /* exact data-parallel normalisation (DP note i): if non-NULL, device int32[2]
+     * GLOBAL counts to divide by instead of the local ones (already all-reduced by the caller) */
+    const int32_t* global_counts;
+} rnad_learner_io;
+
+typedef struct rnad_learner_params {
+    float alpha, eta, lambda_, c, rho, gamma;
+    float eps_threshold; int n_disc;
+    float neurd_clip, beta;
+    float value_weight, neurd_weight;
+} rnad_learner_params;
+
+RNAD_API int64_t rnad_learner_targets_workspace(int T, int64_t B);
+/* phase 1 only: counts[p] = sum over (t,b) of (indices != 0 && turns == p) */
+RNAD_API int rnad_count_played(const int64_t* indices, const int64_t* turns, int T, int64_t B,
+                      int32_t* counts, void* stream);
+RNAD_API int rnad_learner_targets(const rnad_learner_io* io /* host struct */, const rnad_learner_params* p,
+                         int T, int64_t B, int A, void* workspace, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RNAD_B200_H */

@@ -1,0 +1,348 @@
+"""
+Batched self-play environment and rollout recorder - API mirror of the
+reference `environment/episode.py` (`States` :18-125, `Episodes` :131-290,
+`Buffer` :292-333) on top of the sm_100a kernels in csrc/ (C ABI:
+include/rnad_b200.h).
+
+What runs where
+  * `States.observations` -> rnad_observe, `States.step` -> rnad_step (K1);
+  * `Episodes.generate(net)` with an `nn.net.MLP` actor -> ONE launch of the
+    fused persistent rollout kernel rnad_rollout (K2): gathers, both layers of
+    the net, masked softmax, action and chance sampling and the direct
+    (T, B, ...) trajectory writes, with a single host read (t_eff) at the end
+    instead of the reference's two syncs per half-move (episode.py:96,124);
+  * any other actor (e.g. ConvNet) takes the step-by-step path: the same K1
+    kernels around `net.forward`, like the reference loop.
+
+Randomness: the reference samples with the unseeded global torch generator
+(`torch.multinomial`, episode.py:118, net.py:49).  Here every batch draws one
+64-bit seed from torch's default generator (so `torch.manual_seed` makes runs
+reproducible) and the kernels derive per-(game, half-move) uniforms from it
+with Philox4x32-10 and select by inverse CDF (oracle/rnad_oracle.py pins both).
+"""
+
+import ctypes
+import os
+import random
+import time
+from collections import deque
+
+import numpy
+import torch
+
+import _b200
+from environment.tree import Tree
+
+_game_offset_rank_stride = 1 << 40   # disjoint Philox game ids per data-parallel rank
+
+
+def _fresh_seed() -> int:
+    return int(torch.randint(0, 2 ** 62, (1,), dtype=torch.int64).item())
+
+
+def _rank() -> int:
+    import torch.distributed as dist
+
+    return dist.get_rank() if dist.is_available() and dist.is_initialized() else 0
+
+
+class States:
+    """A batch of games, all on the same half-move, each at some node of `tree`."""
+
+    def __init__(self, tree: Tree, batch_size, seed=None):
+        self.tree = tree
+        self.batch_size = batch_size
+        self._idx = torch.ones((batch_size,), dtype=torch.int32, device=tree.device)
+        self._moved = False          # reference: indices is int32 until the first transition, int64 after
+        self._turn = 0
+        self.row_actions = None
+        self.col_actions = None
+        self._alive = None           # device int32 counter written by the last transition
+        self._terminal = False
+        self._t = 0
+        self.seed = _fresh_seed() if seed is None else int(seed)
+        self.game_offset = _rank() * _game_offset_rank_stride
+
+    # -- reference attributes ------------------------------------------------
+    @property
+    def indices(self) -> torch.Tensor:
+        return self._idx.long() if self._moved else self._idx
+
+    @indices.setter
+    def indices(self, value: torch.Tensor):
+        self._idx = value.to(device=self.tree.device, dtype=torch.int32).contiguous()
+        self._alive = None
+        self._terminal = bool(torch.all(self._idx == 0).item())
+
+    @property
+    def player_to_move(self) -> torch.Tensor:
+        return torch.full((self.batch_size,), self._turn, dtype=torch.long, device=self.tree.device)
+
+    @property
+    def terminal(self) -> bool:
+        """True when every game sits on the absorbing node (episode.py:124); syncs only when read."""
+        if self._alive is not None:
+            self._terminal = int(self._alive.item()) == 0
+            self._alive = None
+        return self._terminal
+
+    # -- reference methods ---------------------------------------------------
+    def observations(self) -> torch.Tensor:
+        """(B, 2, A, A): expected-payoff matrix and legal mask from the mover's side (episode.py:46-68)."""
+        obs, _ = self._observe(want_mask=False)
+        return obs
+
+    def _observe(self, want_mask=True):
+        packed = self.tree.packed()
+        a = packed.A
+        with _b200.device_guard(self._idx):
+            obs = torch.empty((self.batch_size, 2, a, a), dtype=torch.float32, device=self._idx.device)
+            mask = torch.empty((self.batch_size, a), dtype=torch.float32, device=self._idx.device) if want_mask else None
+            _b200.lib().rnad_observe(_b200.ptr(packed.ev_tab), a, _b200.ptr(self._idx, torch.int32), self._turn,
+                                     self.batch_size, _b200.ptr(obs), _b200.ptr(mask), _b200.stream())
+        return obs, mask
+
+    def observations_noisy(self) -> torch.Tensor:
+        """Placeholder in the reference too (episode.py:70-82)."""
+        return None
+
+    def step(self, actions: torch.Tensor, u_chance: torch.Tensor = None) -> torch.Tensor:
+        """
+        Commits the mover's actions (episode.py:84-125).  Row half-move: nothing
+        moves, reward 0.  Column half-move: chance is drawn, every game moves to
+        its child node, and games that reach the absorbing node get their payoff.
+        `u_chance` (B,) optionally injects the chance uniforms (parity tests).
+        """
+        dev = self._idx.device
+        actions = actions.to(device=dev, dtype=torch.long).reshape(self.batch_size).contiguous()
+        if self._turn == 0:
+            self.row_actions = actions
+            self._turn = 1
+            rewards = torch.zeros((self.batch_size,), device=dev)
+        else:
+            self.col_actions = actions
+            self._turn = 0
+            packed = self.tree.packed()
+            with _b200.device_guard(self._idx):
+                rewards = torch.empty((self.batch_size,), dtype=torch.float32, device=dev)
+                alive = torch.zeros(1, dtype=torch.int32, device=dev)
+                if u_chance is not None:
+                    u_chance = u_chance.to(device=dev, dtype=torch.float32).contiguous()
+                _b200.lib().rnad_step(_b200.ptr(packed.tr_tab), packed.A, packed.C, _b200.ptr(self._idx, torch.int32),
+                                      _b200.ptr(self.row_actions, torch.int64), _b200.ptr(self.col_actions, torch.int64),
+                                      _b200.ptr(u_chance), self.seed, self._t, self.game_offset, self.batch_size,
+                                      _b200.ptr(rewards), _b200.ptr(alive), _b200.stream())
+            self._alive = alive
+            self._moved = True
+            self.row_actions = None
+            self.col_actions = None
+        self._t += 1
+        return rewards
+
+
+class Episodes:
+    """A batch of rollout trajectories from the root; tensors are time-major (T, B, ...)."""
+
+    TENSOR_KEYS = ("turns", "indices", "observations", "policy", "actions", "rewards", "values", "masks",
+                   "q_estimates", "v_estimates")
+
+    def __init__(self, tree: Tree, batch_size):
+        self.tree: Tree = tree
+        self.batch_size: int = batch_size
+        self.states: States = States(tree, batch_size)
+        self.finished: bool = False
+        self.generation_time: float = 0
+        self.estimation_time: float = 0
+
+        self.t_eff: int = -1
+        self.turns: torch.Tensor = None
+        self.indices: torch.Tensor = None
+        self.observations: torch.Tensor = None
+        self.policy: torch.Tensor = None
+        self.actions: torch.Tensor = None
+        self.rewards: torch.Tensor = None
+        self.values: torch.Tensor = None
+        self.masks: torch.Tensor = None
+
+        self.q_estimates: torch.Tensor = None
+        self.v_estimates: torch.Tensor = None
+
+    # ----------------------------------------------------------------- rollout
+
+    def generate(self, net: torch.nn.Module, precision: str = None, uniforms: torch.Tensor = None):
+        """
+        Plays the batch to the end with `net` as the actor (episode.py:175-230).
+        precision: "tf32" (tcgen05 tensor cores) | "fp32" (CUDA cores) | None = the
+        net's `rollout_precision`, else $RNAD_ROLLOUT_PRECISION, else tf32 where the
+        tensor-core engine supports the net shape.  uniforms: optional (T, B, 2)
+        injected action / chance uniforms (parity tests).
+        """
+        from nn.net import MLP
+
+        net.eval()
+        time_start = time.perf_counter()
+        if type(net) is MLP:
+            self._generate_fused(net, precision, uniforms)
+        else:
+            self._generate_stepwise(net)
+        self.generation_time = time.perf_counter() - time_start
+        self.finished = True
+        net.train()
+
+    def _generate_fused(self, net, precision, uniforms):
+        L = _b200.lib()
+        packed = self.tree.packed()
+        a, b, dev = packed.A, self.batch_size, packed.device
+        if net.max_actions != a:
+            raise _b200.RnadError(f"net.max_actions {net.max_actions} != tree.max_actions {a}")
+        if precision is None:
+            precision = getattr(net, "rollout_precision", None) or os.environ.get("RNAD_ROLLOUT_PRECISION")
+        if precision is None:
+            precision = "tf32" if L.rnad_rollout_tc_supported(a, net.width) else "fp32"
+        t_max = packed.max_half_moves
+        w = _b200.MlpWeights()
+        params = {}
+        for layer in ("value_fc0", "value_fc1", "policy_fc0", "policy_fc1"):
+            lin = getattr(net, layer)
+            for suffix, tensor in (("w", lin.weight), ("b", lin.bias)):
+                tensor = tensor.detach()
+                if tensor.dtype != torch.float32 or tensor.device != dev:
+                    raise _b200.RnadError(f"{layer}: the fused rollout needs fp32 weights on {dev}")
+                params[f"{layer}_{suffix}"] = tensor.contiguous()
+                setattr(w, f"{layer}_{suffix}", params[f"{layer}_{suffix}"].data_ptr())
+        w.width = net.width
+
+        with torch.cuda.device(dev):
+            out = {
+                "indices": torch.empty((t_max, b), dtype=torch.int64, device=dev),
+                "turns": torch.empty((t_max, b), dtype=torch.int64, device=dev),
+                "observations": torch.empty((t_max, b, 2, a, a), dtype=torch.float32, device=dev),
+                "policy": torch.empty((t_max, b, a), dtype=torch.float32, device=dev),
+                "actions": torch.empty((t_max, b, a), dtype=torch.float32, device=dev),
+                "rewards": torch.empty((t_max, b), dtype=torch.float32, device=dev),
+                "values": torch.empty((t_max, b), dtype=torch.float32, device=dev),
+                "masks": torch.empty((t_max, b, a), dtype=torch.float32, device=dev),
+            }
+            traj = _b200.Trajectory(**{k: v.data_ptr() for k, v in out.items()})
+            t_last = torch.full((1,), -1, dtype=torch.int32, device=dev)
+            if uniforms is not None:
+                uniforms = uniforms.to(device=dev, dtype=torch.float32).contiguous()
+                if uniforms.shape[0] < t_max or tuple(uniforms.shape[1:]) != (b, 2):
+                    raise _b200.RnadError(f"uniforms must be ({t_max}+, {b}, 2), got {tuple(uniforms.shape)}")
+                uniforms = uniforms[:t_max].contiguous()
+            L.rnad_rollout(_b200.ptr(packed.ev_tab), _b200.ptr(packed.tr_tab), a, packed.C, ctypes.byref(w), b, t_max,
+                           self.states.seed, self.states.game_offset, _b200.ptr(uniforms),
+                           _b200.PRECISIONS[precision], ctypes.byref(traj), _b200.ptr(t_last), _b200.stream())
+            self.t_eff = int(t_last.item())          # the rollout's only host synchronisation
+        self.precision = precision
+        n = self.t_eff + 1
+        for key, value in out.items():
+            setattr(self, key, value[:n])
+        self.q_estimates = torch.zeros_like(self.policy)
+        self.v_estimates = torch.zeros_like(self.rewards)
+        self.states._idx.zero_()
+        self.states._moved = True
+        self.states._terminal = True
+
+    def _generate_stepwise(self, net):
+        """Reference loop (episode.py:194-227) for actors the fused kernel does not cover."""
+        rec = {k: [] for k in ("values", "indices", "turns", "observations", "policy", "actions", "rewards", "masks")}
+        arange = torch.arange(self.batch_size, device=self.tree.device)
+        while not self.states.terminal:
+            rec["indices"].append(self.states.indices.clone().long())
+            rec["turns"].append(self.states.player_to_move)
+            observations, mask = self.states._observe()
+            with torch.no_grad():
+                logits, policy, value, actions = net.forward(observations)
+            rewards = self.states.step(actions)
+            actions_oh = torch.zeros_like(policy)
+            actions_oh[arange, actions] = 1
+            rec["observations"].append(observations)
+            rec["values"].append(value.reshape(self.batch_size).detach().clone())
+            rec["masks"].append(mask)
+            rec["policy"].append(policy)
+            rec["actions"].append(actions_oh)
+            rec["rewards"].append(rewards)
+            self.t_eff += 1
+        for key, lst in rec.items():
+            setattr(self, key, torch.stack(lst, dim=0))
+        self.q_estimates = torch.zeros_like(self.policy)
+        self.v_estimates = torch.zeros_like(self.rewards)
+
+    # -------------------------------------------------------------- containers
+
+    def __repr__(self):
+        lines = []
+        for key, value in self.__dict__.items():
+            if torch.is_tensor(value) and torch.numel(value) > 20:
+                value = value.shape
+            lines.append(f"{key}: {value}\n")
+        return "".join(lines)
+
+    def _tensor_items(self):
+        return [(k, v) for k, v in self.__dict__.items() if torch.is_tensor(v)]
+
+    def sample(self, batch_size):
+        """A uniformly random subset (without replacement) of the batch dimension (episode.py:243-256)."""
+        assert self.finished
+        batch_size = min(batch_size, self.batch_size)
+        selected = torch.tensor(random.sample(range(self.batch_size), batch_size), dtype=torch.long,
+                                device=self.tree.device)
+        result = Episodes(self.tree, batch_size)
+        for key, value in self._tensor_items():
+            result.__dict__[key] = torch.index_select(value, dim=1, index=selected)
+        result.finished = True
+        result.t_eff = self.t_eff
+        return result
+
+    @classmethod
+    def collate(cls, lst: list):
+        """Zero-pads every member along time to the longest and concatenates along batch (episode.py:258-290)."""
+        t_eff = max(e.t_eff for e in lst)
+        tree = lst[0].tree
+        batch_size = sum(e.batch_size for e in lst)
+        assert all(e.tree == tree for e in lst)
+        assert all(e.finished for e in lst)
+        result = Episodes(tree, batch_size)
+        for key, _ in lst[0]._tensor_items():
+            padded = []
+            for e in lst:
+                x = e.__dict__[key]
+                extra = t_eff - e.t_eff
+                if extra:
+                    x = torch.cat([x, x.new_zeros((extra,) + tuple(x.shape[1:]))], dim=0)
+                padded.append(x)
+            result.__dict__[key] = padded[0] if len(padded) == 1 else torch.cat(padded, dim=1)
+        result.finished = True
+        result.t_eff = t_eff
+        return result
+
+
+class Buffer:
+    """
+    Replay buffer of `Episodes` batches played by older actors (episode.py:292-333).
+    With the default `max_size == 1` training is on-policy; then `sample(B)` of the
+    single stored batch of size B returns that batch itself (the reference returns
+    a random permutation of it - every consumer is a sum over the batch, so the
+    ~all-bytes-once-more permutation copy is skipped).
+    """
+
+    def __init__(self, max_size) -> None:
+        self.max_size = max_size
+        self.episodes_buffer = deque(maxlen=max_size)
+
+    def sample(self, batch_size):
+        n = len(self.episodes_buffer)
+        if n == 1 and self.episodes_buffer[0].batch_size == batch_size and self.episodes_buffer[0].finished:
+            return self.episodes_buffer[0]
+        bucket_sizes = numpy.random.multinomial(batch_size, [1 / n] * n)
+        assert sum(bucket_sizes) == batch_size
+        return Episodes.collate([self.episodes_buffer[i].sample(int(bucket_sizes[i])) for i in range(n)])
+
+    def append(self, episodes: Episodes):
+        self.episodes_buffer.append(episodes)
+        while len(self.episodes_buffer) > self.max_size:
+            self.episodes_buffer.popleft()
+
+    def clear(self):
+        self.episodes_buffer.clear()

@@ -30,3 +30,44 @@ def close(a, b, rtol=1e-5, atol=1e-6):
     err = (a - b).abs()
     bound = atol + rtol * b.abs()
     assert bool((err <= bound).all()), f"max err {err.max().item():.3e} (worst excess {(err - bound).max().item():.3e})"
+
+
+def tree_from_golden(g, device="cpu"):
+    """An `environment.tree.Tree` holding the golden fixture's tables (no generation)."""
+    from environment.tree import Tree
+
+    a, c = int(g["meta"][0]), int(g["meta"][1])
+    tree = Tree(max_actions=a, max_transitions=c)
+    tree.index_tensor = t(g["tree.index"])
+    tree.value_tensor = t(g["tree.value"])
+    tree.chance_tensor = t(g["tree.chance"])
+    tree.expected_value_tensor = t(g["tree.expected_value"])
+    tree.legal_tensor = t(g["tree.legal"])
+    tree.root_value_tensor = t(g["tree.root_value"])
+    tree.solution_tensor = t(g["tree.solution"])
+    tree.hash = 1234
+    tree.to(torch.device(device))
+    return tree
+
+
+def mlp_from_golden(g, prefix, device="cpu"):
+    from nn.net import MLP
+
+    a, width = int(g["meta"][0]), int(g["meta"][3])
+    net = MLP(a, width, device=torch.device(device))
+    net.load_state_dict({k: v.to(device) for k, v in weights_of(g, prefix).items()})
+    return net
+
+
+def episodes_from_golden(g, tree, device="cpu"):
+    from environment.episode import Episodes
+
+    ep_t = episodes_of(g)
+    ep = Episodes(tree, ep_t["indices"].shape[1])
+    for k, v in ep_t.items():
+        setattr(ep, k, v.to(device))
+    ep.t_eff = int(g["ep.t_eff"])
+    ep.finished = True
+    ep.q_estimates = torch.zeros_like(ep.policy)
+    ep.v_estimates = torch.zeros_like(ep.rewards)
+    return ep

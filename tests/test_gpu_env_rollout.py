@@ -1,0 +1,328 @@
+"""
+GPU parity tests of K1 (observe / step / sample) and K2 (fused rollout), through
+the Python API mirror -> ctypes -> C ABI -> sm_100a kernels, against
+  (i) the golden vectors recorded from the unmodified reference, and
+ (ii) the CPU oracle (oracle/rnad_oracle.py) on seeded inputs.
+Integer / index / mask / reward results must be bit-exact.  Floats that pass
+through the net: fp32 engine rtol 1e-5 (+atol 1e-6); tf32 tensor-core engine
+atol 4e-3 on logits-scale quantities (10-bit mantissa inputs, K <= 33).
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import rnad_oracle as orc
+from helpers import close, episodes_of, mlp_from_golden, t, tables_of, tree_from_golden, weights_of
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def cpu(x):
+    return x.detach().cpu()
+
+
+# --------------------------------------------------------------------- K1
+
+def test_packed_tree_tables(golden):
+    _, g = golden
+    tree = tree_from_golden(g, DEV)
+    p = tree.packed()
+    a, c = p.A, p.C
+    ev = cpu(p.ev_tab).view(torch.float32)
+    assert torch.equal(ev[:, : a * a], t(g["tree.expected_value"]).reshape(-1, a * a))
+    dims = cpu(p.ev_tab)[:, a * a]
+    legal = t(g["tree.legal"])[:, 0]
+    assert torch.equal(dims & 0xFF, (legal[:, :, 0] != 0).sum(-1).int())
+    assert torch.equal((dims >> 8) & 0xFF, (legal[:, 0, :] != 0).sum(-1).int())
+    tr = cpu(p.tr_tab)                                         # (S, A*A, stride)
+    chance = t(g["tree.chance"]).permute(0, 2, 3, 1).reshape(-1, a * a, c)
+    index = t(g["tree.index"]).permute(0, 2, 3, 1).reshape(-1, a * a, c)
+    value = t(g["tree.value"]).permute(0, 2, 3, 1).reshape(-1, a * a, c)
+    assert torch.equal(tr[:, :, :c].contiguous().view(torch.float32), chance)
+    assert torch.equal(tr[:, :, c: 2 * c].long(), index)
+    assert torch.equal(tr[:, :, 2 * c: 3 * c].contiguous().view(torch.float32), value)
+    assert p.max_half_moves >= int(g["ep.t_eff"]) + 1
+
+
+def test_states_replay_matches_reference(golden):
+    """States.observations / States.step with the reference's actions and chance uniforms: bit-exact."""
+    from environment.episode import States
+
+    _, g = golden
+    tree = tree_from_golden(g, DEV)
+    idx_ref = t(g["states.indices"])
+    T, B = idx_ref.shape
+    actions = t(g["ep.actions"]).argmax(-1)
+    u = t(g["uniforms"])
+    states = States(tree, B)
+    assert states.indices.dtype == torch.int32
+    for s in range(T):
+        assert torch.equal(cpu(states.indices).long(), idx_ref[s])
+        assert torch.equal(cpu(states.player_to_move), torch.full((B,), s & 1))
+        obs, mask = states._observe()
+        assert torch.equal(cpu(obs), t(g["states.observations"][s]))
+        assert torch.equal(cpu(states.observations()), t(g["states.observations"][s]))
+        assert torch.equal(cpu(mask), t(g["ep.masks"][s]))
+        rew = states.step(actions[s].to(DEV), u_chance=u[s, :, 1].to(DEV))
+        assert torch.equal(cpu(rew), t(g["states.rewards"][s]))
+    assert torch.equal(cpu(states.indices), t(g["states.final_indices"]))
+    assert states.indices.dtype == torch.int64
+    assert states.terminal == bool((t(g["states.final_indices"]) == 0).all())
+
+
+def test_states_philox_chance_matches_oracle(golden):
+    from environment.episode import States
+
+    _, g = golden
+    tree = tree_from_golden(g, DEV)
+    tab = tables_of(g)
+    B = 257
+    states = States(tree, B, seed=99)
+    gen = torch.Generator().manual_seed(5)
+    idx = torch.ones(B, dtype=torch.int64)
+    for s in range(6):
+        obs = orc.observe(tab["expected_value"], tab["legal"], idx, s & 1)
+        n_legal = orc.mover_mask(obs).sum(-1).long()
+        act = (torch.rand(B, generator=gen) * n_legal).long().clamp_max(tree.max_actions - 1)
+        if s & 1:
+            _, uc = orc.philox_uniforms(99, s, np.arange(B))
+            idx, rew, _ = orc.step(tab["index"], tab["value"], tab["chance"], idx, row, act, torch.from_numpy(uc))
+        else:
+            row, rew = act, torch.zeros(B)
+        got = states.step(act.to(DEV))
+        assert torch.equal(cpu(got), rew)
+        assert torch.equal(cpu(states.indices).long(), idx)
+
+
+def test_sample_categorical_matches_oracle():
+    from nn.net import sample_actions
+
+    gen = torch.Generator().manual_seed(0)
+    for n in (2, 3, 4, 7):
+        p = torch.rand(5000, n, generator=gen)
+        p[torch.rand(5000, n, generator=gen) < 0.3] = 0
+        p[:, 0] += (p.sum(-1) == 0).float()
+        p = p / p.sum(-1, keepdim=True)
+        u = torch.rand(5000, generator=gen)
+        u[:10] = 0.0
+        u[10:20] = 0.99999994
+        assert torch.equal(cpu(sample_actions(p.to(DEV), u.to(DEV))), orc.sample_icdf(p, u))
+
+
+def test_mlp_forward_matches_reference(golden):
+    _, g = golden
+    net = mlp_from_golden(g, "net", DEV)
+    for s in (0, 1):
+        obs = t(g["ep.observations"][s]).to(DEV)
+        with torch.no_grad():
+            logits, policy, value, actions = net.forward(obs, u=t(g["uniforms"][s, :, 0]).to(DEV))
+        close(cpu(logits), g[f"fwd{s}.logits"], atol=2e-6)
+        close(cpu(policy), g[f"fwd{s}.policy"], atol=2e-6)
+        close(cpu(value), g[f"fwd{s}.value"], atol=2e-6)
+        want = orc.sample_icdf(cpu(policy), t(g["uniforms"][s, :, 0]))
+        assert torch.equal(cpu(actions), want)
+
+
+# --------------------------------------------------------------------- K2
+
+TOL = {"fp32": dict(rtol=1e-5, atol=2e-6), "tf32": dict(rtol=0, atol=4e-3)}
+
+
+def check_rollout_against_oracle(ep, tables, w, seed=None, uniforms=None, game_offset=0, tol=None):
+    """
+    Replays a GPU trajectory on the CPU oracle, half-move by half-move: every gather,
+    mask and reward must be bit-exact, the net outputs within `tol`, and every sampled
+    action / chance outcome must be exactly the inverse-CDF choice at the same uniform
+    (for actions: of the policy the kernel itself recorded).
+    """
+    T = ep.t_eff + 1
+    B = ep.batch_size
+    A = tables["legal"].shape[-1]
+    idx = torch.ones(B, dtype=torch.int64)
+    row = None
+    games = np.arange(game_offset, game_offset + B)
+    assert ep.indices.dtype == torch.int64 and ep.turns.dtype == torch.int64
+    assert tuple(ep.observations.shape) == (T, B, 2, A, A)
+    for s in range(T):
+        turn = s & 1
+        assert torch.equal(cpu(ep.indices[s]), idx), f"node ids diverge at half-move {s}"
+        assert torch.equal(cpu(ep.turns[s]), torch.full((B,), turn))
+        obs = orc.observe(tables["expected_value"], tables["legal"], idx, turn)
+        assert torch.equal(cpu(ep.observations[s]), obs)
+        assert torch.equal(cpu(ep.masks[s]), orc.mover_mask(obs))
+        logits, policy, value, _ = orc.mlp_forward(w, obs.reshape(B, -1))
+        close(cpu(ep.policy[s]), policy, **tol)
+        close(cpu(ep.values[s]), value[:, 0], **tol)
+        pol_gpu = cpu(ep.policy[s])
+        assert bool((pol_gpu[orc.mover_mask(obs) == 0] == 0).all())
+        close(pol_gpu.sum(-1), torch.ones(B), rtol=0, atol=1e-6)
+        if uniforms is not None:
+            ua, uc = uniforms[s, :, 0], uniforms[s, :, 1]
+        else:
+            ua, uc = (torch.from_numpy(x) for x in orc.philox_uniforms(seed, s, games))
+        act = orc.sample_icdf(pol_gpu, ua)
+        assert torch.equal(cpu(ep.actions[s]).argmax(-1), act)
+        assert torch.equal(cpu(ep.actions[s]), torch.nn.functional.one_hot(act, A).float())
+        if turn == 0:
+            row = act
+            assert float(cpu(ep.rewards[s]).abs().sum()) == 0.0
+        else:
+            idx, rew, _ = orc.step(tables["index"], tables["value"], tables["chance"], idx, row, act, uc)
+            assert torch.equal(cpu(ep.rewards[s]), rew)
+    assert bool((idx == 0).all()), "rollout stopped before every game was terminal"
+    if T > 0:
+        assert bool((cpu(ep.indices[T - 1]) != 0).any()), "t_eff overshoots the last live half-move"
+
+
+def test_fused_rollout_fp32_reproduces_reference_episodes(golden):
+    """Same tree, weights and uniforms as the reference run -> the same Episodes (fp32 engine)."""
+    from environment.episode import Episodes
+
+    _, g = golden
+    tree = tree_from_golden(g, DEV)
+    net = mlp_from_golden(g, "net", DEV)
+    ref = episodes_of(g)
+    B = ref["indices"].shape[1]
+    ep = Episodes(tree, B)
+    ep.generate(net, precision="fp32", uniforms=t(g["uniforms"]).to(DEV))
+    assert ep.t_eff == int(g["ep.t_eff"]) and ep.finished
+    assert torch.equal(cpu(ep.actions), ref["actions"]), "a sampled action differs from the reference under equal uniforms"
+    for key in ("indices", "turns", "rewards", "masks", "observations"):
+        assert torch.equal(cpu(getattr(ep, key)), ref[key]), key
+    close(cpu(ep.policy), ref["policy"], rtol=1e-5, atol=2e-6)
+    close(cpu(ep.values), ref["values"], rtol=1e-5, atol=2e-6)
+    assert float(cpu(ep.q_estimates).abs().sum()) == 0 and ep.q_estimates.shape == ep.policy.shape
+    assert ep.v_estimates.shape == ep.rewards.shape
+
+
+@pytest.mark.parametrize("batch", [1, 127, 640, 5000])
+def test_fused_rollout_fp32_philox_vs_oracle(golden, batch):
+    from environment.episode import Episodes
+
+    _, g = golden
+    tree = tree_from_golden(g, DEV)
+    net = mlp_from_golden(g, "net", DEV)
+    torch.manual_seed(batch)
+    ep = Episodes(tree, batch)
+    ep.generate(net, precision="fp32")
+    check_rollout_against_oracle(ep, tables_of(g), weights_of(g, "net"), seed=ep.states.seed, tol=TOL["fp32"])
+
+
+def wide_net(a, seed, device):
+    from nn.net import MLP
+
+    torch.manual_seed(seed)
+    net = MLP(a, 256)
+    with torch.no_grad():
+        for p in net.parameters():       # larger weights than the default init: a harder numerical case
+            p.mul_(2.0)
+    w = {k: v.detach().clone() for k, v in net.state_dict().items()}
+    return net.to(device), w
+
+
+@pytest.mark.parametrize("precision", ["fp32", "tf32"])
+@pytest.mark.parametrize("batch", [96, 128, 1000, 20000])
+def test_fused_rollout_width256_vs_oracle(golden, precision, batch):
+    """The tensor-core engine (and the fp32 engine on the same nets): width 256, A in 2..4, ragged and regular trees."""
+    from environment.episode import Episodes
+
+    name, g = golden
+    tree = tree_from_golden(g, DEV)
+    net, w = wide_net(tree.max_actions, 7, DEV)
+    net.device = torch.device(DEV)
+    torch.manual_seed(batch + 1)
+    ep = Episodes(tree, batch)
+    ep.generate(net, precision=precision)
+    assert ep.precision == precision
+    check_rollout_against_oracle(ep, tables_of(g), w, seed=ep.states.seed, tol=TOL[precision])
+
+
+def test_default_precision_is_tensor_core_when_supported(golden):
+    from environment.episode import Episodes
+
+    _, g = golden
+    tree = tree_from_golden(g, DEV)
+    net, _ = wide_net(tree.max_actions, 3, DEV)
+    ep = Episodes(tree, 256)
+    ep.generate(net)
+    assert ep.precision == "tf32"
+    small = mlp_from_golden(g, "net", DEV)
+    ep = Episodes(tree, 256)
+    ep.generate(small)
+    assert ep.precision == ("tf32" if small.width == 256 else "fp32")
+
+
+def test_rollout_statistics_follow_policy_and_chance(golden):
+    """Chi-square style check at the root: action and chance frequencies match policy and chance_tensor."""
+    from environment.episode import Episodes
+
+    name, g = golden
+    tree = tree_from_golden(g, DEV)
+    net, w = wide_net(tree.max_actions, 11, DEV)
+    B = 200_000
+    ep = Episodes(tree, B)
+    ep.generate(net, precision="tf32")
+    A = tree.max_actions
+    for s in (0, 1):
+        freq = cpu(ep.actions[s]).mean(0)
+        pol = cpu(ep.policy[s])[0]
+        assert torch.allclose(freq, pol, atol=5 * (0.25 / B) ** 0.5 + 1e-4), (freq, pol)
+    row = cpu(ep.actions[0]).argmax(-1)
+    col = cpu(ep.actions[1]).argmax(-1)
+    nxt = cpu(ep.indices[2]) if ep.t_eff >= 2 else None
+    if nxt is not None:
+        chance = t(g["tree.chance"])[1]
+        index = t(g["tree.index"])[1]
+        sel = (row == 0) & (col == 0)
+        n = int(sel.sum())
+        for k in range(chance.shape[0]):
+            if index[k, 0, 0] != 0 and n > 1000:
+                got = float((nxt[sel] == index[k, 0, 0]).float().mean())
+                assert abs(got - float(chance[k, 0, 0])) < 5 * (0.25 / n) ** 0.5 + 1e-3
+
+
+def test_stepwise_path_with_other_actor(golden):
+    """Actors the fused kernel does not cover (ConvNet) run the reference-style loop on the K1 kernels."""
+    from environment.episode import Episodes
+    from nn.net import ConvNet
+
+    _, g = golden
+    tree = tree_from_golden(g, DEV)
+    torch.manual_seed(0)
+    net = ConvNet(tree.max_actions, channels=4, depth=1, batch_norm=False, device=torch.device(DEV))
+    ep = Episodes(tree, 64)
+    ep.generate(net)
+    T = ep.t_eff + 1
+    tab = tables_of(g)
+    idx = torch.ones(64, dtype=torch.int64)
+    assert ep.indices.shape == (T, 64) and bool((cpu(ep.indices[0]) == 1).all())
+    for s in range(T):
+        obs = orc.observe(tab["expected_value"], tab["legal"], cpu(ep.indices[s]), s & 1)
+        assert torch.equal(cpu(ep.observations[s]), obs)
+        assert torch.equal(cpu(ep.masks[s]), orc.mover_mask(obs))
+    assert ep.finished and ep.states.terminal
+
+
+def test_buffer_and_collate(golden):
+    from environment.episode import Buffer, Episodes
+
+    _, g = golden
+    tree = tree_from_golden(g, DEV)
+    net = mlp_from_golden(g, "net", DEV)
+    buf = Buffer(2)
+    eps = []
+    for _ in range(2):
+        ep = Episodes(tree, 64)
+        ep.generate(net, precision="fp32")
+        buf.append(ep)
+        eps.append(ep)
+    sample = buf.sample(48)
+    assert sample.batch_size == 48 and sample.t_eff == max(e.t_eff for e in eps)
+    assert sample.indices.shape == (sample.t_eff + 1, 48)
+    assert sample.observations.shape[1] == 48
+    one = Buffer(1)
+    one.append(eps[0])
+    assert one.sample(64) is eps[0]
+    sub = eps[0].sample(10)
+    assert sub.policy.shape == (eps[0].t_eff + 1, 10, tree.max_actions)

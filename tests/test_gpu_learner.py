@@ -1,0 +1,246 @@
+"""
+GPU parity tests of K3 (process_policy, v-trace, fused learner targets) and of the
+learner step built on it, against the golden vectors recorded from the unmodified
+reference and against the CPU oracle on larger seeded inputs.
+Bars: process_policy and has_played bit-exact; v-trace / NeuRD floats rtol 1e-5
+(north_star), gradients additionally atol 1e-7 (they are O(1/N) small).
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import rnad_oracle as orc
+from helpers import close, episodes_from_golden, episodes_of, mlp_from_golden, t, tree_from_golden, weights_of
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def cpu(x):
+    return x.detach().cpu()
+
+
+def dev(x):
+    return t(x).to(DEV) if isinstance(x, np.ndarray) else x.to(DEV)
+
+
+def test_process_policy_matches_reference(golden):
+    import learn.vtrace as vtrace
+
+    _, g = golden
+    out = vtrace.process_policy(dev(g["fb.pi"]), dev(g["ep.masks"]), 32, 0.03)
+    assert torch.equal(cpu(out), t(g["pi_processed"]))
+
+
+@pytest.mark.parametrize("a", [2, 3, 4, 5])
+def test_process_policy_random_vs_oracle(a):
+    import learn.vtrace as vtrace
+
+    gen = torch.Generator().manual_seed(a)
+    T, B = 6, 4000
+    mask = (torch.rand(T, B, a, generator=gen) < 0.8).float()
+    mask[..., 0] = 1.0
+    p = torch.rand(T, B, a, generator=gen) ** 3 * mask
+    p = p / p.sum(-1, keepdim=True)
+    p[0, :50] = mask[0, :50] / mask[0, :50].sum(-1, keepdim=True)        # exact ties / uniform rows
+    for n_disc, eps in ((32, 0.03), (16, 0.1), (7, 0.0)):
+        want = orc.process_policy(p, mask, n_disc, eps)
+        got = cpu(vtrace.process_policy(p.to(DEV), mask.to(DEV), n_disc, eps))
+        assert torch.equal(got, want), f"{(got != want).any(-1).sum().item()} rows differ (A={a}, n={n_disc})"
+
+
+def test_v_trace_matches_reference(golden):
+    import learn.vtrace as vtrace
+
+    _, g = golden
+    ep = {k: v.to(DEV) for k, v in episodes_of(g).items()}
+    eta, gamma, c_bar, rho_bar, _ = (float(x) for x in g["scalars"])
+    valid = (ep["indices"] != 0).float()
+    for player in range(2):
+        reward = ep["rewards"] if player == 0 else -ep["rewards"]
+        vt, hp, lo = vtrace.v_trace(dev(g["v_target_net"]), valid, ep["turns"], ep["policy"], dev(g["pi_processed"]),
+                                    dev(g["log_policy_reg"]), vtrace._player_others(ep["turns"], valid, player),
+                                    ep["actions"], reward, player, eta=eta, lambda_=1.0, c=c_bar, rho=rho_bar,
+                                    gamma=gamma)
+        assert hp.dtype == torch.int64 and vt.shape == (*valid.shape, 1)
+        assert torch.equal(cpu(hp), t(g[f"vt{player}.has_played"]))
+        assert torch.equal(cpu(hp), cpu(vtrace._has_played(valid, ep["turns"], player)))
+        close(cpu(vt), g[f"vt{player}.v_target"], rtol=1e-5, atol=1e-6)
+        close(cpu(lo), g[f"vt{player}.learning_output"], rtol=1e-5, atol=1e-6)
+        exact = torch.equal(cpu(vt), t(g[f"vt{player}.v_target"])) and torch.equal(cpu(lo), t(g[f"vt{player}.learning_output"]))
+        print(f"v_trace player {player}: bit-exact={exact}")
+
+
+def test_learner_targets_match_reference(golden):
+    """The fused kernel against everything the reference computed from the same four nets' outputs."""
+    import learn.vtrace as vtrace
+
+    _, g = golden
+    tree = tree_from_golden(g, DEV)
+    ep = episodes_from_golden(g, tree, DEV)
+    eta, gamma, c_bar, rho_bar, alpha = (float(x) for x in g["scalars"])
+    # the regularisation nets' log-policies are not stored in the fixture: recompute them with the oracle
+    _, log_pi_reg, _, _ = orc.mlp_forward_batch(weights_of(g, "reg"), t(g["ep.observations"]))
+    _, log_pi_reg_, _, _ = orc.mlp_forward_batch(weights_of(g, "reg_"), t(g["ep.observations"]))
+    out = vtrace.learner_targets(ep, dev(g["fb.logit"]), dev(g["fb.pi"]), dev(g["fb.log_pi"]), dev(g["fb.v"]),
+                                 dev(g["v_target_net"]), log_pi_reg.to(DEV), log_pi_reg_.to(DEV), alpha=alpha, eta=eta,
+                                 c=c_bar, rho=rho_bar, gamma=gamma, neurd_clip=10 ** 3, beta=2, want_outputs=True)
+    assert torch.equal(cpu(out.pi_processed), t(g["pi_processed"]))
+    for p in range(2):
+        assert torch.equal(cpu(out.has_played[p]), t(g[f"vt{p}.has_played"]))
+        close(cpu(out.v_target[p]), g[f"vt{p}.v_target"], rtol=1e-5, atol=5e-6)
+        close(cpu(out.learning_output[p]), g[f"vt{p}.learning_output"], rtol=2e-5, atol=2e-5)
+    counts = cpu(out.counts).tolist()
+    assert counts == [int(g["vt0.has_played"].sum()), int(g["vt1.has_played"].sum())]
+    losses = cpu(out.losses)
+    close(losses[0], g["loss_v"], rtol=1e-5, atol=1e-6)
+    close(losses[1], g["loss_nerd"], rtol=1e-5, atol=2e-6)
+    close(cpu(out.d_logit), g["d_logit"], rtol=1e-5, atol=1e-7)
+    close(cpu(out.d_v).unsqueeze(-1), g["d_v"], rtol=1e-5, atol=1e-7)
+    assert torch.equal(cpu(vtrace.count_played(ep)), cpu(out.counts))
+
+
+def test_api_losses_match_reference(golden):
+    """get_loss_v / get_loss_nerd (API-compat torch expressions) and their autograd gradients on the GPU."""
+    import learn.vtrace as vtrace
+
+    _, g = golden
+    ep = {k: v.to(DEV) for k, v in episodes_of(g).items()}
+    valid = (ep["indices"] != 0).float()
+    logit = dev(g["fb.logit"]).requires_grad_()
+    v = dev(g["fb.v"]).requires_grad_()
+    vts = [dev(g[f"vt{p}.v_target"]) for p in range(2)]
+    hps = [dev(g[f"vt{p}.has_played"]) for p in range(2)]
+    qs = [dev(g[f"vt{p}.learning_output"]) for p in range(2)]
+    lv = vtrace.get_loss_v([v] * 2, vts, hps)
+    ones = torch.ones_like(valid).unsqueeze(-1)
+    ln = vtrace.get_loss_nerd([logit] * 2, [dev(g["pi_processed"])] * 2, qs, valid, ep["turns"], ep["masks"],
+                              [ones] * 2, clip=10 ** 3, threshold=2)
+    close(cpu(lv), g["loss_v"])
+    close(cpu(ln), g["loss_nerd"], atol=1e-6)
+    (lv + ln).backward()
+    close(cpu(logit.grad), g["d_logit"], atol=1e-7)
+    close(cpu(v.grad), g["d_v"], atol=1e-7)
+
+
+def test_rnad_learn_gradients_match_reference(golden):
+    """RNaD.__learn on the reference's episodes and nets gives the reference's parameter gradients."""
+    from learn.rnad import RNaD
+
+    name, g = golden
+    tree = tree_from_golden(g, DEV)
+    ep = episodes_from_golden(g, tree, DEV)
+    eta, gamma, c_bar, rho_bar, alpha = (float(x) for x in g["scalars"])
+    a, width = int(g["meta"][0]), int(g["meta"][3])
+    trial = RNaD(tree=tree, device=torch.device(DEV), directory_name=f"pytest_{name}", eta=eta,
+                 batch_size=ep.batch_size, vtrace_gamma=gamma, c_bar=c_bar, roh_bar=rho_bar,
+                 net_params={"type": "MLP", "max_actions": a, "width": width})
+    for attr, prefix in (("net", "learner"), ("net_target", "target"), ("net_reg", "reg"), ("net_reg_", "reg_")):
+        setattr(trial, attr, mlp_from_golden(g, prefix, DEV))
+    trial.net.train()
+    trial._RNaD__learn(ep, alpha)
+    for k, p in trial.net.named_parameters():
+        close(cpu(p.grad), g[f"rnad_grad.{k}"], rtol=2e-5, atol=2e-7)
+    losses = cpu(trial.last_losses)
+    close(losses[0], g["loss_v"], rtol=2e-5, atol=2e-6)
+    close(losses[1], g["loss_nerd"], rtol=2e-5, atol=4e-6)
+
+
+@pytest.mark.parametrize("a,T,B", [(2, 4, 3000), (3, 8, 10000), (4, 16, 2000), (5, 6, 1500)])
+def test_learner_targets_random_vs_oracle(a, T, B):
+    """Larger synthetic trajectories with ragged validity, off-policy ratios and non-trivial scalars."""
+    import learn.vtrace as vtrace
+
+    gen = torch.Generator().manual_seed(100 + a)
+    mask = (torch.rand(T, B, a, generator=gen) < 0.75).float()
+    mask[..., 0] = 1.0
+
+    def rand_policy():
+        p = (torch.rand(T, B, a, generator=gen) + 0.05) * mask
+        return p / p.sum(-1, keepdim=True)
+
+    length = torch.randint(1, T + 1, (B,), generator=gen)
+    indices = (torch.arange(T).view(T, 1) < length.view(1, B)).long() * torch.randint(1, 1000, (T, B), generator=gen)
+    turns = (torch.arange(T) % 2).view(T, 1).expand(T, B).contiguous()
+    mu, pi = rand_policy(), rand_policy()
+    logit = torch.randn(T, B, a, generator=gen) * 2
+    log_pi = torch.where(mask != 0, torch.log(pi.clamp_min(1e-30)), torch.zeros_like(pi))
+    log_pi_reg = torch.where(mask != 0, torch.log(rand_policy().clamp_min(1e-30)), torch.zeros_like(pi))
+    log_pi_reg_ = torch.where(mask != 0, torch.log(rand_policy().clamp_min(1e-30)), torch.zeros_like(pi))
+    act = torch.multinomial(mu.view(-1, a), 1, generator=gen).view(T, B)
+    actions = torch.nn.functional.one_hot(act, a).float()
+    last = (torch.arange(T).view(T, 1) == (length - 1).view(1, B)) & (turns == 1)
+    rewards = torch.where(last, torch.randint(0, 2, (T, B), generator=gen).float() * 2 - 1, torch.zeros(T, B))
+    v = torch.randn(T, B, 1, generator=gen) * 0.5
+    v_net = torch.randn(T, B, 1, generator=gen) * 0.5
+    alpha, eta, lam, c, rho, gamma, clip, beta = 0.4, 0.2, 1.0, 0.8, 0.9, 0.95, 0.7, 1.5
+
+    valid = (indices != 0).float()
+    pi_proc = orc.process_policy(pi, mask, 32, 0.03)
+    L = log_pi - (alpha * log_pi_reg + (1 - alpha) * log_pi_reg_)
+    vts, hps, qs = [], [], []
+    for p in range(2):
+        r = rewards if p == 0 else -rewards
+        vt, hp, lo = orc.v_trace(v_net, valid, turns, mu, pi_proc, L, actions, r, p, eta=eta, lambda_=lam, c=c,
+                                 rho=rho, gamma=gamma)
+        vts.append(vt), hps.append(hp), qs.append(lo)
+    logit_g = logit.clone().requires_grad_()
+    v_g = v.clone().requires_grad_()
+    lv = orc.loss_v(v_g, vts, hps)
+    ln = orc.loss_nerd(logit_g, pi_proc, qs, valid, turns, mask, clip, beta)
+    (2.0 * lv + 0.5 * ln).backward()
+
+    class Ep:
+        pass
+
+    ep = Ep()
+    ep.indices, ep.turns, ep.policy, ep.actions = indices.to(DEV), turns.to(DEV), mu.to(DEV), actions.to(DEV)
+    ep.rewards, ep.masks = rewards.to(DEV), mask.to(DEV)
+    out = vtrace.learner_targets(ep, logit.to(DEV), pi.to(DEV), log_pi.to(DEV), v.to(DEV), v_net.to(DEV),
+                                 log_pi_reg.to(DEV), log_pi_reg_.to(DEV), alpha=alpha, eta=eta, lambda_=lam, c=c,
+                                 rho=rho, gamma=gamma, neurd_clip=clip, beta=beta, value_weight=2.0, neurd_weight=0.5,
+                                 want_outputs=True)
+    assert torch.equal(cpu(out.pi_processed), pi_proc)
+    for p in range(2):
+        assert torch.equal(cpu(out.has_played[p]), hps[p])
+        close(cpu(out.v_target[p]), vts[p], rtol=1e-5, atol=1e-6)
+        close(cpu(out.learning_output[p]), qs[p], rtol=1e-5, atol=2e-6)
+    close(cpu(out.losses)[0], lv.detach(), rtol=1e-5, atol=1e-6)
+    close(cpu(out.losses)[1], ln.detach(), rtol=1e-5, atol=1e-6)
+    close(cpu(out.d_logit), logit_g.grad, rtol=1e-5, atol=1e-8)
+    close(cpu(out.d_v).unsqueeze(-1), v_g.grad, rtol=1e-5, atol=1e-8)
+    # without the optional outputs the gradients are the same
+    lean = vtrace.learner_targets(ep, logit.to(DEV), pi.to(DEV), log_pi.to(DEV), v.to(DEV), v_net.to(DEV),
+                                  log_pi_reg.to(DEV), log_pi_reg_.to(DEV), alpha=alpha, eta=eta, lambda_=lam, c=c,
+                                  rho=rho, gamma=gamma, neurd_clip=clip, beta=beta, value_weight=2.0, neurd_weight=0.5)
+    assert torch.equal(cpu(lean.d_logit), cpu(out.d_logit)) and torch.equal(cpu(lean.d_v), cpu(out.d_v))
+
+
+def test_rnad_short_run_reduces_exploitability():
+    """cfg1-sized end-to-end run on the GPU: NashConv of the target net falls well below the initial net's."""
+    import random
+
+    from environment.tree import Tree
+    from learn.rnad import RNaD
+    from util.metric import NashConvData
+
+    np.random.seed(6)
+    random.seed(6)
+    torch.manual_seed(6)
+    tree = Tree(max_actions=2, max_transitions=1, depth_bound=2)
+    tree.generate()
+    tree.to(torch.device(DEV))
+    trial = RNaD(tree=tree, device=torch.device(DEV), directory_name=f"pytest_cfg1_{np.random.randint(1 << 30)}",
+                 eta=0.2, bounds=[6], delta_m=[100], lr=1e-3, gamma_averaging=0.01, batch_size=256, logit_clip=2,
+                 net_params={"type": "MLP", "max_actions": 2, "width": 256})
+    trial._RNaD__initialize()
+    data = NashConvData(tree)
+    data.get_nashconv_from_net(tree, trial.net_target)
+    before = (data.row_best[1] + data.col_best[1]).item()
+    trial.run(checkpoint_mod=10 ** 6, expl_mod=1, log_mod=10 ** 6)
+    assert trial.total_steps == 600 and trial.m == 6
+    data = NashConvData(tree)
+    data.get_nashconv_from_net(tree, trial.net_target)
+    after = (data.row_best[1] + data.col_best[1]).item()
+    print(f"NashConv before {before:.4f} after 600 steps {after:.4f}; history {trial.nashconv_history}")
+    assert after < 0.5 * before and after < 0.2
