@@ -1,0 +1,440 @@
+#!/usr/bin/env python
+"""
+Benchmark of the R-NaD self-play hot path (BASELINE.json metric: self-play env
+steps/s, with learner updates/s alongside).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl native|reference] [--config cfg2]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A "step" is one pass of the fused rollout (K2, which contains the K1 gathers) over
+one batch of B games played from the root to the end: B * T env steps (one env step
+= one game advancing one half-move).  Prints ONE JSON line.
+
+native arm
+  value     device-timed (CUDA events on the launch stream, max over ranks) kernel
+            throughput with tree, weights and output buffers resident in HBM;
+  e2e       the same metric through the public API (`Episodes.generate`) with the
+            actor weights arriving from pinned HOST memory every step and the game
+            returns read back to the host, copies inside the timed region;
+  roofline  the rollout kernel against the measured HBM copy bandwidth, algorithmic
+            bytes per env step from SURVEY.md section 8d (gather reads + API-faithful
+            trajectory writes);
+  learner   one full learner update (rollout + 4x forward_batch + K3 + backward +
+            [NCCL all-reduce] + Adam + EMA) timed the same way: updates/s;
+  cpu_baseline  the CPU restatement of the reference path (oracle/, "port") timed on
+            this box's host cores on a bounded sample.
+reference arm (--impl reference): the CPU path alone, all host threads.
+"""
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+for _p in (os.path.join(REPO, "r-nad_b200"), REPO):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+CONFIGS = {
+    # name: (depth, max_actions, max_transitions, batch per GPU)
+    "cfg1": (2, 2, 1, 256),
+    "cfg2": (4, 3, 2, 65536),
+    "cfg2small": (3, 3, 2, 8192),
+}
+
+
+def algorithmic_bytes_per_env_step(a, c):
+    """K1 reads 8A^2 + 2C + 6, K2 API-faithful trajectory writes 24 + 8A^2 + 12A."""
+    return (8 * a * a + 2 * c + 6) + (24 + 8 * a * a + 12 * a)
+
+
+def flops_per_env_step(a, width=256):
+    return 2 * width * (4 * a * a + a + 1)
+
+
+def make_tree(depth, a, c, seed=0):
+    import random
+
+    from environment.tree import Tree
+
+    np.random.seed(seed)
+    random.seed(seed)
+    torch.manual_seed(seed)
+    tree = Tree(max_actions=a, max_transitions=c, depth_bound=depth)
+    tree.generate()
+    return tree
+
+
+def measured_peaks():
+    path = os.path.join(REPO, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            d = json.load(f)
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d["bf16_tflops"], "source": "measured (MEASURED_PEAKS.json)"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
+
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+             "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu_index = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.gpu_index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, sm_max, reasons = [], [], set()
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        for line in self.lines:
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                sm_max.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, flag in zip(names, f[5:9]):
+                if flag.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(sm_max) if sm_max else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------- native arm
+
+class RolloutRunner:
+    """Pre-allocated trajectory buffers + a direct C-ABI launch (no host sync) for kernel timing."""
+
+    def __init__(self, tree, net, batch, precision):
+        import ctypes
+
+        import _b200
+
+        self._b200, self._ctypes = _b200, ctypes
+        self.L = _b200.lib()
+        self.packed = tree.packed()
+        p = self.packed
+        dev = p.device
+        self.batch, self.T, self.precision = batch, p.max_half_moves, _b200.PRECISIONS[precision]
+        a, t = p.A, self.T
+        self.out = {
+            "indices": torch.empty((t, batch), dtype=torch.int64, device=dev),
+            "turns": torch.empty((t, batch), dtype=torch.int64, device=dev),
+            "observations": torch.empty((t, batch, 2, a, a), dtype=torch.float32, device=dev),
+            "policy": torch.empty((t, batch, a), dtype=torch.float32, device=dev),
+            "actions": torch.empty((t, batch, a), dtype=torch.float32, device=dev),
+            "rewards": torch.empty((t, batch), dtype=torch.float32, device=dev),
+            "values": torch.empty((t, batch), dtype=torch.float32, device=dev),
+            "masks": torch.empty((t, batch, a), dtype=torch.float32, device=dev),
+        }
+        self.traj = _b200.Trajectory(**{k: v.data_ptr() for k, v in self.out.items()})
+        self.w = _b200.MlpWeights()
+        for layer in ("value_fc0", "value_fc1", "policy_fc0", "policy_fc1"):
+            lin = getattr(net, layer)
+            setattr(self.w, layer + "_w", lin.weight.data_ptr())
+            setattr(self.w, layer + "_b", lin.bias.data_ptr())
+        self.w.width = net.width
+        self.t_last = torch.full((1,), -1, dtype=torch.int32, device=dev)
+        self.seed = 1
+
+    def launch(self):
+        b, c = self._b200, self._ctypes
+        p = self.packed
+        self.seed += 1
+        self.L.rnad_rollout(b.ptr(p.ev_tab), b.ptr(p.tr_tab), p.A, p.C, c.byref(self.w), self.batch, self.T,
+                            self.seed, 0, None, self.precision, c.byref(self.traj), b.ptr(self.t_last), b.stream())
+
+
+def timed_steps(fn, steps, warmup, flush, barrier):
+    """W warm-up calls, then K calls each bracketed by CUDA events on the current stream, L2 flushed in between."""
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    barrier()
+    torch.cuda.synchronize()
+    total_ms = 0.0
+    wall0 = time.perf_counter()
+    for _ in range(steps):
+        flush()
+        start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        start.record()
+        fn()
+        stop.record()
+        stop.synchronize()
+        total_ms += start.elapsed_time(stop)
+    torch.cuda.synchronize()
+    barrier()
+    torch.cuda.synchronize()
+    return total_ms, time.perf_counter() - wall0
+
+
+def cpu_rollout_baseline(tree_tables, weights, a, batch, t_max, budget_s, threads):
+    """The reference path restated on the CPU (oracle/, torch-CPU ops like the reference's own), bounded sample."""
+    from oracle import rnad_oracle as orc
+
+    torch.set_num_threads(threads)
+    orc.rollout(tree_tables, weights, min(batch, 1024), t_max, seed=0)       # warm-up
+    done, steps_done, t0 = 0, 0, time.perf_counter()
+    while True:
+        out = orc.rollout(tree_tables, weights, batch, t_max, seed=done + 1)
+        steps_done += int((out["indices"] != 0).sum())
+        done += 1
+        elapsed = time.perf_counter() - t0
+        if elapsed > budget_s or done >= 20:
+            break
+    return steps_done / elapsed, done, elapsed
+
+
+def run_native(args):
+    import torch.distributed as dist
+
+    from environment.episode import Episodes
+    from learn.rnad import RNaD
+    from nn.net import MLP
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py (native arm) needs a CUDA device; there is no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+
+    depth, a, c, batch = CONFIGS[args.config]
+    if args.batch:
+        batch = args.batch
+    tree_cpu = make_tree(depth, a, c, seed=0)
+    tables = {"index": tree_cpu.index_tensor.clone(), "value": tree_cpu.value_tensor.clone(),
+              "chance": tree_cpu.chance_tensor.clone(), "expected_value": tree_cpu.expected_value_tensor.clone(),
+              "legal": tree_cpu.legal_tensor.clone()}
+    n_nodes = int(tree_cpu.index_tensor.shape[0])
+    tree = tree_cpu
+    tree.to(dev)
+    torch.manual_seed(1234)
+    net = MLP(a, 256, device=dev)
+    weights_cpu = {k: v.detach().cpu().clone() for k, v in net.state_dict().items()}
+    precision = args.precision
+    runner = RolloutRunner(tree, net, batch, precision)
+    T = runner.T
+    env_steps = batch * T                       # regular tree: every (t, b) slot is a valid env step
+
+    flush_buf = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)
+
+    def flush():
+        flush_buf.fill_(1.0)
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+
+    # ---- value: kernel throughput, everything resident
+    kernel_ms, _ = timed_steps(runner.launch, args.steps, args.warmup, flush, barrier)
+    assert int(runner.t_last.item()) == T - 1
+
+    # ---- e2e: public API with host buffers
+    pinned_w = {k: v.pin_memory() for k, v in weights_cpu.items()}
+    returns_host = torch.empty(batch, dtype=torch.float32).pin_memory()
+    state = dict(net.named_parameters())
+    h2d_bytes = sum(v.numel() * 4 for v in pinned_w.values())
+    d2h_bytes = batch * 4 + 4                   # per-game returns + t_eff
+
+    def e2e_step():
+        with torch.no_grad():
+            for k, v in pinned_w.items():
+                state[k].copy_(v, non_blocking=True)
+        ep = Episodes(tree, batch)
+        ep.generate(net, precision=precision)
+        returns_host.copy_(ep.rewards.sum(0), non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    e2e_ms, _ = timed_steps(e2e_step, args.steps, args.warmup, flush, barrier)
+
+    # ---- learner: one full update through the public RNaD loop body
+    trial = RNaD(tree=tree, device=dev, directory_name=f"bench_rank{rank}", batch_size=batch, eta=0.2, lr=1e-3,
+                 gamma_averaging=0.01, logit_clip=2, net_params={"type": "MLP", "max_actions": a, "width": 256})
+    trial.net = net
+    trial.net.train()
+    trial.net_target, trial.net_reg, trial.net_reg_ = (MLP(a, 256, device=dev) for _ in range(3))
+    for other in (trial.net_target, trial.net_reg, trial.net_reg_):
+        other.load_state_dict(net.state_dict())
+    trial.optimizer = torch.optim.Adam(net.parameters(), lr=1e-3, betas=(0.0, 0.999), eps=1e-8)
+    loss_host = torch.empty(2, dtype=torch.float32).pin_memory()
+
+    def learner_step():
+        trial.learner_step(alpha=0.5)
+        trial.total_steps += 1
+        loss_host.copy_(trial.last_losses, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    learner_steps = max(3, args.steps // 2)
+    learner_ms, _ = timed_steps(learner_step, learner_steps, max(3, args.warmup), flush, barrier)
+    clocks = sampler.stop()
+
+    # ---- max over ranks
+    times = torch.tensor([kernel_ms, e2e_ms, learner_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(times, op=dist.ReduceOp.MAX)
+    kernel_ms, e2e_ms, learner_ms = (float(x) for x in times.tolist())
+
+    result = None
+    if rank == 0:
+        peaks = measured_peaks()
+        total_env_steps = env_steps * world
+        value = total_env_steps * args.steps / (kernel_ms / 1e3)
+        per_launch_s = kernel_ms / 1e3 / args.steps
+        bytes_per_launch = algorithmic_bytes_per_env_step(a, c) * env_steps
+        achieved_gbs = bytes_per_launch / per_launch_s / 1e9
+        tflops = flops_per_env_step(a) * env_steps / per_launch_s / 1e12
+        cpu = None
+        if world == 1 or True:
+            threads = os.cpu_count() or 1
+            cpu_value, cpu_rollouts, cpu_elapsed = cpu_rollout_baseline(tables, weights_cpu, a, batch, T,
+                                                                        args.cpu_budget, threads)
+            cpu = {"value": cpu_value, "unit": "env_steps/s", "cores": threads, "kind": "port",
+                   "sample": f"{cpu_rollouts} rollouts of {batch} games x {T} half-moves on the same tree and net "
+                             f"({cpu_elapsed:.1f} s, torch-CPU ops, {threads} threads)"}
+        result = {
+            "metric": "self_play_env_steps_per_sec", "value": value, "unit": "env_steps/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": kernel_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "tf32 (tcgen05, fp32 accumulate) + fp32" if precision == "tf32" else "fp32",
+            "data": "synthetic",
+            "config": {"workload": f"{args.config}: depth={depth} max_actions={a} max_transitions={c} regular tree "
+                                   f"({n_nodes} nodes), batch={batch} games per GPU, T={T} half-moves, MLP width 256, "
+                                   f"fused rollout+net kernel ({precision})",
+                       "env_steps_per_step": total_env_steps, "l2": "256 MiB buffer written between timed steps",
+                       "partitioning": f"games sharded, {world} rank(s), no data-path collective in the rollout"},
+            "clocks": clocks,
+            "e2e": {"value": total_env_steps * args.steps / (e2e_ms / 1e3), "unit": "env_steps/s",
+                    "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
+                    "ms_per_step": e2e_ms / args.steps,
+                    "what": "net weights copied from pinned host memory, Episodes.generate(net), per-game returns "
+                            "and t_eff read back to the host"},
+            "gpu_launches": args.steps,
+            "roofline": {"bound": "hbm", "achieved": achieved_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                         "frac": achieved_gbs / peaks["hbm_gbs"], "traffic": None,
+                         "kernel": "rollout_tc_kernel" if precision == "tf32" else "rollout_fp32_kernel",
+                         "algorithmic_bytes_per_env_step": algorithmic_bytes_per_env_step(a, c),
+                         "peak_source": peaks["source"]},
+            "roofline_tensor": {"achieved": tflops, "unit": "TFLOP/s (algorithmic MLP flops)",
+                                "peak_bf16": peaks["bf16_tflops"], "frac_of_bf16_peak": tflops / peaks["bf16_tflops"]},
+            "learner": {"updates_per_sec": learner_steps / (learner_ms / 1e3), "ms_per_update": learner_ms / learner_steps,
+                        "env_steps_per_sec": total_env_steps * learner_steps / (learner_ms / 1e3),
+                        "steps": learner_steps,
+                        "what": "RNaD.learner_step: rollout + 4x forward_batch + fused v-trace/NeuRD targets + "
+                                "backward" + (" + NCCL grad all-reduce" if world > 1 else "") + " + Adam + EMA, "
+                                "losses read back each step"},
+            "cpu_baseline": cpu,
+        }
+        print(json.dumps(result), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return result
+
+
+# ------------------------------------------------------------------------ reference arm
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return None
+    from oracle import rnad_oracle as orc
+    from nn.net import MLP
+
+    depth, a, c, batch = CONFIGS[args.config]
+    if args.batch:
+        batch = args.batch
+    tree = make_tree(depth, a, c, seed=0)
+    tables = {"index": tree.index_tensor, "value": tree.value_tensor, "chance": tree.chance_tensor,
+              "expected_value": tree.expected_value_tensor, "legal": tree.legal_tensor}
+    torch.manual_seed(1234)
+    net = MLP(a, 256)
+    weights = {k: v.detach().clone() for k, v in net.state_dict().items()}
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    t_max = 2 * depth
+    sample_batch = min(batch, args.reference_batch)
+    for _ in range(min(args.warmup, 2)):
+        orc.rollout(tables, weights, sample_batch, t_max, seed=0)
+    total, t0 = 0, time.perf_counter()
+    for i in range(args.steps):
+        out = orc.rollout(tables, weights, sample_batch, t_max, seed=i + 1)
+        total += int((out["indices"] != 0).sum())
+    elapsed = time.perf_counter() - t0
+    value = total / elapsed
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    result = {
+        "impl": "reference", "metric": "self_play_env_steps_per_sec", "value": value, "unit": "env_steps/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": elapsed * 1e3 / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
+        "config": {"workload": f"{args.config}: depth={depth} max_actions={a} max_transitions={c} regular tree, "
+                               f"MLP width 256; each step = one rollout of {sample_batch} games x {t_max} half-moves "
+                               f"(bounded sample of the {batch}-game batch)"},
+        "cpu_baseline": {"value": value, "unit": "env_steps/s", "cores": threads, "kind": "port",
+                         "sample": f"{args.steps} rollouts of {sample_batch} games, CPU restatement of the reference "
+                                   f"path (oracle/), torch-CPU ops on {threads} threads"},
+        "e2e": {"value": value, "unit": "env_steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(result), flush=True)
+    return result
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--config", default="cfg2", choices=sorted(CONFIGS))
+    ap.add_argument("--batch", type=int, default=0, help="games per GPU (default: the config's)")
+    ap.add_argument("--precision", default="tf32", choices=["tf32", "fp32"])
+    ap.add_argument("--cpu-budget", type=float, default=15.0, help="seconds of CPU work for cpu_baseline")
+    ap.add_argument("--reference-batch", type=int, default=65536)
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "native" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_native(args)
+
+
+if __name__ == "__main__":
+    main()
