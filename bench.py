@@ -165,6 +165,9 @@ class RolloutRunner:
             setattr(self.w, layer + "_b", lin.bias.data_ptr())
         self.w.width = net.width
         self.t_last = torch.full((1,), -1, dtype=torch.int32, device=dev)
+        ws = int(self.L.rnad_rollout_workspace_bytes(a, net.width, self.precision))
+        self.workspace = torch.empty(max(ws, 16), dtype=torch.uint8, device=dev)
+        self.launches_per_step = 2 if ws else 1      # weight-image pre-kernel + rollout kernel
         self.seed = 1
 
     def launch(self):
@@ -172,7 +175,8 @@ class RolloutRunner:
         p = self.packed
         self.seed += 1
         self.L.rnad_rollout(b.ptr(p.ev_tab), b.ptr(p.tr_tab), p.A, p.C, c.byref(self.w), self.batch, self.T,
-                            self.seed, 0, None, self.precision, c.byref(self.traj), b.ptr(self.t_last), b.stream())
+                            self.seed, 0, None, self.precision, c.byref(self.traj), b.ptr(self.t_last),
+                            b.ptr(self.workspace), b.stream())
 
 
 def timed_steps(fn, steps, warmup, flush, barrier):
@@ -346,7 +350,7 @@ def run_native(args):
                     "ms_per_step": e2e_ms / args.steps,
                     "what": "net weights copied from pinned host memory, Episodes.generate(net), per-game returns "
                             "and t_eff read back to the host"},
-            "gpu_launches": args.steps,
+            "gpu_launches": args.steps * runner.launches_per_step,
             "roofline": {"bound": "hbm", "achieved": achieved_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                          "frac": achieved_gbs / peaks["hbm_gbs"], "traffic": None,
                          "kernel": "rollout_tc_kernel" if precision == "tf32" else "rollout_fp32_kernel",

@@ -109,6 +109,9 @@ RNAD_API int rnad_sample_categorical(const float* p, int64_t B, int N, const flo
  *   actions f32 one-hot (T,B,A), rewards f32, values f32, masks f32 (T,B,A).
  * t_last (device int32, caller sets to -1): max over games of the last
  * half-move at which the game was not yet on the absorbing node (= t_eff).
+ * workspace: 16-byte aligned device scratch of rnad_rollout_workspace_bytes()
+ * (the tensor-core engine lays the weights out in MMA operand order there once per
+ * call and every CTA fetches that image with one TMA bulk copy); may be NULL when 0.
  * ------------------------------------------------------------------------ */
 typedef struct rnad_mlp_weights {
     const float* value_fc0_w; const float* value_fc0_b;
@@ -127,7 +130,9 @@ RNAD_API int rnad_rollout(const uint32_t* ev_tab, const uint32_t* tr_tab, int A,
                  const rnad_mlp_weights* w /* host struct of device pointers */,
                  int64_t B, int T, uint64_t seed, int64_t game_offset, const float* uniforms,
                  int precision, const rnad_trajectory* out /* host struct of device pointers */,
-                 int32_t* t_last, void* stream);
+                 int32_t* t_last, void* workspace, void* stream);
+
+RNAD_API int64_t rnad_rollout_workspace_bytes(int A, int width, int precision);
 
 /* 1 if the RNAD_PREC_TF32 engine serves this net shape (width == 256, 2 <= A <= 4), else 0 */
 RNAD_API int rnad_rollout_tc_supported(int A, int width);

@@ -23,7 +23,7 @@ PRECISIONS = {"fp32": PREC_FP32, "tf32": PREC_TF32}
 
 EXPORTS = (
     "rnad_last_error", "rnad_version", "rnad_device_sm_count", "rnad_packed_strides", "rnad_tree_pack",
-    "rnad_observe", "rnad_step", "rnad_sample_categorical", "rnad_rollout", "rnad_rollout_tc_supported",
+    "rnad_observe", "rnad_step", "rnad_sample_categorical", "rnad_rollout", "rnad_rollout_workspace_bytes", "rnad_rollout_tc_supported",
     "rnad_process_policy", "rnad_vtrace", "rnad_learner_targets_workspace", "rnad_count_played",
     "rnad_learner_targets",
 )
@@ -83,7 +83,9 @@ def lib():
     L.rnad_sample_categorical.argtypes = [c_void_p, c_int64, c_int, c_void_p, c_uint64, c_int, c_int64, c_void_p,
                                           c_void_p]
     L.rnad_rollout.argtypes = [c_void_p, c_void_p, c_int, c_int, POINTER(MlpWeights), c_int64, c_int, c_uint64,
-                               c_int64, c_void_p, c_int, POINTER(Trajectory), c_void_p, c_void_p]
+                               c_int64, c_void_p, c_int, POINTER(Trajectory), c_void_p, c_void_p, c_void_p]
+    L.rnad_rollout_workspace_bytes.restype = c_int64
+    L.rnad_rollout_workspace_bytes.argtypes = [c_int, c_int, c_int]
     L.rnad_rollout_tc_supported.argtypes = [c_int, c_int]
     L.rnad_process_policy.argtypes = [c_void_p, c_void_p, c_int64, c_int, c_int, c_float, c_void_p, c_void_p]
     L.rnad_vtrace.argtypes = [c_void_p] * 9 + [c_int] + [c_float] * 5 + [c_int, c_int64, c_int] + [c_void_p] * 4

@@ -5,7 +5,8 @@ using namespace rnad;
 
 extern "C" int rnad_rollout(const uint32_t* ev_tab, const uint32_t* tr_tab, int A, int C, const rnad_mlp_weights* w,
                             int64_t B, int T, uint64_t seed, int64_t game_offset, const float* uniforms,
-                            int precision, const rnad_trajectory* out, int32_t* t_last, void* stream) {
+                            int precision, const rnad_trajectory* out, int32_t* t_last, void* workspace,
+                            void* stream) {
     RNAD_REQUIRE(ev_tab && tr_tab && w && out && t_last, "rnad_rollout: null pointer");
     RNAD_REQUIRE(A >= 1 && A <= RNAD_MAX_ACTIONS, "rnad_rollout: max_actions %d outside [1,%d]", A, RNAD_MAX_ACTIONS);
     RNAD_REQUIRE(C >= 1 && C <= RNAD_MAX_TRANSITIONS, "rnad_rollout: max_transitions %d outside [1,%d]", C,
@@ -37,7 +38,7 @@ extern "C" int rnad_rollout(const uint32_t* ev_tab, const uint32_t* tr_tab, int 
     cudaStream_t st = (cudaStream_t)stream;
     switch (precision) {
         case RNAD_PREC_FP32: return rollout_fp32(g, st);
-        case RNAD_PREC_TF32: return rollout_tc(g, st);
+        case RNAD_PREC_TF32: return rollout_tc(g, workspace, st);
     }
     set_error("rnad_rollout: unknown precision %d", precision);
     return RNAD_EINVAL;
@@ -45,3 +46,9 @@ extern "C" int rnad_rollout(const uint32_t* ev_tab, const uint32_t* tr_tab, int 
 
 // 1 if the tensor-core engine serves this net shape, else 0
 extern "C" int rnad_rollout_tc_supported(int A, int width) { return rollout_tc_supported(A, width) ? 1 : 0; }
+
+// bytes of device scratch rnad_rollout needs for this net shape and engine (0 = none)
+extern "C" int64_t rnad_rollout_workspace_bytes(int A, int width, int precision) {
+    if (precision == RNAD_PREC_TF32 && rollout_tc_supported(A, width)) return rollout_tc_workspace_bytes(A);
+    return 0;
+}

@@ -230,9 +230,12 @@ class Episodes:
                 if uniforms.shape[0] < t_max or tuple(uniforms.shape[1:]) != (b, 2):
                     raise _b200.RnadError(f"uniforms must be ({t_max}+, {b}, 2), got {tuple(uniforms.shape)}")
                 uniforms = uniforms[:t_max].contiguous()
+            ws_bytes = int(L.rnad_rollout_workspace_bytes(a, net.width, _b200.PRECISIONS[precision]))
+            workspace = torch.empty(ws_bytes, dtype=torch.uint8, device=dev) if ws_bytes else None
             L.rnad_rollout(_b200.ptr(packed.ev_tab), _b200.ptr(packed.tr_tab), a, packed.C, ctypes.byref(w), b, t_max,
                            self.states.seed, self.states.game_offset, _b200.ptr(uniforms),
-                           _b200.PRECISIONS[precision], ctypes.byref(traj), _b200.ptr(t_last), _b200.stream())
+                           _b200.PRECISIONS[precision], ctypes.byref(traj), _b200.ptr(t_last), _b200.ptr(workspace),
+                           _b200.stream())
             self.t_eff = int(t_last.item())          # the rollout's only host synchronisation
         self.precision = precision
         n = self.t_eff + 1

@@ -31,15 +31,10 @@ import torch.nn as nn
 
 import environment.episode as episode
 import environment.tree as tree
+import learn.dp as dp
 import learn.vtrace as vtrace
 import nn.net as net
 import util.metric as metric
-
-
-def _dist():
-    import torch.distributed as dist
-
-    return dist if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1 else None
 
 
 class RNaD:
@@ -126,7 +121,7 @@ class RNaD:
         self.net_reg_: nn.Module = None
         self.optimizer = None
         self.last_losses = None      # device tensor [loss_v, loss_nerd] of the latest step
-        self._workspace = None
+        self.nashconv_history = []   # (total_steps, NashConv of the target net)
 
     # ------------------------------------------------------------------ nets
 
@@ -145,8 +140,7 @@ class RNaD:
                                 eps=self.epsilon_adam)
 
     def _is_writer(self):
-        d = _dist()
-        return d is None or d.get_rank() == 0
+        return dp.rank() == 0
 
     # ------------------------------------------------------- init / checkpoints
 
@@ -166,10 +160,7 @@ class RNaD:
                                         map_location=self.device)
                 self.net.load_state_dict(checkpoint["net"])
                 logging.info("Loading init net from {}".format(self.use_same_init_net_as))
-            d = _dist()
-            if d is not None:   # every rank starts from rank 0's weights
-                for p in self.net.parameters():
-                    d.broadcast(p.data, src=0)
+            dp.broadcast_parameters(self.net)   # every rank starts from rank 0's weights
             self.net.train()
             self.net_target = self.__new_net()
             self.net_target.load_state_dict(self.net.state_dict())
@@ -264,15 +255,11 @@ class RNaD:
             _, log_pi_reg, _, _ = self.net_reg.forward_batch(episodes)
             _, log_pi_reg_, _, _ = self.net_reg_.forward_batch(episodes)
 
-        d = _dist()
         global_counts = None
-        if d is not None:
+        if dp.group() is not None:
             # exact data-parallel losses: normalise by the GLOBAL number of steps each player took
-            global_counts = vtrace.count_played(episodes)
-            d.all_reduce(global_counts)
+            global_counts = dp.all_reduce_counts(vtrace.count_played(episodes))
 
-        if self._workspace is None or self._workspace.device != logit.device:
-            self._workspace = None
         out = vtrace.learner_targets(
             episodes, logit, pi, log_pi, v, v_target, log_pi_reg, log_pi_reg_,
             alpha=alpha, eta=self.eta, lambda_=1.0, c=self.c_bar, rho=self.roh_bar, gamma=self.vtrace_gamma,
@@ -282,8 +269,7 @@ class RNaD:
         self.last_losses = out.losses
         torch.autograd.backward([logit, v], [out.d_logit, out.d_v.unsqueeze(-1)])
 
-        if d is not None:
-            self.__allreduce_gradients(d)
+        dp.all_reduce_gradients(self.net.parameters())   # no-op unless torch.distributed is initialised
 
         if log is not None:
             valid = (episodes.indices != 0).to(torch.float)
@@ -291,9 +277,7 @@ class RNaD:
             total_norm = torch.sqrt(sum(p.grad.detach().pow(2).sum() for p in self.net.parameters())).item()
             logit_mean = logit.mean().item()
             uniform_policy = torch.nn.functional.normalize(masks, p=1, dim=-1)
-            losses = out.losses.tolist()
-            if d is not None:
-                pass   # losses are this rank's share of the global loss
+            losses = out.losses.tolist()   # under data parallelism: this rank's share of the global loss
             log.update({
                 "loss_v": losses[0],
                 "loss_nerd": losses[1],
@@ -307,16 +291,6 @@ class RNaD:
             })
 
         nn.utils.clip_grad_norm_(self.net.parameters(), self.grad_clip)
-
-    def __allreduce_gradients(self, d):
-        """ONE collective per step: sum the flat gradient over ranks (local terms are already divided by global counts)."""
-        grads = [p.grad for p in self.net.parameters()]
-        flat = torch.cat([g.reshape(-1) for g in grads])
-        d.all_reduce(flat)
-        offset = 0
-        for g in grads:
-            g.copy_(flat[offset: offset + g.numel()].view_as(g))
-            offset += g.numel()
 
     def learner_step(self, alpha: float, buffer: "episode.Buffer" = None, log: dict = None):
         """One iteration of the rnad.py:495 loop body without the schedule bookkeeping: rollout, learn, Adam, EMA."""
@@ -382,7 +356,6 @@ class RNaD:
 
     def run(self, max_updates=10 ** 6, checkpoint_mod=1000, expl_mod=1, log_mod=20):
         """Starts a new run or resumes the latest checkpoint of `directory_name`."""
-        self.nashconv_history = []
         self.__initialize()
         self.__resume(max_updates=max_updates, checkpoint_mod=checkpoint_mod, expl_mod=expl_mod, log_mod=log_mod)
         if self.wandb:
