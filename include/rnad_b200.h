@@ -197,6 +197,40 @@ RNAD_API int rnad_count_played(const int64_t* indices, const int64_t* turns, int
 RNAD_API int rnad_learner_targets(const rnad_learner_io* io /* host struct */, const rnad_learner_params* p,
                          int T, int64_t B, int A, void* workspace, void* stream);
 
+/* ------------------------------------------------------------------------
+ * Learner-side net passes of RNaD.__learn, fused (rnad.py:373-380, 424-425;
+ * net.py:64-85 forward_batch).  observations: (N, 2A^2) f32 = the (T,B,2,A,A)
+ * trajectory tensor flattened, N = T*B.  Tensor-core engine only: width 256,
+ * 2 <= A <= 4 (rnad_learner_mlp_supported); otherwise the caller keeps the
+ * reference-style batched GEMM path.
+ *
+ * rnad_learner_forward: ONE pass computes, per row,
+ *   learner net : logit (N,A), pi (N,A), log_pi (N,A), v (N)      [forward_batch outputs]
+ *   target net  : v_target (N)                                     [value trunk only]
+ *   reg nets    : log_pi_reg (N,A), log_pi_reg_ (N,A)              [policy trunks only]
+ * rnad_learner_backward: parameter gradients of the learner net for given
+ *   d_logit (N,A), d_v (N) (from rnad_learner_targets), written (not accumulated)
+ *   to flat_grad, rnad_learner_param_count() floats in state_dict order:
+ *   value_fc0.weight, .bias, value_fc1.weight, .bias, policy_fc0.weight, .bias,
+ *   policy_fc1.weight, .bias.  Deterministic (fixed-order reduction).
+ * workspace: 256-byte aligned device scratch of rnad_learner_mlp_workspace_bytes().
+ * ------------------------------------------------------------------------ */
+typedef struct rnad_learner_fwd_out {
+    float* logit; float* pi; float* log_pi; float* v;
+    float* v_target; float* log_pi_reg; float* log_pi_reg_;
+} rnad_learner_fwd_out;
+
+RNAD_API int rnad_learner_mlp_supported(int A, int width);
+RNAD_API int64_t rnad_learner_mlp_workspace_bytes(int A, int width);
+RNAD_API int rnad_learner_param_count(int A, int width);
+RNAD_API int rnad_learner_forward(const float* observations, int64_t N, int A,
+                         const rnad_mlp_weights* net, const rnad_mlp_weights* target,
+                         const rnad_mlp_weights* reg, const rnad_mlp_weights* reg_,
+                         const rnad_learner_fwd_out* out, void* workspace, void* stream);
+RNAD_API int rnad_learner_backward(const float* observations, int64_t N, int A, const rnad_mlp_weights* net,
+                          const float* d_logit, const float* d_v, float* flat_grad,
+                          void* workspace, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

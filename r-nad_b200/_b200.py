@@ -25,7 +25,8 @@ EXPORTS = (
     "rnad_last_error", "rnad_version", "rnad_device_sm_count", "rnad_packed_strides", "rnad_tree_pack",
     "rnad_observe", "rnad_step", "rnad_sample_categorical", "rnad_rollout", "rnad_rollout_workspace_bytes", "rnad_rollout_tc_supported",
     "rnad_process_policy", "rnad_vtrace", "rnad_learner_targets_workspace", "rnad_count_played",
-    "rnad_learner_targets",
+    "rnad_learner_targets", "rnad_learner_mlp_supported", "rnad_learner_mlp_workspace_bytes",
+    "rnad_learner_param_count", "rnad_learner_forward", "rnad_learner_backward",
 )
 
 
@@ -50,6 +51,10 @@ class LearnerIO(Structure):
         + [("v_target", c_void_p * 2), ("has_played", c_void_p * 2), ("learning_output", c_void_p * 2)]
         + [("losses", c_void_p), ("counts", c_void_p), ("global_counts", c_void_p)]
     )
+
+
+class LearnerFwdOut(Structure):
+    _fields_ = [(n, c_void_p) for n in ("logit", "pi", "log_pi", "v", "v_target", "log_pi_reg", "log_pi_reg_")]
 
 
 class LearnerParams(Structure):
@@ -94,9 +99,19 @@ def lib():
     L.rnad_count_played.argtypes = [c_void_p, c_void_p, c_int, c_int64, c_void_p, c_void_p]
     L.rnad_learner_targets.argtypes = [POINTER(LearnerIO), POINTER(LearnerParams), c_int, c_int64, c_int, c_void_p,
                                        c_void_p]
+    L.rnad_learner_mlp_supported.argtypes = [c_int, c_int]
+    L.rnad_learner_mlp_workspace_bytes.restype = c_int64
+    L.rnad_learner_mlp_workspace_bytes.argtypes = [c_int, c_int]
+    L.rnad_learner_param_count.argtypes = [c_int, c_int]
+    L.rnad_learner_forward.argtypes = [c_void_p, c_int64, c_int] + [POINTER(MlpWeights)] * 4 + [
+        POINTER(LearnerFwdOut), c_void_p, c_void_p]
+    L.rnad_learner_backward.argtypes = [c_void_p, c_int64, c_int, POINTER(MlpWeights), c_void_p, c_void_p, c_void_p,
+                                        c_void_p, c_void_p]
+    no_errcheck = ("rnad_version", "rnad_device_sm_count", "rnad_rollout_tc_supported", "rnad_learner_mlp_supported",
+                   "rnad_learner_param_count")
     for name in EXPORTS:
         fn = getattr(L, name)
-        if fn.restype is c_int and name not in ("rnad_version", "rnad_device_sm_count", "rnad_rollout_tc_supported"):
+        if fn.restype is c_int and name not in no_errcheck:
             fn.errcheck = _errcheck
     _lib = L
     return L
@@ -123,6 +138,24 @@ def ptr(t, dtype=None):
     if dtype is not None and t.dtype != dtype:
         raise RnadError(f"expected {dtype}, got {t.dtype}")
     return c_void_p(t.data_ptr())
+
+
+def mlp_weights(net, device=None):
+    """rnad_mlp_weights for an nn.net.MLP (fp32, contiguous, on one CUDA device); keeps the tensors alive on the struct."""
+    w = MlpWeights()
+    keep = []
+    for layer in ("value_fc0", "value_fc1", "policy_fc0", "policy_fc1"):
+        lin = getattr(net, layer)
+        for suffix, tensor in (("w", lin.weight), ("b", lin.bias)):
+            tensor = tensor.detach()
+            if tensor.dtype != torch.float32 or not tensor.is_cuda or (device is not None and tensor.device != device):
+                raise RnadError(f"{layer}: the kernels need fp32 weights on {device or 'a CUDA device'}")
+            tensor = tensor.contiguous()
+            keep.append(tensor)
+            setattr(w, f"{layer}_{suffix}", tensor.data_ptr())
+    w.width = net.width
+    w._keep = keep
+    return w
 
 
 def device_guard(t):

@@ -1,0 +1,672 @@
+// Learner-side net passes of RNaD.__learn, fused (SURVEY.md section 8 f#3):
+//
+//   rnad_learner_forward   the four forward_batch calls of rnad.py:373-380 in ONE pass
+//                          over the trajectory: learner (logit, pi, log_pi, v), target
+//                          net (v only), regularisation nets (log_pi only) = five trunk
+//                          evaluations per step instead of eight, first layers on
+//                          tcgen05 (kind::tf32, fp32 accumulate in TMEM), the hidden
+//                          activations never leave the SM.
+//   rnad_learner_backward  parameter gradients of the learner net given d loss/d logit
+//                          and d loss/d v (from rnad_learner_targets): recomputes the two
+//                          learner trunks on the tensor core, reduces
+//                              dW2 = g^T relu(h),  dh = (g W2) * [h > 0],  dW1 = dh^T x
+//                          over the 128 rows of a tile in fp32 on the CUDA cores, keeps
+//                          per-CTA sums in registers across tiles, and a second kernel
+//                          adds the per-CTA partials in a fixed order (deterministic).
+//
+// Reference: nn/net.py:64-85 (forward_batch), learn/rnad.py:373-380, 424-425.
+// In the reference these are 8 x T small GEMMs + ~40 elementwise launches forward and
+// autograd's mirror image backward, with the (T*B x 256) activations written to and
+// re-read from HBM about ten times per update.
+#include "tc_common.cuh"
+
+namespace rnad {
+namespace tc {
+
+constexpr int kLearnThreads = 256;   // two threads per trajectory row
+constexpr int kFwdTrunks = 5;        // learner value, learner policy, target value, reg policy, reg_ policy
+
+template <int A>
+struct Shape {
+    static constexpr int KIN = 2 * A * A;
+    static constexpr bool kBiasInK = (KIN % 8) != 0;
+    static constexpr int KP = round_up(KIN + (kBiasInK ? 1 : 0), 8);
+    static constexpr int kTrunkBytes = kHidden * KP * 4;
+    // number of learner parameters, in state_dict order:
+    // value_fc0.{weight,bias}, value_fc1.{weight,bias}, policy_fc0.{weight,bias}, policy_fc1.{weight,bias}
+    static constexpr int kOffV0w = 0;
+    static constexpr int kOffV0b = kOffV0w + kHidden * KIN;
+    static constexpr int kOffV1w = kOffV0b + kHidden;
+    static constexpr int kOffV1b = kOffV1w + kHidden;
+    static constexpr int kOffP0w = kOffV1b + 1;
+    static constexpr int kOffP0b = kOffP0w + kHidden * KIN;
+    static constexpr int kOffP1w = kOffP0b + kHidden;
+    static constexpr int kOffP1b = kOffP1w + A * kHidden;
+    static constexpr int kParams = kOffP1b + A;
+};
+
+// ------------------------------------------------------------------ forward
+
+template <int A>
+struct FwdPlan : Shape<A> {
+    using S = Shape<A>;
+    static constexpr int kB = 0;                                        // 5 first-layer operands
+    static constexpr int kW2v = kB + kFwdTrunks * S::kTrunkBytes;       // value_fc1.weight of learner, target
+    static constexpr int kW2p = kW2v + 2 * kHidden * 4;                 // policy_fc1.weight [j][4] of learner, reg, reg_
+    static constexpr int kB1 = kW2p + 3 * kHidden * 16;                 // first-layer biases, 5 x 256
+    static constexpr int kB2 = kB1 + kFwdTrunks * kHidden * 4;          // second-layer biases: 5 x 4 f32
+    static constexpr int kImageBytes = kB2 + kFwdTrunks * 16;
+    static constexpr int kA = kImageBytes;                              // A operand tile
+    static constexpr int kPart = kA + kTileM * S::KP * 4;               // upper-half partial sums: 128 x 5 x float4
+    static constexpr int kBar = kPart + kTileM * kFwdTrunks * 16;       // mbarriers: image, stage 0, stage 1
+    static constexpr int kTmem = kBar + 32;
+    static constexpr int kBytes = kTmem + 16;
+    static_assert(kImageBytes % 16 == 0 && kA % 16 == 0 && kPart % 16 == 0 && kBar % 8 == 0, "alignment");
+};
+
+struct FwdNets {
+    rnad_mlp_weights net, target, reg, reg_;
+};
+
+struct FwdOut {
+    float* logit;
+    float* pi;
+    float* log_pi;
+    float* v;
+    float* v_target;
+    float* log_pi_reg;
+    float* log_pi_reg_;
+};
+
+template <int A>
+__global__ void pack_fwd_image_kernel(FwdNets w, uint8_t* __restrict__ image) {
+    using P = FwdPlan<A>;
+    const int thread = blockIdx.x * blockDim.x + threadIdx.x, n_threads = gridDim.x * blockDim.x;
+    const float* w1[kFwdTrunks] = {w.net.value_fc0_w, w.net.policy_fc0_w, w.target.value_fc0_w, w.reg.policy_fc0_w,
+                                   w.reg_.policy_fc0_w};
+    const float* b1[kFwdTrunks] = {w.net.value_fc0_b, w.net.policy_fc0_b, w.target.value_fc0_b, w.reg.policy_fc0_b,
+                                   w.reg_.policy_fc0_b};
+#pragma unroll
+    for (int tr = 0; tr < kFwdTrunks; ++tr) {
+        pack_trunk_operand<P::KIN, P::KP, P::kBiasInK>(w1[tr], b1[tr], image + P::kB + tr * P::kTrunkBytes, thread,
+                                                       n_threads);
+        for (int j = thread; j < kHidden; j += n_threads) reinterpret_cast<float*>(image + P::kB1)[tr * kHidden + j] = b1[tr][j];
+    }
+    const float* w2v[2] = {w.net.value_fc1_w, w.target.value_fc1_w};
+    const float* w2p[3] = {w.net.policy_fc1_w, w.reg.policy_fc1_w, w.reg_.policy_fc1_w};
+    for (int j = thread; j < kHidden; j += n_threads) {
+#pragma unroll
+        for (int i = 0; i < 2; ++i) reinterpret_cast<float*>(image + P::kW2v)[i * kHidden + j] = w2v[i][j];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
+            p.x = w2p[i][j];
+            if (A > 1) p.y = w2p[i][1 * kHidden + j];
+            if (A > 2) p.z = w2p[i][2 * kHidden + j];
+            if (A > 3) p.w = w2p[i][3 * kHidden + j];
+            reinterpret_cast<float4*>(image + P::kW2p)[i * kHidden + j] = p;
+        }
+    }
+    if (thread < kFwdTrunks * 4) {
+        const int tr = thread >> 2, a = thread & 3;
+        const float* b2[kFwdTrunks] = {w.net.value_fc1_b, w.net.policy_fc1_b, w.target.value_fc1_b, w.reg.policy_fc1_b,
+                                       w.reg_.policy_fc1_b};
+        const int n = (tr == 0 || tr == 2) ? 1 : A;
+        reinterpret_cast<float*>(image + P::kB2)[thread] = a < n ? b2[tr][a] : 0.f;
+    }
+}
+
+// row of the observation tensor -> registers (8-byte loads; KIN is even)
+template <int KIN>
+__device__ __forceinline__ void load_row(const float* __restrict__ obs, int64_t row, bool active, float (&x)[KIN]) {
+    const float2* src = reinterpret_cast<const float2*>(obs + row * KIN);
+#pragma unroll
+    for (int i = 0; i < KIN / 2; ++i) {
+        const float2 v = active ? __ldg(src + i) : make_float2(0.f, 0.f);
+        x[2 * i] = v.x;
+        x[2 * i + 1] = v.y;
+    }
+}
+
+template <int KIN, int KP, bool kBiasInK>
+__device__ __forceinline__ void store_operand_row(uint8_t* tile, int lane, const float (&x)[KIN]) {
+#pragma unroll
+    for (int q = 0; q < KP / 4; ++q) {
+        float v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int k = 4 * q + u;
+            v[u] = k < KIN ? to_tf32(x[k < KIN ? k : 0]) : ((kBiasInK && k == KIN) ? 1.f : 0.f);
+        }
+        *reinterpret_cast<float4*>(tile + operand_offset<KP>(lane, 4 * q)) = make_float4(v[0], v[1], v[2], v[3]);
+    }
+}
+
+template <int KP>
+__device__ __forceinline__ void issue_trunk_mma(uint32_t a_base, uint32_t b_trunk, uint32_t d_tmem, uint32_t mbar) {
+#pragma unroll
+    for (int s = 0; s < KP / 8; ++s) mma_tf32(d_tmem, make_desc<KP>(a_base + s * 256), make_desc<KP>(b_trunk + s * 256), s > 0);
+    mma_commit(mbar);
+}
+
+// net.py:76-80: masked softmax / log-softmax of one row
+template <int A>
+__device__ __forceinline__ void policy_heads(const float (&logit)[A], const bool (&mask)[A], float (&pi)[A],
+                                             float (&log_pi)[A]) {
+    float e[A];
+    float sum = 0.f;
+#pragma unroll
+    for (int a = 0; a < A; ++a) {
+        e[a] = mask[a] ? expf(logit[a]) : 0.f;
+        sum += e[a];
+    }
+    const float denom = fmaxf(sum, 1e-12f);
+    const float log_sum = logf(sum);
+#pragma unroll
+    for (int a = 0; a < A; ++a) {
+        pi[a] = e[a] / denom;
+        log_pi[a] = mask[a] ? logit[a] - log_sum : 0.f;
+    }
+}
+
+template <int A>
+__global__ void __launch_bounds__(kLearnThreads, 1) learner_fwd_kernel(const float* __restrict__ obs, int64_t N,
+                                                                        const uint8_t* __restrict__ image, FwdOut out) {
+    using P = FwdPlan<A>;
+    constexpr int KIN = P::KIN, KP = P::KP;
+    static_assert(A <= 4, "one float4 of second-layer weights per hidden unit");
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & (kTileM - 1), half = tid >> 7;
+    const uint32_t bar_img = smem_u32(smem + P::kBar), bar_stage[2] = {bar_img + 8, bar_img + 16};
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + P::kTmem);
+
+    if (warp == 0) tmem_alloc<512>(tmem_slot);
+    if (tid == 0) {
+        mbar_init(bar_img, 1);
+        mbar_init(bar_stage[0], 1);
+        mbar_init(bar_stage[1], 1);
+        mbar_fence_init();
+        tma_bulk_load(smem, image, P::kImageBytes, bar_img);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    mbar_wait(bar_img, 0);
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tmem_mine = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(half * 128);
+    const uint32_t a_base = smem_u32(smem + P::kA), b_base = smem_u32(smem + P::kB);
+    const float* b1 = reinterpret_cast<const float*>(smem + P::kB1);
+    const float* b2 = reinterpret_cast<const float*>(smem + P::kB2);
+    const float* w2v = reinterpret_cast<const float*>(smem + P::kW2v);
+    const float4* w2p = reinterpret_cast<const float4*>(smem + P::kW2p);
+    float4* s_part = reinterpret_cast<float4*>(smem + P::kPart);
+
+    uint32_t phase[2] = {0u, 0u};
+    const int64_t num_tiles = (N + kTileM - 1) / kTileM;
+    for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int64_t row = tile * kTileM + lane;
+        const bool active = row < N;
+        bool mask[A];
+#pragma unroll
+        for (int a = 0; a < A; ++a) mask[a] = false;
+        if (half == 0) {
+            float x[KIN];
+            load_row<KIN>(obs, row, active, x);
+#pragma unroll
+            for (int a = 0; a < A; ++a) mask[a] = x[A * A + a * A] != 0.f;   // obs[:, 1, :, 0]
+            store_operand_row<KIN, KP, P::kBiasInK>(smem + P::kA, lane, x);
+            fence_async_smem();
+        }
+        tc_fence_before();
+        __syncthreads();
+        if (tid == 0) {
+            tc_fence_after();
+            issue_trunk_mma<KP>(a_base, b_base + 0 * P::kTrunkBytes, tmem_base + 0, bar_stage[0]);
+            issue_trunk_mma<KP>(a_base, b_base + 1 * P::kTrunkBytes, tmem_base + 256, bar_stage[1]);
+        }
+
+        float4 part[kFwdTrunks];
+#pragma unroll
+        for (int pass = 0; pass < kFwdTrunks; ++pass) {
+            constexpr int kNone = 0;
+            (void)kNone;
+            const int stage = pass & 1;
+            const bool value_pass = pass == 0 || pass == 2;
+            mbar_wait(bar_stage[stage], phase[stage]);
+            phase[stage] ^= 1u;
+            tc_fence_after();
+            float vacc[4] = {0.f, 0.f, 0.f, 0.f};
+            float lacc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+            const float* b1p = b1 + pass * kHidden + half * 128;
+            const float* w2vp = w2v + (pass == 2 ? kHidden : 0) + half * 128;
+            const float4* w2pp = w2p + (pass == 1 ? 0 : pass == 3 ? kHidden : 2 * kHidden) + half * 128;
+            const uint32_t taddr = tmem_mine + stage * 256;
+            uint32_t ra[32], rb[32];
+            tmem_ld32(taddr, ra);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                tmem_ld_wait();
+                if (c + 1 < 4) {
+                    if (c & 1) tmem_ld32(taddr + (c + 1) * 32, ra);
+                    else tmem_ld32(taddr + (c + 1) * 32, rb);
+                }
+                if (value_pass) {
+                    if (c & 1) consume_chunk<A, true, !P::kBiasInK>(rb, 0, b1p + c * 32, w2vp + c * 32, w2pp, vacc, lacc);
+                    else consume_chunk<A, true, !P::kBiasInK>(ra, 0, b1p + c * 32, w2vp + c * 32, w2pp, vacc, lacc);
+                } else {
+                    if (c & 1) consume_chunk<A, false, !P::kBiasInK>(rb, 0, b1p + c * 32, w2vp, w2pp + c * 32, vacc, lacc);
+                    else consume_chunk<A, false, !P::kBiasInK>(ra, 0, b1p + c * 32, w2vp, w2pp + c * 32, vacc, lacc);
+                }
+            }
+            part[pass] = value_pass ? make_float4((vacc[0] + vacc[1]) + (vacc[2] + vacc[3]), 0.f, 0.f, 0.f)
+                                    : make_float4(lacc[0][0] + lacc[1][0], lacc[0][1] + lacc[1][1],
+                                                  lacc[0][2] + lacc[1][2], lacc[0][3] + lacc[1][3]);
+            tc_fence_before();
+            if (pass + 2 < kFwdTrunks) {
+                __syncthreads();   // every thread has drained this accumulator stage
+                if (tid == 0) {
+                    tc_fence_after();
+                    issue_trunk_mma<KP>(a_base, b_base + (pass + 2) * P::kTrunkBytes, tmem_base + stage * 256,
+                                        bar_stage[stage]);
+                }
+            }
+        }
+        if (half == 1) {
+#pragma unroll
+            for (int pass = 0; pass < kFwdTrunks; ++pass) s_part[lane * kFwdTrunks + pass] = part[pass];
+        }
+        __syncthreads();
+        if (half == 0 && active) {
+            float4 tot[kFwdTrunks];
+#pragma unroll
+            for (int pass = 0; pass < kFwdTrunks; ++pass) {
+                const float4 o = s_part[lane * kFwdTrunks + pass];
+                const float4 bias = *reinterpret_cast<const float4*>(b2 + pass * 4);
+                tot[pass] = make_float4((part[pass].x + o.x) + bias.x, (part[pass].y + o.y) + bias.y,
+                                        (part[pass].z + o.z) + bias.z, (part[pass].w + o.w) + bias.w);
+            }
+            out.v[row] = tot[0].x;
+            out.v_target[row] = tot[2].x;
+            const float heads[3][4] = {{tot[1].x, tot[1].y, tot[1].z, tot[1].w},
+                                       {tot[3].x, tot[3].y, tot[3].z, tot[3].w},
+                                       {tot[4].x, tot[4].y, tot[4].z, tot[4].w}};
+            float* log_dst[3] = {out.log_pi, out.log_pi_reg, out.log_pi_reg_};
+#pragma unroll
+            for (int hnet = 0; hnet < 3; ++hnet) {
+                float logit[A], pi[A], log_pi[A];
+#pragma unroll
+                for (int a = 0; a < A; ++a) logit[a] = heads[hnet][a];
+                policy_heads<A>(logit, mask, pi, log_pi);
+#pragma unroll
+                for (int a = 0; a < A; ++a) {
+                    log_dst[hnet][row * A + a] = log_pi[a];
+                    if (hnet == 0) {
+                        out.logit[row * A + a] = logit[a];
+                        out.pi[row * A + a] = pi[a];
+                    }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc<512>(tmem_base);
+}
+
+// ----------------------------------------------------------------- backward
+
+template <int A>
+struct BwdPlan : Shape<A> {
+    using S = Shape<A>;
+    static constexpr int kHStride = kHidden + 1;                        // fp32 words per row of the activation tile
+    static constexpr int kB = 0;                                        // learner value, policy first layers
+    static constexpr int kB1 = kB + 2 * S::kTrunkBytes;                 // their biases, 2 x 256
+    static constexpr int kImageBytes = kB1 + 2 * kHidden * 4;
+    static constexpr int kA = kImageBytes;                              // A operand tile (tf32)
+    static constexpr int kG = kA + kTileM * S::KP * 4;                  // [128][8]: d_v, d_logit[0..A)
+    static constexpr int kH = kG + kTileM * 32;                         // relu(h) of one trunk, [128][257] f32
+    static constexpr int kXraw = kH + kTileM * kHStride * 4;            // exact fp32 inputs [128][KIN] (if they fit)
+    static constexpr bool kExactX = kXraw + kTileM * S::KIN * 4 + 64 <= 227 * 1024;
+    static constexpr int kBar = round_up(kXraw + (kExactX ? kTileM * S::KIN * 4 : 0), 16);
+    static constexpr int kTmem = kBar + 32;
+    static constexpr int kBytes = kTmem + 16;
+    static_assert(kBytes <= 227 * 1024, "backward tile does not fit in shared memory");
+};
+
+template <int A>
+__global__ void pack_bwd_image_kernel(rnad_mlp_weights w, uint8_t* __restrict__ image) {
+    using P = BwdPlan<A>;
+    const int thread = blockIdx.x * blockDim.x + threadIdx.x, n_threads = gridDim.x * blockDim.x;
+    pack_trunk_operand<P::KIN, P::KP, P::kBiasInK>(w.value_fc0_w, w.value_fc0_b, image + P::kB, thread, n_threads);
+    pack_trunk_operand<P::KIN, P::KP, P::kBiasInK>(w.policy_fc0_w, w.policy_fc0_b, image + P::kB + P::kTrunkBytes,
+                                                   thread, n_threads);
+    for (int j = thread; j < kHidden; j += n_threads) {
+        reinterpret_cast<float*>(image + P::kB1)[j] = w.value_fc0_b[j];
+        reinterpret_cast<float*>(image + P::kB1)[kHidden + j] = w.policy_fc0_b[j];
+    }
+}
+
+template <int A>
+__global__ void __launch_bounds__(kLearnThreads, 1) learner_bwd_kernel(const float* __restrict__ obs, int64_t N,
+                                                                        const uint8_t* __restrict__ image,
+                                                                        rnad_mlp_weights w,
+                                                                        const float* __restrict__ d_logit,
+                                                                        const float* __restrict__ d_v,
+                                                                        float* __restrict__ partials) {
+    using P = BwdPlan<A>;
+    constexpr int KIN = P::KIN, KP = P::KP, HS = P::kHStride;
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & (kTileM - 1), half = tid >> 7;
+    const uint32_t bar_img = smem_u32(smem + P::kBar), bar_stage[2] = {bar_img + 8, bar_img + 16};
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + P::kTmem);
+
+    if (warp == 0) tmem_alloc<512>(tmem_slot);
+    if (tid == 0) {
+        mbar_init(bar_img, 1);
+        mbar_init(bar_stage[0], 1);
+        mbar_init(bar_stage[1], 1);
+        mbar_fence_init();
+        tma_bulk_load(smem, image, P::kImageBytes, bar_img);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    mbar_wait(bar_img, 0);
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tmem_mine = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(half * 128);
+    const uint32_t a_base = smem_u32(smem + P::kA), b_base = smem_u32(smem + P::kB);
+    const float* b1 = reinterpret_cast<const float*>(smem + P::kB1);
+    float* s_g = reinterpret_cast<float*>(smem + P::kG);
+    float* s_h = reinterpret_cast<float*>(smem + P::kH);
+    float* s_x = reinterpret_cast<float*>(smem + P::kXraw);
+
+    // thread j owns hidden unit j of both trunks in the reduction phase
+    const int j = tid;
+    const float w2v_j = w.value_fc1_w[j];
+    float w2p_j[A];
+#pragma unroll
+    for (int a = 0; a < A; ++a) w2p_j[a] = w.policy_fc1_w[a * kHidden + j];
+    float gw1[2][KIN], gb1[2] = {0.f, 0.f}, gw2v = 0.f, gw2p[A], gb2 = 0.f;
+#pragma unroll
+    for (int k = 0; k < KIN; ++k) gw1[0][k] = gw1[1][k] = 0.f;
+#pragma unroll
+    for (int a = 0; a < A; ++a) gw2p[a] = 0.f;
+
+    uint32_t phase[2] = {0u, 0u};
+    const int64_t num_tiles = (N + kTileM - 1) / kTileM;
+    for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int64_t row = tile * kTileM + lane;
+        const bool active = row < N;
+        if (half == 0) {
+            float x[KIN];
+            load_row<KIN>(obs, row, active, x);
+            store_operand_row<KIN, KP, P::kBiasInK>(smem + P::kA, lane, x);
+            if (P::kExactX) {
+#pragma unroll
+                for (int k = 0; k < KIN; ++k) s_x[lane * KIN + k] = x[k];
+            }
+            fence_async_smem();
+        } else {
+            float4 g0 = make_float4(0.f, 0.f, 0.f, 0.f), g1 = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (active) {
+                g0.x = d_v[row];
+                g0.y = d_logit[row * A + 0];
+                if (A > 1) g0.z = d_logit[row * A + 1];
+                if (A > 2) g0.w = d_logit[row * A + 2];
+                if (A > 3) g1.x = d_logit[row * A + 3];
+            }
+            reinterpret_cast<float4*>(s_g + lane * 8)[0] = g0;
+            reinterpret_cast<float4*>(s_g + lane * 8)[1] = g1;
+        }
+        tc_fence_before();
+        __syncthreads();
+        if (tid == 0) {
+            tc_fence_after();
+            issue_trunk_mma<KP>(a_base, b_base, tmem_base + 0, bar_stage[0]);
+            issue_trunk_mma<KP>(a_base, b_base + P::kTrunkBytes, tmem_base + 256, bar_stage[1]);
+        }
+#pragma unroll
+        for (int tr = 0; tr < 2; ++tr) {
+            // ---- activations of this trunk: TMEM -> relu -> shared [row][hidden]
+            mbar_wait(bar_stage[tr], phase[tr]);
+            phase[tr] ^= 1u;
+            tc_fence_after();
+            const uint32_t taddr = tmem_mine + tr * 256;
+            uint32_t ra[32], rb[32];
+            tmem_ld32(taddr, ra);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                tmem_ld_wait();
+                if (c + 1 < 4) {
+                    if (c & 1) tmem_ld32(taddr + (c + 1) * 32, ra);
+                    else tmem_ld32(taddr + (c + 1) * 32, rb);
+                }
+                const int col = half * 128 + c * 32;
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    float h = __uint_as_float((c & 1) ? rb[i] : ra[i]);
+                    if (!P::kBiasInK) h += b1[tr * kHidden + col + i];
+                    s_h[lane * HS + col + i] = fmaxf(h, 0.f);
+                }
+            }
+            tc_fence_before();
+            __syncthreads();
+            // ---- reduce over the 128 rows of the tile, hidden unit j per thread
+            {
+                float acc_w1[KIN], acc_b1 = 0.f, acc_w2[A];
+#pragma unroll
+                for (int k = 0; k < KIN; ++k) acc_w1[k] = 0.f;
+#pragma unroll
+                for (int a = 0; a < A; ++a) acc_w2[a] = 0.f;
+                float acc_b2 = 0.f;
+#pragma unroll 2
+                for (int n = 0; n < kTileM; ++n) {
+                    const float r = s_h[n * HS + j];
+                    const float4 g0 = reinterpret_cast<const float4*>(s_g + n * 8)[0];
+                    float s;
+                    if (tr == 0) {
+                        s = g0.x * w2v_j;
+                        acc_w2[0] = fmaf(g0.x, r, acc_w2[0]);
+                    } else {
+                        const float gl[4] = {g0.y, g0.z, g0.w, A > 3 ? s_g[n * 8 + 4] : 0.f};
+                        s = 0.f;
+#pragma unroll
+                        for (int a = 0; a < A; ++a) {
+                            s = fmaf(gl[a], w2p_j[a], s);
+                            acc_w2[a] = fmaf(gl[a], r, acc_w2[a]);
+                        }
+                    }
+                    if (tr == 0 && j <= A) acc_b2 += s_g[n * 8 + j];   // threads 0..A also sum the output-bias gradients
+                    const float dh = r > 0.f ? s : 0.f;
+                    acc_b1 += dh;
+                    if (P::kExactX) {
+                        const float2* xr = reinterpret_cast<const float2*>(s_x + n * KIN);
+#pragma unroll
+                        for (int k2 = 0; k2 < KIN / 2; ++k2) {
+                            const float2 xv = xr[k2];
+                            acc_w1[2 * k2] = fmaf(dh, xv.x, acc_w1[2 * k2]);
+                            acc_w1[2 * k2 + 1] = fmaf(dh, xv.y, acc_w1[2 * k2 + 1]);
+                        }
+                    } else {
+#pragma unroll
+                        for (int q = 0; q < KIN / 4; ++q) {   // tf32-rounded inputs straight from the operand tile
+                            const float4 xv = *reinterpret_cast<const float4*>(smem + P::kA + operand_offset<KP>(n, 4 * q));
+                            acc_w1[4 * q + 0] = fmaf(dh, xv.x, acc_w1[4 * q + 0]);
+                            acc_w1[4 * q + 1] = fmaf(dh, xv.y, acc_w1[4 * q + 1]);
+                            acc_w1[4 * q + 2] = fmaf(dh, xv.z, acc_w1[4 * q + 2]);
+                            acc_w1[4 * q + 3] = fmaf(dh, xv.w, acc_w1[4 * q + 3]);
+                        }
+                    }
+                }
+#pragma unroll
+                for (int k = 0; k < KIN; ++k) gw1[tr][k] += acc_w1[k];
+                gb1[tr] += acc_b1;
+                if (tr == 0) {
+                    gw2v += acc_w2[0];
+                    gb2 += acc_b2;
+                } else {
+#pragma unroll
+                    for (int a = 0; a < A; ++a) gw2p[a] += acc_w2[a];
+                }
+            }
+            __syncthreads();   // s_h (and after the second trunk: the operand tile, s_g, s_x) may be overwritten
+        }
+    }
+
+    // ---- this CTA's partial gradient, flat in state_dict order
+    float* dst = partials + (int64_t)blockIdx.x * P::kParams;
+#pragma unroll
+    for (int k = 0; k < KIN; ++k) {
+        dst[P::kOffV0w + j * KIN + k] = gw1[0][k];
+        dst[P::kOffP0w + j * KIN + k] = gw1[1][k];
+    }
+    dst[P::kOffV0b + j] = gb1[0];
+    dst[P::kOffP0b + j] = gb1[1];
+    dst[P::kOffV1w + j] = gw2v;
+#pragma unroll
+    for (int a = 0; a < A; ++a) dst[P::kOffP1w + a * kHidden + j] = gw2p[a];
+    if (j == 0) dst[P::kOffV1b] = gb2;
+    else if (j <= A) dst[P::kOffP1b + j - 1] = gb2;
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc<512>(tmem_base);
+}
+
+__global__ void reduce_partials_kernel(const float* __restrict__ partials, int n_parts, int n_params,
+                                       float* __restrict__ flat_grad) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_params) return;
+    float acc = 0.f;
+    for (int p = 0; p < n_parts; ++p) acc += partials[(int64_t)p * n_params + i];
+    flat_grad[i] = acc;
+}
+
+constexpr int kMaxBwdCtas = 160;
+
+template <int A>
+int64_t workspace_bytes() {
+    return round_up(FwdPlan<A>::kImageBytes, 256) + round_up(BwdPlan<A>::kImageBytes, 256) +
+           (int64_t)kMaxBwdCtas * Shape<A>::kParams * 4;
+}
+
+template <int A, typename Kernel>
+int prepare(Kernel kernel, size_t smem, const char* what) {
+    int rc = check_cuda(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), what);
+    if (rc) return rc;
+    return check_cuda(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                           cudaSharedmemCarveoutMaxShared), what);
+}
+
+template <int A>
+int launch_forward(const float* obs, int64_t N, const FwdNets& nets, const FwdOut& out, uint8_t* workspace,
+                   cudaStream_t st) {
+    using P = FwdPlan<A>;
+    static_assert(P::kBytes <= 227 * 1024, "forward image does not fit in shared memory");
+    pack_fwd_image_kernel<A><<<48, 256, 0, st>>>(nets, workspace);
+    RNAD_CHECK_LAUNCH("pack_fwd_image_kernel");
+    int rc = prepare<A>(learner_fwd_kernel<A>, P::kBytes, "cudaFuncSetAttribute(learner_fwd)");
+    if (rc) return rc;
+    int64_t blocks = (N + kTileM - 1) / kTileM;
+    if (blocks > sm_count()) blocks = sm_count();
+    learner_fwd_kernel<A><<<(int)blocks, kLearnThreads, P::kBytes, st>>>(obs, N, workspace, out);
+    RNAD_CHECK_LAUNCH("learner_fwd_kernel");
+    return RNAD_OK;
+}
+
+template <int A>
+int launch_backward(const float* obs, int64_t N, const rnad_mlp_weights& w, const float* d_logit, const float* d_v,
+                    float* flat_grad, uint8_t* workspace, cudaStream_t st) {
+    using P = BwdPlan<A>;
+    uint8_t* image = workspace + round_up(FwdPlan<A>::kImageBytes, 256);
+    float* partials = reinterpret_cast<float*>(image + round_up(P::kImageBytes, 256));
+    pack_bwd_image_kernel<A><<<24, 256, 0, st>>>(w, image);
+    RNAD_CHECK_LAUNCH("pack_bwd_image_kernel");
+    int rc = prepare<A>(learner_bwd_kernel<A>, P::kBytes, "cudaFuncSetAttribute(learner_bwd)");
+    if (rc) return rc;
+    int64_t blocks = (N + kTileM - 1) / kTileM;
+    const int cap = sm_count() < kMaxBwdCtas ? sm_count() : kMaxBwdCtas;
+    if (blocks > cap) blocks = cap;
+    learner_bwd_kernel<A><<<(int)blocks, kLearnThreads, P::kBytes, st>>>(obs, N, image, w, d_logit, d_v, partials);
+    RNAD_CHECK_LAUNCH("learner_bwd_kernel");
+    reduce_partials_kernel<<<(P::kParams + 255) / 256, 256, 0, st>>>(partials, (int)blocks, P::kParams, flat_grad);
+    RNAD_CHECK_LAUNCH("reduce_partials_kernel");
+    return RNAD_OK;
+}
+
+}  // namespace tc
+}  // namespace rnad
+
+using namespace rnad;
+
+static bool weights_ok(const rnad_mlp_weights* w) {
+    return w && w->value_fc0_w && w->value_fc0_b && w->value_fc1_w && w->value_fc1_b && w->policy_fc0_w &&
+           w->policy_fc0_b && w->policy_fc1_w && w->policy_fc1_b;
+}
+
+extern "C" {
+
+int rnad_learner_mlp_supported(int A, int width) { return (width == tc::kHidden && A >= 2 && A <= 4) ? 1 : 0; }
+
+int64_t rnad_learner_mlp_workspace_bytes(int A, int width) {
+    if (!rnad_learner_mlp_supported(A, width)) return 0;
+    switch (A) {
+        case 2: return tc::workspace_bytes<2>();
+        case 3: return tc::workspace_bytes<3>();
+        case 4: return tc::workspace_bytes<4>();
+    }
+    return 0;
+}
+
+int rnad_learner_param_count(int A, int width) {
+    if (!rnad_learner_mlp_supported(A, width)) return 0;
+    return 2 * width * (2 * A * A) + 2 * width + width + 1 + A * width + A;
+}
+
+int rnad_learner_forward(const float* observations, int64_t N, int A, const rnad_mlp_weights* net,
+                         const rnad_mlp_weights* target, const rnad_mlp_weights* reg, const rnad_mlp_weights* reg_,
+                         const rnad_learner_fwd_out* out, void* workspace, void* stream) {
+    RNAD_REQUIRE(observations && out && workspace, "rnad_learner_forward: null pointer");
+    RNAD_REQUIRE(weights_ok(net) && weights_ok(target) && weights_ok(reg) && weights_ok(reg_),
+                 "rnad_learner_forward: null weight pointer");
+    RNAD_REQUIRE(out->logit && out->pi && out->log_pi && out->v && out->v_target && out->log_pi_reg && out->log_pi_reg_,
+                 "rnad_learner_forward: null output pointer");
+    RNAD_REQUIRE(N >= 0, "rnad_learner_forward: negative row count");
+    if (!rnad_learner_mlp_supported(A, net->width) || target->width != net->width || reg->width != net->width ||
+        reg_->width != net->width) {
+        set_error("rnad_learner_forward: needs four nets of width 256 and 2 <= max_actions <= 4");
+        return RNAD_EUNSUPPORTED;
+    }
+    RNAD_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "rnad_learner_forward: workspace must be 256-byte aligned");
+    if (N == 0) return RNAD_OK;
+    tc::FwdNets nets{*net, *target, *reg, *reg_};
+    tc::FwdOut o{out->logit, out->pi, out->log_pi, out->v, out->v_target, out->log_pi_reg, out->log_pi_reg_};
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (A) {
+        case 2: return tc::launch_forward<2>(observations, N, nets, o, (uint8_t*)workspace, st);
+        case 3: return tc::launch_forward<3>(observations, N, nets, o, (uint8_t*)workspace, st);
+        case 4: return tc::launch_forward<4>(observations, N, nets, o, (uint8_t*)workspace, st);
+    }
+    return RNAD_EINVAL;
+}
+
+int rnad_learner_backward(const float* observations, int64_t N, int A, const rnad_mlp_weights* net,
+                          const float* d_logit, const float* d_v, float* flat_grad, void* workspace, void* stream) {
+    RNAD_REQUIRE(observations && d_logit && d_v && flat_grad && workspace, "rnad_learner_backward: null pointer");
+    RNAD_REQUIRE(weights_ok(net), "rnad_learner_backward: null weight pointer");
+    RNAD_REQUIRE(N >= 1, "rnad_learner_backward: empty batch");
+    if (!rnad_learner_mlp_supported(A, net->width)) {
+        set_error("rnad_learner_backward: needs width 256 and 2 <= max_actions <= 4");
+        return RNAD_EUNSUPPORTED;
+    }
+    RNAD_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "rnad_learner_backward: workspace must be 256-byte aligned");
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (A) {
+        case 2: return tc::launch_backward<2>(observations, N, *net, d_logit, d_v, flat_grad, (uint8_t*)workspace, st);
+        case 3: return tc::launch_backward<3>(observations, N, *net, d_logit, d_v, flat_grad, (uint8_t*)workspace, st);
+        case 4: return tc::launch_backward<4>(observations, N, *net, d_logit, d_v, flat_grad, (uint8_t*)workspace, st);
+    }
+    return RNAD_EINVAL;
+}
+
+}  // extern "C"

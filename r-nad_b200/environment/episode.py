@@ -200,17 +200,7 @@ class Episodes:
         if precision is None:
             precision = "tf32" if L.rnad_rollout_tc_supported(a, net.width) else "fp32"
         t_max = packed.max_half_moves
-        w = _b200.MlpWeights()
-        params = {}
-        for layer in ("value_fc0", "value_fc1", "policy_fc0", "policy_fc1"):
-            lin = getattr(net, layer)
-            for suffix, tensor in (("w", lin.weight), ("b", lin.bias)):
-                tensor = tensor.detach()
-                if tensor.dtype != torch.float32 or tensor.device != dev:
-                    raise _b200.RnadError(f"{layer}: the fused rollout needs fp32 weights on {dev}")
-                params[f"{layer}_{suffix}"] = tensor.contiguous()
-                setattr(w, f"{layer}_{suffix}", params[f"{layer}_{suffix}"].data_ptr())
-        w.width = net.width
+        w = _b200.mlp_weights(net, dev)
 
         with torch.cuda.device(dev):
             out = {

@@ -51,6 +51,13 @@ def all_reduce_gradients(parameters) -> int:
     return offset
 
 
+def all_reduce_flat(flat: torch.Tensor) -> None:
+    """Sums an already-flat gradient buffer over ranks in place (the fused learner's params' .grad are views of it)."""
+    d = group()
+    if d is not None:
+        d.all_reduce(flat)
+
+
 def broadcast_parameters(module: torch.nn.Module, src: int = 0) -> None:
     d = group()
     if d is None:

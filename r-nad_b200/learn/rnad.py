@@ -32,6 +32,7 @@ import torch.nn as nn
 import environment.episode as episode
 import environment.tree as tree
 import learn.dp as dp
+import learn.fused as fused
 import learn.vtrace as vtrace
 import nn.net as net
 import util.metric as metric
@@ -122,6 +123,8 @@ class RNaD:
         self.optimizer = None
         self.last_losses = None      # device tensor [loss_v, loss_nerd] of the latest step
         self.nashconv_history = []   # (total_steps, NashConv of the target net)
+        self.learner_engine = None   # None = auto: "fused" tensor-core kernels where supported, else "torch"
+        self._fused = None
 
     # ------------------------------------------------------------------ nets
 
@@ -249,11 +252,21 @@ class RNaD:
 
     def __learn(self, episodes: episode.Episodes, alpha: float, log: dict = None):
         """Gradients of the learner net from a batch of trajectories (rnad.py:353-456)."""
-        logit, log_pi, pi, v = self.net.forward_batch(episodes)
-        with torch.no_grad():
-            _, _, pi_target, v_target = self.net_target.forward_batch(episodes)
-            _, log_pi_reg, _, _ = self.net_reg.forward_batch(episodes)
-            _, log_pi_reg_, _, _ = self.net_reg_.forward_batch(episodes)
+        engine = fused.engine_for(self.net, self.learner_engine)
+        pi_target = None
+        if engine == "fused":
+            if self._fused is None or self._fused.device != next(self.net.parameters()).device:
+                self._fused = fused.FusedLearner(self.net)
+            f = self._fused.forward(episodes.observations[: episodes.t_eff + 1], self.net, self.net_target,
+                                    self.net_reg, self.net_reg_)
+            logit, log_pi, pi, v = f["logit"], f["log_pi"], f["pi"], f["v"]
+            v_target, log_pi_reg, log_pi_reg_ = f["v_target"], f["log_pi_reg"], f["log_pi_reg_"]
+        else:
+            logit, log_pi, pi, v = self.net.forward_batch(episodes)
+            with torch.no_grad():
+                _, _, pi_target, v_target = self.net_target.forward_batch(episodes)
+                _, log_pi_reg, _, _ = self.net_reg.forward_batch(episodes)
+                _, log_pi_reg_, _, _ = self.net_reg_.forward_batch(episodes)
 
         global_counts = None
         if dp.group() is not None:
@@ -267,28 +280,34 @@ class RNaD:
             beta=self.beta, value_weight=self.value_weight, neurd_weight=self.neurd_weight,
             global_counts=global_counts)
         self.last_losses = out.losses
-        torch.autograd.backward([logit, v], [out.d_logit, out.d_v.unsqueeze(-1)])
-
-        dp.all_reduce_gradients(self.net.parameters())   # no-op unless torch.distributed is initialised
+        if engine == "fused":
+            flat = self._fused.backward(episodes.observations[: episodes.t_eff + 1], self.net, out.d_logit, out.d_v)
+            dp.all_reduce_flat(flat)                      # the params' .grad are views of this buffer
+        else:
+            torch.autograd.backward([logit, v], [out.d_logit, out.d_v.unsqueeze(-1)])
+            dp.all_reduce_gradients(self.net.parameters())   # no-op unless torch.distributed is initialised
 
         if log is not None:
-            valid = (episodes.indices != 0).to(torch.float)
-            masks = episodes.masks
-            total_norm = torch.sqrt(sum(p.grad.detach().pow(2).sum() for p in self.net.parameters())).item()
-            logit_mean = logit.mean().item()
-            uniform_policy = torch.nn.functional.normalize(masks, p=1, dim=-1)
-            losses = out.losses.tolist()   # under data parallelism: this rank's share of the global loss
-            log.update({
-                "loss_v": losses[0],
-                "loss_nerd": losses[1],
-                "traj_len": valid.sum(0).mean(-1).item(),
-                "gradient_norm": total_norm,
-                "logit_mean": logit_mean,
-                "logit_max": torch.max(torch.abs(logit - logit_mean)).item(),
-                "entropy": metric.kld(pi, uniform_policy, valid, legal_actions=masks),
-                "entropy_target": metric.kld(pi_target, uniform_policy, valid, legal_actions=masks),
-                "actor_learner_kld": metric.kld(pi, episodes.policy, valid, legal_actions=masks),
-            })
+            with torch.no_grad():
+                if pi_target is None:
+                    _, _, pi_target, _ = self.net_target.forward_batch(episodes)
+                valid = (episodes.indices != 0).to(torch.float)
+                masks = episodes.masks
+                total_norm = torch.sqrt(sum(p.grad.detach().pow(2).sum() for p in self.net.parameters())).item()
+                logit_mean = logit.mean().item()
+                uniform_policy = torch.nn.functional.normalize(masks, p=1, dim=-1)
+                losses = out.losses.tolist()   # under data parallelism: this rank's share of the global loss
+                log.update({
+                    "loss_v": losses[0],
+                    "loss_nerd": losses[1],
+                    "traj_len": valid.sum(0).mean(-1).item(),
+                    "gradient_norm": total_norm,
+                    "logit_mean": logit_mean,
+                    "logit_max": torch.max(torch.abs(logit - logit_mean)).item(),
+                    "entropy": metric.kld(pi, uniform_policy, valid, legal_actions=masks),
+                    "entropy_target": metric.kld(pi_target, uniform_policy, valid, legal_actions=masks),
+                    "actor_learner_kld": metric.kld(pi, episodes.policy, valid, legal_actions=masks),
+                })
 
         nn.utils.clip_grad_norm_(self.net.parameters(), self.grad_clip)
 

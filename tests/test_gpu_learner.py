@@ -138,6 +138,7 @@ def test_rnad_learn_gradients_match_reference(golden):
     for attr, prefix in (("net", "learner"), ("net_target", "target"), ("net_reg", "reg"), ("net_reg_", "reg_")):
         setattr(trial, attr, mlp_from_golden(g, prefix, DEV))
     trial.net.train()
+    trial.learner_engine = "torch"          # fp32 batched GEMMs + autograd: the exact-parity engine
     trial._RNaD__learn(ep, alpha)
     for k, p in trial.net.named_parameters():
         close(cpu(p.grad), g[f"rnad_grad.{k}"], rtol=2e-5, atol=2e-7)
@@ -244,3 +245,124 @@ def test_rnad_short_run_reduces_exploitability():
     after = (data.row_best[1] + data.col_best[1]).item()
     print(f"NashConv before {before:.4f} after 600 steps {after:.4f}; history {trial.nashconv_history}")
     assert after < 0.5 * before and after < 0.2
+
+
+# ----------------------------------------------------------- fused learner net passes (tcgen05, tf32)
+
+def _four_nets(a, seed):
+    from nn.net import MLP
+
+    torch.manual_seed(seed)
+    nets = []
+    for _ in range(4):
+        net = MLP(a, 256)
+        with torch.no_grad():
+            for p in net.parameters():
+                p.mul_(1.5)
+        nets.append(net)
+    weights = [{k: v.detach().clone() for k, v in n.state_dict().items()} for n in nets]
+    for n in nets:
+        n.to(DEV)
+        n.device = torch.device(DEV)
+    return nets, weights
+
+
+def _random_observations(a, T, B, seed):
+    gen = torch.Generator().manual_seed(seed)
+    ev = torch.rand(T, B, a, a, generator=gen) * 2 - 1
+    rows = torch.randint(1, a + 1, (T, B, 1, 1), generator=gen)
+    cols = torch.randint(1, a + 1, (T, B, 1, 1), generator=gen)
+    legal = ((torch.arange(a).view(1, 1, a, 1) < rows) & (torch.arange(a).view(1, 1, 1, a) < cols)).float()
+    return torch.stack([ev * legal, legal], dim=2).contiguous()
+
+
+@pytest.mark.parametrize("a,T,B", [(2, 4, 300), (3, 8, 4099), (4, 5, 2048), (3, 1, 1)])
+def test_fused_learner_forward_vs_oracle(a, T, B):
+    import learn.fused as fused
+
+    nets, weights = _four_nets(a, 5 + a)
+    obs = _random_observations(a, T, B, 17)
+    assert fused.supported(nets[0])
+    fl = fused.FusedLearner(nets[0])
+    out = fl.forward(obs.to(DEV), *nets)
+    ref_net = orc.mlp_forward_batch(weights[0], obs)
+    ref_tgt = orc.mlp_forward_batch(weights[1], obs)
+    ref_reg = orc.mlp_forward_batch(weights[2], obs)
+    ref_reg_ = orc.mlp_forward_batch(weights[3], obs)
+    tol = dict(rtol=0, atol=5e-3)             # tf32 first layer (10-bit mantissa), fp32 everywhere else
+    close(cpu(out["logit"]), ref_net[0], **tol)
+    close(cpu(out["log_pi"]), ref_net[1], **tol)
+    close(cpu(out["pi"]), ref_net[2], **tol)
+    close(cpu(out["v"]), ref_net[3], **tol)
+    close(cpu(out["v_target"]), ref_tgt[3], **tol)
+    close(cpu(out["log_pi_reg"]), ref_reg[1], **tol)
+    close(cpu(out["log_pi_reg_"]), ref_reg_[1], **tol)
+    mask = obs[:, :, 1, :, 0]
+    assert bool((cpu(out["pi"])[mask == 0] == 0).all()) and bool((cpu(out["log_pi"])[mask == 0] == 0).all())
+    close(cpu(out["pi"]).sum(-1), torch.ones(T, B), rtol=0, atol=1e-6)
+    err = (cpu(out["logit"]) - ref_net[0]).abs().max().item()
+    print(f"fused forward A={a}: max |logit error| = {err:.2e}")
+
+
+@pytest.mark.parametrize("a,T,B", [(2, 4, 300), (3, 8, 4099), (4, 5, 2048), (3, 2, 77)])
+def test_fused_learner_backward_vs_autograd(a, T, B):
+    import learn.fused as fused
+    from nn.net import MLP
+
+    nets, weights = _four_nets(a, 9 + a)
+    obs = _random_observations(a, T, B, 23)
+    gen = torch.Generator().manual_seed(3)
+    d_logit = torch.randn(T, B, a, generator=gen) / (T * B)
+    d_v = torch.randn(T, B, generator=gen) / (T * B)
+    d_logit[:, ::3] = 0                       # invalid / opponent steps carry exact zeros
+    d_v[:, ::3] = 0
+    ref = MLP(a, 256)
+    ref.load_state_dict(weights[0])
+
+    class Ep:
+        pass
+
+    ep = Ep()
+    ep.observations, ep.t_eff = obs, T - 1
+    logit, _, _, v = ref.forward_batch(ep)
+    torch.autograd.backward([logit, v], [d_logit, d_v.unsqueeze(-1)])
+    fl = fused.FusedLearner(nets[0])
+    flat = fl.backward(obs.to(DEV), nets[0], d_logit.to(DEV), d_v.to(DEV))
+    assert flat.numel() == sum(p.numel() for p in ref.parameters())
+    for (name, p_ref), p_gpu in zip(ref.named_parameters(), nets[0].parameters()):
+        got, want = cpu(p_gpu.grad), p_ref.grad
+        rel = (got - want).norm() / want.norm().clamp_min(1e-30)
+        assert rel < 3e-3, f"{name}: relative gradient error {rel:.2e}"
+        cos = torch.nn.functional.cosine_similarity(got.flatten(), want.flatten(), dim=0)
+        assert cos > 0.99999, f"{name}: cosine {cos:.7f}"
+    # deterministic: a second call gives the same bits
+    again = fl.backward(obs.to(DEV), nets[0], d_logit.to(DEV), d_v.to(DEV)).clone()
+    assert torch.equal(again, fl.flat_grad)
+
+
+def test_rnad_learn_fused_engine_tracks_reference(golden):
+    """Default (fused, tf32) engine on the reference's episodes: gradients within tf32 noise of the reference's."""
+    from learn.rnad import RNaD
+    import learn.fused as fused
+
+    name, g = golden
+    a, width = int(g["meta"][0]), int(g["meta"][3])
+    tree = tree_from_golden(g, DEV)
+    ep = episodes_from_golden(g, tree, DEV)
+    eta, gamma, c_bar, rho_bar, alpha = (float(x) for x in g["scalars"])
+    trial = RNaD(tree=tree, device=torch.device(DEV), directory_name=f"pytest_fused_{name}", eta=eta,
+                 batch_size=ep.batch_size, vtrace_gamma=gamma, c_bar=c_bar, roh_bar=rho_bar,
+                 net_params={"type": "MLP", "max_actions": a, "width": width})
+    for attr, prefix in (("net", "learner"), ("net_target", "target"), ("net_reg", "reg"), ("net_reg_", "reg_")):
+        setattr(trial, attr, mlp_from_golden(g, prefix, DEV))
+    expected = "fused" if width == 256 and 2 <= a <= 4 else "torch"
+    assert fused.engine_for(trial.net) == expected
+    trial._RNaD__learn(ep, alpha)
+    flat_got = torch.cat([cpu(p.grad).flatten() for p in trial.net.parameters()])
+    flat_ref = torch.cat([t(g[f"rnad_grad.{k}"]).flatten() for k, _ in trial.net.named_parameters()])
+    rel = ((flat_got - flat_ref).norm() / flat_ref.norm()).item()
+    print(f"{name}: engine={expected} relative gradient error {rel:.2e}")
+    assert rel < (2e-2 if expected == "fused" else 1e-4)
+    losses = cpu(trial.last_losses)
+    close(losses[0], g["loss_v"], rtol=1e-2, atol=1e-3)
+    close(losses[1], g["loss_nerd"], rtol=1e-2, atol=2e-3)
