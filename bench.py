@@ -337,7 +337,8 @@ def run_native(args):
             "metric": "self_play_env_steps_per_sec", "value": value, "unit": "env_steps/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": kernel_ms / args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "tf32 (tcgen05, fp32 accumulate) + fp32" if precision == "tf32" else "fp32",
+            "vs_baseline": None, "dtype": {"tf32": "tf32 (tcgen05, fp32 accumulate) + fp32", "tf32x2": "tf32 (tcgen05, fp32 accumulate)",
+                                          "fp32": "fp32"}[precision],
             "data": "synthetic",
             "config": {"workload": f"{args.config}: depth={depth} max_actions={a} max_transitions={c} regular tree "
                                    f"({n_nodes} nodes), batch={batch} games per GPU, T={T} half-moves, MLP width 256, "
@@ -353,7 +354,8 @@ def run_native(args):
             "gpu_launches": args.steps * runner.launches_per_step,
             "roofline": {"bound": "hbm", "achieved": achieved_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                          "frac": achieved_gbs / peaks["hbm_gbs"], "traffic": None,
-                         "kernel": "rollout_tc_kernel" if precision == "tf32" else "rollout_fp32_kernel",
+                         "kernel": {"tf32": "rollout_tc_kernel", "tf32x2": "rollout_tc2_kernel",
+                                    "fp32": "rollout_fp32_kernel"}[precision],
                          "algorithmic_bytes_per_env_step": algorithmic_bytes_per_env_step(a, c),
                          "peak_source": peaks["source"]},
             "roofline_tensor": {"achieved": tflops, "unit": "TFLOP/s (algorithmic MLP flops)",
@@ -429,7 +431,7 @@ def main():
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--config", default="cfg2", choices=sorted(CONFIGS))
     ap.add_argument("--batch", type=int, default=0, help="games per GPU (default: the config's)")
-    ap.add_argument("--precision", default="tf32", choices=["tf32", "fp32"])
+    ap.add_argument("--precision", default="tf32", choices=["tf32", "tf32x2", "fp32"])
     ap.add_argument("--cpu-budget", type=float, default=15.0, help="seconds of CPU work for cpu_baseline")
     ap.add_argument("--reference-batch", type=int, default=65536)
     args = ap.parse_args()

@@ -39,6 +39,7 @@ extern "C" {
 /* precision / engine selector of the fused rollout */
 #define RNAD_PREC_FP32 0 /* FFMA on the CUDA cores, fp32 throughout (validation build) */
 #define RNAD_PREC_TF32 1 /* first layer on tcgen05 tensor cores, kind::tf32, fp32 accumulate in TMEM */
+#define RNAD_PREC_TF32X2 2 /* both layers on tcgen05 (kind::tf32); the second reads relu(hidden) from tensor memory */
 
 #define RNAD_MAX_ACTIONS 8
 #define RNAD_MAX_TRANSITIONS 8

@@ -157,6 +157,63 @@ def mlp_forward(w, obs_flat):
     return logits, policy, value, e
 
 
+def tf32_rna(x: torch.Tensor) -> torch.Tensor:
+    """fp32 -> tf32 (10-bit mantissa) as PTX `cvt.rna.tf32.f32`: nearest, ties away from zero."""
+    bits = x.detach().to(torch.float32).contiguous().view(torch.int32)
+    out = ((bits + 0x1000) & ~0x1FFF).view(torch.float32)
+    return torch.where(torch.isfinite(x), out, x)
+
+
+def tf32_trunc(x: torch.Tensor) -> torch.Tensor:
+    """What the tensor core does to an fp32 operand it is handed as tf32: the low 13 mantissa bits are ignored."""
+    bits = x.detach().to(torch.float32).contiguous().view(torch.int32)
+    return (bits & ~0x1FFF).view(torch.float32)
+
+
+def tc_bias_in_k(A: int) -> bool:
+    """
+    Whether the tensor-core engines carry the first-layer bias as a constant-1 input column (then it is
+    tf32-rounded like a weight) or add it in fp32 after the MMA: in K when 2A^2 is not a multiple of the
+    tf32 MMA K of 8, i.e. when K has padding to spare.
+    """
+    return (2 * A * A) % 8 != 0
+
+
+def mlp_forward_tc(w, obs_flat, second_layer="fp32", dtype=torch.float64):
+    """
+    Emulation of the NUMERICS of the tensor-core engines for `MLP.forward` (net.py:37-47), evaluated in
+    float64 so that only the engines' accumulation order is left as a difference:
+      first layers   x, W (and the bias when it rides in K) rounded to tf32 (cvt.rna), exact products,
+                     wide accumulation;
+      second layers  second_layer="fp32" (precision "tf32" rollout engine, learner kernels): fp32 operands;
+                     second_layer="tf32" (precision "tf32x2" rollout engine): relu(h) in fp32 truncated to
+                     tf32 by the tensor core, W rounded to tf32 (cvt.rna), bias added in fp32.
+    Returns logits, policy, value, exp_logits, hidden_value, hidden_policy (pre-activation) in `dtype`.
+    """
+    A = w["policy_fc1.weight"].shape[0]
+    bias_k = tc_bias_in_k(A)
+    x = tf32_rna(obs_flat).to(dtype)
+    mask = obs_flat[:, A * A: 2 * A * A: A] != 0
+
+    def trunk(name):
+        w0 = tf32_rna(w[name + "_fc0.weight"]).to(dtype)
+        b0 = (tf32_rna(w[name + "_fc0.bias"]) if bias_k else w[name + "_fc0.bias"]).to(dtype)
+        pre = x @ w0.T + b0
+        h = torch.relu(pre)
+        if second_layer == "tf32":
+            h = tf32_trunc(h.to(torch.float32)).to(dtype)
+            w1 = tf32_rna(w[name + "_fc1.weight"]).to(dtype)
+        else:
+            w1 = w[name + "_fc1.weight"].to(dtype)
+        return pre, h @ w1.T + w[name + "_fc1.bias"].to(dtype)
+
+    pre_v, value = trunk("value")
+    pre_p, logits = trunk("policy")
+    e = torch.where(mask, torch.exp(logits), torch.zeros_like(logits))
+    policy = e / torch.clamp_min(e.sum(-1, keepdim=True), 1e-12)
+    return logits, policy, value, e, pre_v, pre_p
+
+
 def mlp_forward_batch(w, observations):
     """
     `MLP.forward_batch` (net.py:64-85) on (T,B,2,A,A) observations, all T at

@@ -15,11 +15,12 @@ from ctypes import POINTER, Structure, c_float, c_int, c_int32, c_int64, c_uint6
 import torch
 
 _HERE = os.path.dirname(os.path.realpath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "librnad_b200.so")
+LIB_PATH = os.environ.get("RNAD_B200_LIB") or os.path.join(_HERE, "lib", "librnad_b200.so")   # override: development builds
 
 PREC_FP32 = 0
 PREC_TF32 = 1
-PRECISIONS = {"fp32": PREC_FP32, "tf32": PREC_TF32}
+PREC_TF32X2 = 2
+PRECISIONS = {"fp32": PREC_FP32, "tf32": PREC_TF32, "tf32x2": PREC_TF32X2}
 
 EXPORTS = (
     "rnad_last_error", "rnad_version", "rnad_device_sm_count", "rnad_packed_strides", "rnad_tree_pack",

@@ -301,7 +301,16 @@ def test_fused_learner_forward_vs_oracle(a, T, B):
     assert bool((cpu(out["pi"])[mask == 0] == 0).all()) and bool((cpu(out["log_pi"])[mask == 0] == 0).all())
     close(cpu(out["pi"]).sum(-1), torch.ones(T, B), rtol=0, atol=1e-6)
     err = (cpu(out["logit"]) - ref_net[0]).abs().max().item()
-    print(f"fused forward A={a}: max |logit error| = {err:.2e}")
+    # tight check against the engine's numerics restated on the CPU (tf32-rounded first-layer operands, fp64
+    # accumulation): what is left is the fp32 accumulation order of the MMA and of the second layer
+    flat = obs.reshape(T * B, -1)
+    for key_l, key_v, wts in (("logit", "v", weights[0]), (None, "v_target", weights[1])):
+        e_logit, _, e_v, _, _, _ = orc.mlp_forward_tc(wts, flat)
+        if key_l:
+            close(cpu(out[key_l]).double().reshape(T * B, a), e_logit, rtol=0, atol=2e-5)
+        close(cpu(out[key_v]).double().reshape(T * B, 1), e_v, rtol=0, atol=2e-5)
+    err_tc = (cpu(out["logit"]).double().reshape(T * B, a) - orc.mlp_forward_tc(weights[0], flat)[0]).abs().max().item()
+    print(f"fused forward A={a}: max |logit error| = {err:.2e} vs fp32 net, {err_tc:.2e} vs tf32-aware oracle")
 
 
 @pytest.mark.parametrize("a,T,B", [(2, 4, 300), (3, 8, 4099), (4, 5, 2048), (3, 2, 77)])
@@ -316,6 +325,24 @@ def test_fused_learner_backward_vs_autograd(a, T, B):
     d_v = torch.randn(T, B, generator=gen) / (T * B)
     d_logit[:, ::3] = 0                       # invalid / opponent steps carry exact zeros
     d_v[:, ::3] = 0
+    # Reference = autograd (float64) through the engine's own forward numerics (oracle.mlp_forward_tc: tf32-rounded
+    # first-layer operands, straight-through), so that the relu masks agree and the comparison is tight.  Against
+    # the plain fp32 net the two differ by the ~1e-3 of hidden units whose pre-activation changes sign under
+    # tf32 rounding (relative gradient error ~2e-2 on this synthetic input) - checked loosely below.
+    w64 = {k: v.double().requires_grad_(True) for k, v in weights[0].items()}
+    bias_k = orc.tc_bias_in_k(a)
+    x = orc.tf32_rna(obs.reshape(T * B, -1)).double()
+
+    def trunk(name):
+        w0 = w64[name + "_fc0.weight"]
+        w0r = w0 + (orc.tf32_rna(weights[0][name + "_fc0.weight"]).double() - w0).detach()
+        b0 = w64[name + "_fc0.bias"]
+        b0r = b0 + (orc.tf32_rna(weights[0][name + "_fc0.bias"]).double() - b0).detach() if bias_k else b0
+        h = torch.relu(x @ w0r.T + b0r)
+        return h @ w64[name + "_fc1.weight"].T + w64[name + "_fc1.bias"]
+
+    v64, logit64 = trunk("value"), trunk("policy")
+    torch.autograd.backward([logit64, v64], [d_logit.reshape(T * B, a).double(), d_v.reshape(T * B, 1).double()])
     ref = MLP(a, 256)
     ref.load_state_dict(weights[0])
 
@@ -330,11 +357,13 @@ def test_fused_learner_backward_vs_autograd(a, T, B):
     flat = fl.backward(obs.to(DEV), nets[0], d_logit.to(DEV), d_v.to(DEV))
     assert flat.numel() == sum(p.numel() for p in ref.parameters())
     for (name, p_ref), p_gpu in zip(ref.named_parameters(), nets[0].parameters()):
-        got, want = cpu(p_gpu.grad), p_ref.grad
+        got, want = cpu(p_gpu.grad).double(), w64[name].grad
         rel = (got - want).norm() / want.norm().clamp_min(1e-30)
-        assert rel < 3e-3, f"{name}: relative gradient error {rel:.2e}"
-        cos = torch.nn.functional.cosine_similarity(got.flatten(), want.flatten(), dim=0)
-        assert cos > 0.99999, f"{name}: cosine {cos:.7f}"
+        assert rel < 1e-3, f"{name}: relative gradient error vs the tf32-aware reference {rel:.2e}"
+        rel32 = (got - p_ref.grad.double()).norm() / p_ref.grad.double().norm().clamp_min(1e-30)
+        assert rel32 < 6e-2, f"{name}: relative gradient error vs the fp32 net {rel32:.2e}"
+        cos = torch.nn.functional.cosine_similarity(got.flatten(), p_ref.grad.double().flatten(), dim=0)
+        assert cos > 0.998, f"{name}: cosine {cos:.7f}"
     # deterministic: a second call gives the same bits
     again = fl.backward(obs.to(DEV), nets[0], d_logit.to(DEV), d_v.to(DEV)).clone()
     assert torch.equal(again, fl.flat_grad)
