@@ -137,6 +137,8 @@ RNAD_API int64_t rnad_rollout_workspace_bytes(int A, int width, int precision);
 
 /* 1 if the RNAD_PREC_TF32 engine serves this net shape (width == 256, 2 <= A <= 4), else 0 */
 RNAD_API int rnad_rollout_tc_supported(int A, int width);
+/* 1 if the RNAD_PREC_TF32X2 engine serves this shape (width == 256, 2 <= A <= 4, max_transitions C <= 4), else 0 */
+RNAD_API int rnad_rollout_tc2_supported(int A, int width, int C);
 
 /* ------------------------------------------------------------------------
  * K3  learn/vtrace.py + learn/rnad.py:368-425

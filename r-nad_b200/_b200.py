@@ -93,6 +93,7 @@ def lib():
     L.rnad_rollout_workspace_bytes.restype = c_int64
     L.rnad_rollout_workspace_bytes.argtypes = [c_int, c_int, c_int]
     L.rnad_rollout_tc_supported.argtypes = [c_int, c_int]
+    L.rnad_rollout_tc2_supported.argtypes = [c_int, c_int, c_int]
     L.rnad_process_policy.argtypes = [c_void_p, c_void_p, c_int64, c_int, c_int, c_float, c_void_p, c_void_p]
     L.rnad_vtrace.argtypes = [c_void_p] * 9 + [c_int] + [c_float] * 5 + [c_int, c_int64, c_int] + [c_void_p] * 4
     L.rnad_learner_targets_workspace.restype = c_int64

@@ -48,6 +48,9 @@ extern "C" int rnad_rollout(const uint32_t* ev_tab, const uint32_t* tr_tab, int 
 // 1 if the tensor-core engine serves this net shape, else 0
 extern "C" int rnad_rollout_tc_supported(int A, int width) { return rollout_tc_supported(A, width) ? 1 : 0; }
 
+// 1 if the RNAD_PREC_TF32X2 engine serves this net and tree shape, else 0
+extern "C" int rnad_rollout_tc2_supported(int A, int width, int C) { return rollout_tc2_supported(A, width, C) ? 1 : 0; }
+
 // bytes of device scratch rnad_rollout needs for this net shape and engine (0 = none)
 extern "C" int64_t rnad_rollout_workspace_bytes(int A, int width, int precision) {
     if (precision == RNAD_PREC_TF32 && rollout_tc_supported(A, width)) return rollout_tc_workspace_bytes(A);

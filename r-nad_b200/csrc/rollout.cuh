@@ -25,5 +25,6 @@ bool rollout_tc_supported(int A, int width);
 int64_t rollout_tc_workspace_bytes(int A);
 int rollout_tc2(const RolloutArgs& g, void* workspace, cudaStream_t st);
 int64_t rollout_tc2_workspace_bytes(int A);
+bool rollout_tc2_supported(int A, int width, int C);
 
 }  // namespace rnad

@@ -1,29 +1,34 @@
 // K2, tensor-core build with BOTH layers of the net on tcgen05 (RNAD_PREC_TF32X2):
 // Episodes.generate fused with MLP.forward as a persistent, warp-specialised kernel.
 //
-// A CTA owns a tile of 128 games for all T half-moves; game g of the tile is TMEM
-// lane g.  Nine warps:
+// One CTA per SM owns all 512 TMEM columns and keeps TWO tiles of 128 games ("sides")
+// in flight, half a step out of phase: while the tensor core and the epilogue warps
+// work on one side's half-move, the other side's head warps sample actions, advance
+// the games and publish the next observations.  Game g of a tile is TMEM lane g.
 //
-//   warp 8 (one lane)   issues every tcgen05.mma.  Per half-move the 512 hidden units
-//                       (value trunk | policy trunk) are processed as 8 chunks of 64
-//                       through a ring of three 64-column TMEM slots:
-//                         MMA1(c)  D[128 x 64]  = obs[128 x KP] (smem) x W1_c^T (smem)   kind::tf32
-//                         MMA2(c)  D2[128 x 16] += relu(D)[128 x 64] (TMEM) x W2_c^T (smem)
-//                       i.e. the second layers read their A operand straight from tensor
-//                       memory; column 0 of D2 is the value, columns 1..A the logits.
-//   warps 0..7          epilogue of MMA1: tcgen05.ld 32 columns, relu (the bias rides in K
-//                       as a constant-1 input column where K has padding, else one FADD),
-//                       tcgen05.st back in place, arrive on the chunk's mbarrier.  This
-//                       is all the CUDA cores do per hidden unit: one FMNMX.
-//   warps 0..3          head: read D2, masked softmax, Philox inverse-CDF action draw,
-//                       chance draw + child gather on column half-moves, trajectory
-//                       record, next observation -> A-operand tile (tf32) + fp32 staging.
-//   warps 4..7          copy the staged observations of the tile (one contiguous block of
-//                       the (T,B,2,A,A) tensor) to HBM with coalesced 16-byte stores.
+//   warp 16 (elected lane)  issues every tcgen05.mma as ONE stream of chunks
+//                           (side 0, t) c0..c3, (side 1, t) c0..c3, (side 0, t+1) ...
+//                           A chunk is 128 hidden units of [value trunk | policy trunk]:
+//                             MMA1  D[128 x 128]  = obs[128 x KP] (TMEM) x W1_c^T (smem)      kind::tf32, 3 slots
+//                             MMA2  D2[128 x 16] += relu(D)[128 x 128] (TMEM) x W2_c^T (smem)
+//                           both with the A operand in tensor memory; column 0 of D2 is the
+//                           value, columns 1..A the logits.
+//   warps 8..15             epilogue of MMA1: tcgen05.ld, relu (the bias rides in K as a
+//                           constant-1 input column where K has padding, else one FADD),
+//                           tcgen05.st back in place, arrive on the slot's mbarrier.  One
+//                           FMNMX per hidden unit is all the CUDA cores do for the net.
+//   warps 0..3 / 4..7       heads of side 0 / 1, one thread per game: read D2, masked
+//                           softmax, Philox inverse-CDF action draw, next observation ->
+//                           tensor memory (tf32).  Off the critical path (the tensor core is
+//                           busy with the other side): trajectory record, fp32 observations
+//                           (staged per warp, stored as coalesced 16-byte words), the next
+//                           uniforms, and on row half-moves the chance draw + child gather
+//                           for EVERY column action the opponent may pick, parked in shared
+//                           memory - so that no global load sits between a column action and
+//                           the next observation.
 //
-// Everything is ordered by mbarriers (no CTA-wide barrier inside the rollout); two CTAs
-// per SM (256 TMEM columns each) overlap one tile's head with the other's MMAs.
-// The weights arrive as ONE TMA bulk copy of an image a pre-kernel lays out in operand
+// Everything is ordered by mbarriers; no CTA-wide barrier inside the rollout.  The
+// weights arrive as ONE TMA bulk copy of an image a pre-kernel lays out in operand
 // order.  Reference: environment/episode.py:175-230, nn/net.py:37-51.
 #include "game.cuh"
 #include "rollout.cuh"
@@ -34,61 +39,58 @@ namespace tc2 {
 
 using namespace rnad::tc;
 
-constexpr int kHeadWarps = 4;              // warps 0..3: one thread per game
+constexpr int kSides = 2;                        // tiles in flight per CTA
+constexpr int kHeadWarps = 4 * kSides;           // warps 0..7: one thread per game
 #ifndef RNAD_TC2_EPI_WARPS
 #define RNAD_TC2_EPI_WARPS 8
 #endif
-constexpr int kEpiWarps = RNAD_TC2_EPI_WARPS;   // warps 4..: relu epilogue of the first layers (4 or 8)
-constexpr int kMmaWarp = kHeadWarps + kEpiWarps;
-constexpr int kThreads = (kMmaWarp + 1) * 32;
-constexpr int kChunk = 64;                 // hidden units per pipeline stage
-constexpr int kChunks = 2 * kHidden / kChunk;
+constexpr int kEpiWarps = RNAD_TC2_EPI_WARPS;    // relu epilogue warps (8 or 16)
+constexpr int kMmaWarp = kHeadWarps + kEpiWarps;   // first of the two MMA warps (they take alternate stream items)
+constexpr int kMmaWarps = 2;
+constexpr int kThreads = (kMmaWarp + kMmaWarps) * 32;
+constexpr int kChunk = 128;                      // hidden units per pipeline stage
+constexpr int kChunks = 2 * kHidden / kChunk;    // per side and half-move
 constexpr int kSlots = 3;
-constexpr int kD2Col = kSlots * kChunk;    // 16 columns of second-layer accumulators
-constexpr int kObsCol = kD2Col + 16;       // up to 32 columns: the observations, A operand of the first layers
-constexpr int kTmemCols = 256;
-constexpr int kN2 = 16;                    // N of the second-layer MMA (smallest legal at M = 128)
-constexpr int kK2 = 2 * kHidden;           // its K: value trunk | policy trunk
+constexpr int kSideCol = kSlots * kChunk;        // per side 64 columns: 16 of second-layer accumulators, 32 of observations
+constexpr int kTmemCols = 512;
+constexpr int kN2 = 16;                          // N of the second-layer MMA (smallest legal at M = 128)
+constexpr int kK2 = 2 * kHidden;                 // its K: value trunk | policy trunk
+
+// per side: two second-layer accumulators of 16 columns (even / odd chunks, one per MMA warp), then the observations
+__host__ __device__ constexpr int d2_col(int side) { return kSideCol + 64 * side; }
+__host__ __device__ constexpr int obs_col(int side) { return kSideCol + 64 * side + 32; }
 
 template <int A>
 struct Plan {
     static constexpr int KIN = 2 * A * A;
     static constexpr bool kBiasInK = (KIN % 8) != 0;
     static constexpr int KP = round_up(KIN + (kBiasInK ? 1 : 0), 8);
-    static constexpr bool kStage = A < 4;                            // A = 4: a row is one 128-byte line, stored directly
+    static constexpr int kCandWords = A * A + 3;                     // child, reward, ev[A*A], rows|cols
     static constexpr int kSbo1 = (KP / 4) * 128;                     // bytes between 8-row groups of a [rows x KP] operand
     static constexpr int kW1 = 0;                                    // [512 x KP] tf32
     static constexpr int kW2 = kW1 + 2 * kHidden * KP * 4;           // rows 0..7 of [16 x 512] tf32 (rows 8..15 alias what follows)
     static constexpr int kB1 = kW2 + 8 * kK2 * 4;                    // first-layer biases, 512 f32 (used when !kBiasInK)
     static constexpr int kB2 = kB1 + 2 * kHidden * 4;                // value bias, policy biases (8 f32)
     static constexpr int kImageBytes = kB2 + 32;
-    static constexpr int kObs = kImageBytes;                         // fp32 observation staging [128 x KIN]
-    static constexpr int kBar = kObs + (kStage ? kTileM * KIN * 4 : 0);
-    static constexpr int kNumBars = 2 + 2 * kSlots + 1;              // image, A-ready, d1[3], relu[3], d2
+    static constexpr int kObs = kImageBytes;                         // fp32 observation staging, [side][128 x KIN]
+    static constexpr int kCand = kObs + kSides * kTileM * KIN * 4;   // transition candidates, [side][A][kCandWords][128]
+    static constexpr int kBar = kCand + kSides * A * kCandWords * kTileM * 4;
+    static constexpr int kNumBars = 1 + kSides + 2 * kSlots + kSides;   // image, obs-ready[2], d1[3], relu[3], d2[2]
     static constexpr int kTmem = kBar + 8 * kNumBars;
     static constexpr int kBytes = kTmem + 16;
     // the second 8-row group of the W2 operand is read 16 KB behind the first: it must stay inside the allocation
-    static constexpr int kMinBytes = kW2 + 2 * 8 * kK2 * 4;
-    static_assert(kImageBytes % 16 == 0 && kObs % 16 == 0 && kBar % 8 == 0 && (32 * KIN * 4) % 16 == 0, "alignment");
-    static_assert(KP <= 32 && kObsCol + KP <= kTmemCols, "observation columns do not fit");
+    static_assert(kBytes >= kW2 + 2 * 8 * kK2 * 4, "W2 operand alias runs past the allocation");
+    static_assert(kBytes <= 227 * 1024, "shared memory plan does not fit");
+    static_assert(kImageBytes % 16 == 0 && kObs % 16 == 0 && kCand % 16 == 0 && kBar % 8 == 0 && (32 * KIN * 4) % 16 == 0,
+                  "alignment");
+    static_assert(KP <= 32, "observation columns do not fit");
 };
 
 __host__ __device__ constexpr uint32_t instr_desc(int n) {
     return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
 }
 
-__device__ __forceinline__ void mma_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, bool acc) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
-        "}\n" ::"r"(d_tmem),
-        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"((uint32_t)acc)
-        : "memory");
-}
-
-// A operand from tensor memory (lane = row, one 32-bit column per K element)
+// A operand from tensor memory (lane = row, one 32-bit column per K element), B from shared memory
 __device__ __forceinline__ void mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, bool acc) {
     asm volatile(
         "{\n\t"
@@ -109,7 +111,7 @@ __device__ __forceinline__ uint64_t desc_sbo(uint32_t smem_addr, uint32_t sbo_by
     return d;
 }
 
-__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t* r) {
     asm volatile(
         "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
         "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
@@ -118,6 +120,18 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32
         "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]),
         "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]),
         "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld32p(uint32_t taddr, uint32_t* r) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
         : "memory");
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
@@ -133,6 +147,26 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
                  : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
                  : "r"(taddr)
                  : "memory");
+}
+
+// mbarrier wait with a small code footprint (the hot loops of three warp roles share the instruction cache);
+// try_wait suspends the warp for a hardware time slice per probe, the spin bound turns a lost arrival into a trap
+constexpr uint32_t kSuspendHintNs = 20000;   // let the hardware park a waiting warp instead of polling
+__device__ __forceinline__ void mbar_wait_c(uint32_t mbar, uint32_t parity) {
+    uint32_t done = 0;
+#pragma unroll 1
+    for (int spin = 0; !done; ++spin) {
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t"
+            "}\n"
+            : "=r"(done)
+            : "r"(mbar), "r"(parity), "r"(kSuspendHintNs)
+            : "memory");
+        if (spin > (1 << 22)) __trap();
+    }
 }
 
 __device__ __forceinline__ void mbar_arrive(uint32_t mbar) {
@@ -151,14 +185,15 @@ __device__ __forceinline__ bool elect_one() {
     return pred != 0;
 }
 
-__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
-
 #ifdef RNAD_TRACE
-// development aid: cycle stamps of CTA 0's first tile.  [role][half-move][event]
-__device__ long long g_trace[3][16][24];
-#define TR(role, t, ev) do { if (blockIdx.x == 0 && tile == blockIdx.x && (t) < 16) g_trace[role][t][ev] = clock64(); } while (0)
+// development aid: cycle stamps of CTA 0's first tile pair.  [role][half-move][event]
+__device__ long long g_trace[4][16][24];
+#define TR(role, t, ev) do { if (blockIdx.x == 0 && first_pair && (t) < 16) g_trace[role][t][ev] = clock64(); } while (0)
+// stream items: flat [role 2 = MMA warp, role 3 = epilogue warp 0][2 * item + which]
+#define TRI(role, item, which) do { if (blockIdx.x == 0 && (item) >= 16 && (item) < 16 + 40) (&g_trace[role][0][0])[8 * ((item) - 16) + (which)] = clock64(); } while (0)
 #else
 #define TR(role, t, ev) do { } while (0)
+#define TRI(role, item, which) do { } while (0)
 #endif
 
 template <int A>
@@ -195,7 +230,18 @@ __global__ void pack_weights_kernel(rnad_mlp_weights w, uint8_t* __restrict__ im
     }
 }
 
-// masked softmax with the fast exp2 / reciprocal units (net.py:45-46: e = where(mask, exp(logit), 0); e / max(sum e, 1e-12)).
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+// masked softmax on the fast exp2 / reciprocal units (net.py:45-46: e = where(mask, exp(logit), 0); e / max(sum e, 1e-12)).
 // A few ulp from the exact formula; the recorded policy is the one every later decision uses.
 template <int A>
 __device__ __forceinline__ void masked_softmax_fast(const float (&logit)[A], int n_legal, float (&policy)[A]) {
@@ -203,16 +249,77 @@ __device__ __forceinline__ void masked_softmax_fast(const float (&logit)[A], int
     float sum = 0.f;
 #pragma unroll
     for (int a = 0; a < A; ++a) {
-        e[a] = a < n_legal ? exp2f(logit[a] * 1.4426950408889634f) : 0.f;
+        e[a] = a < n_legal ? ex2_approx(logit[a] * 1.4426950408889634f) : 0.f;
         sum += e[a];
     }
-    const float inv = __frcp_rn(fmaxf(sum, 1e-12f));
+    const float inv = rcp_approx(fmaxf(sum, 1e-12f));
 #pragma unroll
     for (int a = 0; a < A; ++a) policy[a] = e[a] * inv;
 }
 
-template <int A>
-__global__ void __launch_bounds__(kThreads, 2) rollout_tc2_kernel(RolloutArgs g, const uint8_t* __restrict__ image) {
+// Row half-move, off the critical path: for EVERY column action c the opponent may answer with, the chance draw
+// at uniform u (episode.py:106-121), the child id, the reward and the child's node record - two rounds of
+// independent 16-byte gathers - parked in shared memory as [c][word][game]: child, reward, ev[A*A], rows|cols.
+template <int A, int C>
+__device__ __forceinline__ void gather_candidates(const uint32_t* __restrict__ tr_tab, const uint32_t* __restrict__ ev_tab,
+                                                  int node, int row_action, float u, bool active, uint32_t* s_cand,
+                                                  int cand_words) {
+    constexpr int TRS = tr_stride_of(C);
+    constexpr int EVS = ev_stride_of(A);
+    uint32_t w[A][TRS];
+    const uint4* ent = reinterpret_cast<const uint4*>(tr_tab + ((int64_t)node * A * A + row_action * A) * TRS);
+#pragma unroll
+    for (int c = 0; c < A; ++c)
+#pragma unroll
+        for (int q = 0; q < TRS / 4; ++q) {
+            const uint4 v = active ? __ldg(ent + c * (TRS / 4) + q) : make_uint4(0u, 0u, 0u, 0u);
+            w[c][4 * q + 0] = v.x;
+            w[c][4 * q + 1] = v.y;
+            w[c][4 * q + 2] = v.z;
+            w[c][4 * q + 3] = v.w;
+        }
+    int child[A];
+    float rew[A];
+#pragma unroll
+    for (int c = 0; c < A; ++c) {
+        float acc = 0.f;
+        uint32_t ch = w[c][C], val = w[c][2 * C];
+        bool done = false;
+#pragma unroll
+        for (int k = 0; k < C; ++k) {       // same rule as transition() / sample_icdf
+            const float pk = __uint_as_float(w[c][k]);
+            acc = __fadd_rn(acc, pk);
+            const bool positive = pk > 0.f;
+            if (!done && positive) {
+                ch = w[c][C + k];
+                val = w[c][2 * C + k];
+            }
+            done = done || (positive && (u < acc));
+        }
+        child[c] = active ? (int)ch : 0;
+        rew[c] = child[c] == 0 ? __uint_as_float(val) : 0.f;
+    }
+    uint4 rec[A][EVS / 4];
+#pragma unroll
+    for (int c = 0; c < A; ++c)
+#pragma unroll
+        for (int q = 0; q < EVS / 4; ++q)
+            rec[c][q] = active ? __ldg(reinterpret_cast<const uint4*>(ev_tab + (int64_t)child[c] * EVS) + q)
+                               : make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+    for (int c = 0; c < A; ++c) {
+        uint32_t* dst = s_cand + c * cand_words * kTileM;
+        dst[0] = (uint32_t)child[c];
+        dst[kTileM] = __float_as_uint(active ? rew[c] : 0.f);
+        const uint32_t* r = reinterpret_cast<const uint32_t*>(rec[c]);
+#pragma unroll
+        for (int i = 0; i < A * A; ++i) dst[(2 + i) * kTileM] = r[i];
+        dst[(2 + A * A) * kTileM] = active ? (r[A * A] & 0xffffu) : 0x0101u;
+    }
+}
+
+template <int A, int C>
+__global__ void __launch_bounds__(kThreads, 1) rollout_tc2_kernel(RolloutArgs g, const uint8_t* __restrict__ image) {
     using P = Plan<A>;
     constexpr int KIN = P::KIN, KP = P::KP;
     static_assert(A <= 4, "value + logits must fit the 8 useful columns of the second-layer accumulator");
@@ -220,20 +327,24 @@ __global__ void __launch_bounds__(kThreads, 2) rollout_tc2_kernel(RolloutArgs g,
     const int tid = threadIdx.x;
     const int warp = tid >> 5;
     const uint32_t bar0 = smem_u32(smem + P::kBar);
-    const uint32_t bar_img = bar0, bar_a = bar0 + 8;
-    const uint32_t bar_d2 = bar0 + 16 + 16 * kSlots;
+    const uint32_t bar_img = bar0;
+    auto bar_a = [&](int side) { return bar0 + 8 + 8 * side; };                       // observations of `side` in TMEM
+    auto bar_d1 = [&](int slot) { return bar0 + 8 + 8 * kSides + 8 * slot; };         // MMA1 into the slot complete
+    auto bar_relu = [&](int slot) { return bar0 + 8 + 8 * kSides + 8 * (kSlots + slot); };   // relu written back
+    auto bar_d2 = [&](int side) { return bar0 + 8 + 8 * kSides + 16 * kSlots + 8 * side; };  // value / logits complete
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + P::kTmem);
-    // bar_d1[s] = bar0 + 16 + 8 s, bar_relu[s] = bar0 + 16 + 8 (kSlots + s)
 
     if (warp == kMmaWarp) tmem_alloc<kTmemCols>(tmem_slot);
     if (tid == 0) {
         mbar_init(bar_img, 1);
-        mbar_init(bar_a, kHeadWarps);                               // one arrival per head warp
-        for (int s = 0; s < kSlots; ++s) {
-            mbar_init(bar0 + 16 + 8 * s, 1);                        // MMA1 of the slot complete (tcgen05.commit)
-            mbar_init(bar0 + 16 + 8 * (kSlots + s), kEpiWarps);     // relu written back, one arrival per epilogue warp
+        for (int s = 0; s < kSides; ++s) {
+            mbar_init(bar_a(s), 4);              // one arrival per head warp of the side
+            mbar_init(bar_d2(s), kMmaWarps);     // each MMA warp commits its half of the chunks
         }
-        mbar_init(bar_d2, 1);
+        for (int s = 0; s < kSlots; ++s) {
+            mbar_init(bar_d1(s), 1);             // tcgen05.commit
+            mbar_init(bar_relu(s), kEpiWarps);   // one arrival per epilogue warp
+        }
         mbar_fence_init();
         tma_bulk_load(smem, image, P::kImageBytes, bar_img);
     }
@@ -242,57 +353,62 @@ __global__ void __launch_bounds__(kThreads, 2) rollout_tc2_kernel(RolloutArgs g,
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     const int64_t num_tiles = (g.B + kTileM - 1) / kTileM;
+    const int64_t num_pairs = (num_tiles + kSides - 1) / kSides;
+    int64_t my_pairs = 0;                        // pairs this CTA plays: blockIdx.x, blockIdx.x + gridDim.x, ...
+    if ((int64_t)blockIdx.x < num_pairs) my_pairs = (num_pairs - 1 - blockIdx.x) / gridDim.x + 1;
 
-    if (warp == kMmaWarp) {
-        // ------------------------------------------------------------ MMA issuer
+    if (warp >= kMmaWarp) {
+        // ------------------------------------------------------------ MMA issuers
         // The whole warp runs the loop converged and one elected lane issues: the descriptors then live in
         // uniform registers (an `if (lane == 0)` branch makes ptxas wrap every UTCHMMA in a waterfall loop).
-        mbar_wait(bar_img, 0);
+        mbar_wait_c(bar_img, 0);
         const uint64_t w1_desc = desc_sbo(smem_u32(smem + P::kW1), P::kSbo1);
         const uint64_t w2_desc = desc_sbo(smem_u32(smem + P::kW2), 8 * kK2 * 4);
         constexpr uint32_t kIdesc1 = instr_desc(kChunk), kIdesc2 = instr_desc(kN2);
-        uint32_t ph_a = 0, ph_relu = 0;   // bit s of ph_relu = parity of slot s
-        auto mma1 = [&](int c) {          // first layers, hidden units [64c, 64c+64): A = observations in tensor memory
-            const int slot = c % kSlots;
-#pragma unroll
-            for (int s = 0; s < KP / 8; ++s)
-                mma_ts(tmem_base + slot * kChunk, tmem_base + kObsCol + s * 8,
-                       w1_desc + (uint64_t)((c * (kChunk / 8) * P::kSbo1 + s * 256) >> 4), kIdesc1, s > 0);
-            mma_commit(bar0 + 16 + 8 * slot);
-        };
-        for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-            for (int t = 0; t < g.T; ++t) {
-                TR(0, t, 0);
-                mbar_wait(bar_a, ph_a);
-                ph_a ^= 1u;
+        // Stream item i = ((pair * T + t) * kSides + side) * kChunks + c lives in slot i % kSlots.  Its step is
+        //     wait relu(i) -> MMA2(i) -> MMA1(i + kSlots) into the slot MMA2(i) has just read -> commit,
+        // and the two MMA warps take alternate items, so that the tensor core always has the other warp's work
+        // queued while one warp sits in a barrier wait.  Chunks of one parity accumulate into their own D2
+        // (MMAs of one thread execute in order; those of different threads are ordered by the barriers only).
+        const int w = warp - kMmaWarp;
+        const int64_t n_items = my_pairs * g.T * kSides * kChunks;
+        int seen_hm[kSides] = {-1, -1};
+        auto mma1 = [&](int64_t j) {             // first layers of item j: A = observations in tensor memory
+            const int c = (int)(j & (kChunks - 1)), side = (int)(j / kChunks) & 1, slot = (int)(j % kSlots);
+            const int hm = (int)(j / (kChunks * kSides));   // half-move counter of the side
+            if (hm != seen_hm[side]) {           // the observations of this half-move must have been published
+                mbar_wait_c(bar_a(side), (uint32_t)hm & 1u);   // (each MMA warp checks for itself: they do not order each other)
                 tc_fence_after();
-                TR(0, t, 1);
-                if (elect_one()) {
-                    mma1(0);
-                    mma1(1);
-                    mma1(2);
-                }
-                __syncwarp();
-                TR(0, t, 2);
-#pragma unroll
-                for (int c = 0; c < kChunks; ++c) {
-                    const int slot = c % kSlots;
-                    mbar_wait(bar0 + 16 + 8 * (kSlots + slot), (ph_relu >> slot) & 1u);
-                    ph_relu ^= 1u << slot;
-                    tc_fence_after();
-                    TR(0, t, 3 + 2 * c);
-                    if (elect_one()) {
-#pragma unroll
-                        for (int s = 0; s < kChunk / 8; ++s)   // second layers: A = relu(hidden) in tensor memory
-                            mma_ts(tmem_base + kD2Col, tmem_base + slot * kChunk + s * 8,
-                                   w2_desc + (uint64_t)(((c * (kChunk / 8) + s) * 256) >> 4), kIdesc2, (c | s) != 0);
-                        if (c + kSlots < kChunks) mma1(c + kSlots);
-                        if (c == kChunks - 1) mma_commit(bar_d2);
-                    }
-                    __syncwarp();
-                    TR(0, t, 4 + 2 * c);
-                }
+                seen_hm[side] = hm;
             }
+            if (elect_one()) {
+#pragma unroll
+                for (int s = 0; s < KP / 8; ++s)
+                    mma_ts(tmem_base + slot * kChunk, tmem_base + obs_col(side) + s * 8,
+                           w1_desc + (uint64_t)((c * (kChunk / 8) * P::kSbo1 + s * 256) >> 4), kIdesc1, s > 0);
+                mma_commit(bar_d1(slot));
+            }
+            __syncwarp();
+        };
+        if (w == 0)
+            for (int64_t j = 0; j < kSlots && j < n_items; ++j) mma1(j);
+#pragma unroll 1
+        for (int64_t i = w; i < n_items; i += kMmaWarps) {
+            const int c = (int)(i & (kChunks - 1)), side = (int)(i / kChunks) & 1, slot = (int)(i % kSlots);
+            mbar_wait_c(bar_relu(slot), (uint32_t)(i / kSlots) & 1u);
+            tc_fence_after();
+            TRI(2, i, 0);
+            if (elect_one()) {
+#pragma unroll
+                for (int s = 0; s < kChunk / 8; ++s)   // second layers: A = relu(hidden) in tensor memory
+                    mma_ts(tmem_base + d2_col(side) + 16 * w, tmem_base + slot * kChunk + s * 8,
+                           w2_desc + (uint64_t)(((c * (kChunk / 8) + s) * 256) >> 4), kIdesc2, (c >= kMmaWarps) || s > 0);
+                if (c + kMmaWarps >= kChunks) mma_commit(bar_d2(side));
+            }
+            __syncwarp();
+            TRI(2, i, 1);
+            if (i + kSlots < n_items) mma1(i + kSlots);
+            TRI(2, i, 2);
         }
     } else if (warp >= kHeadWarps) {
         // ------------------------------------------------------------ epilogue of the first layers
@@ -301,66 +417,70 @@ __global__ void __launch_bounds__(kThreads, 2) rollout_tc2_kernel(RolloutArgs g,
         constexpr int kCols = kChunk / kPart;
         const uint32_t tmem_mine = tmem_base + ((uint32_t)((e & 3) * 32) << 16) + (uint32_t)((e >> 2) * kCols);
         const float* b1 = reinterpret_cast<const float*>(smem + P::kB1) + (e >> 2) * kCols;
-        if (!P::kBiasInK) mbar_wait(bar_img, 0);
+        if (!P::kBiasInK) mbar_wait_c(bar_img, 0);
+        const int64_t n_items = my_pairs * g.T * kSides * kChunks;
         uint32_t ph_d1 = 0;
-        for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-            for (int t = 0; t < g.T; ++t) {
+        int slot = 0, c = 0;
+#pragma unroll 1
+        for (int64_t i = 0; i < n_items; ++i) {
+            mbar_wait_c(bar_d1(slot), (ph_d1 >> slot) & 1u);
+            ph_d1 ^= 1u << slot;
+            tc_fence_after();
+            if (e == 0) TRI(2, i, 3);
+            const uint32_t taddr = tmem_mine + slot * kChunk;
+            uint32_t r[kCols];
 #pragma unroll
-                for (int c = 0; c < kChunks; ++c) {
-                    const int slot = c % kSlots;
-                    if (c == 0 && (tid & 31) == 0 && e == 0) TR(2, t, 0);
-                    mbar_wait(bar0 + 16 + 8 * slot, (ph_d1 >> slot) & 1u);
-                    ph_d1 ^= 1u << slot;
-                    tc_fence_after();
-                    if ((tid & 31) == 0 && e == 0) TR(2, t, 1 + 2 * c);
-                    const uint32_t taddr = tmem_mine + slot * kChunk;
-                    uint32_t r[kCols];
+            for (int q = 0; q < kCols / 32; ++q) tmem_ld32p(taddr + q * 32, r + q * 32);
+            tmem_ld_wait();
+            if (!P::kBiasInK) {
+                const float4* bias = reinterpret_cast<const float4*>(b1 + c * kChunk);
 #pragma unroll
-                    for (int q = 0; q < kCols / 32; ++q) tmem_ld32(taddr + q * 32, *reinterpret_cast<uint32_t(*)[32]>(r + q * 32));
-                    tmem_ld_wait();
-                    if (!P::kBiasInK) {
-                        const float4* bias = reinterpret_cast<const float4*>(b1 + c * kChunk);
-#pragma unroll
-                        for (int i = 0; i < kCols / 4; ++i) {
-                            const float4 bb = bias[i];
-                            r[4 * i + 0] = __float_as_uint(__uint_as_float(r[4 * i + 0]) + bb.x);
-                            r[4 * i + 1] = __float_as_uint(__uint_as_float(r[4 * i + 1]) + bb.y);
-                            r[4 * i + 2] = __float_as_uint(__uint_as_float(r[4 * i + 2]) + bb.z);
-                            r[4 * i + 3] = __float_as_uint(__uint_as_float(r[4 * i + 3]) + bb.w);
-                        }
-                    }
-#pragma unroll
-                    for (int i = 0; i < kCols; ++i) r[i] = __float_as_uint(fmaxf(__uint_as_float(r[i]), 0.f));
-#pragma unroll
-                    for (int q = 0; q < kCols / 32; ++q) tmem_st32(taddr + q * 32, *reinterpret_cast<uint32_t(*)[32]>(r + q * 32));
-                    tmem_st_wait();
-                    tc_fence_before();
-                    __syncwarp();
-                    if ((tid & 31) == 0) mbar_arrive(bar0 + 16 + 8 * (kSlots + slot));
-                    if ((tid & 31) == 0 && e == 0) TR(2, t, 2 + 2 * c);
+                for (int k = 0; k < kCols / 4; ++k) {
+                    const float4 bb = bias[k];
+                    r[4 * k + 0] = __float_as_uint(__uint_as_float(r[4 * k + 0]) + bb.x);
+                    r[4 * k + 1] = __float_as_uint(__uint_as_float(r[4 * k + 1]) + bb.y);
+                    r[4 * k + 2] = __float_as_uint(__uint_as_float(r[4 * k + 2]) + bb.z);
+                    r[4 * k + 3] = __float_as_uint(__uint_as_float(r[4 * k + 3]) + bb.w);
                 }
             }
+#pragma unroll
+            for (int k = 0; k < kCols; ++k) r[k] = __float_as_uint(fmaxf(__uint_as_float(r[k]), 0.f));
+#pragma unroll
+            for (int q = 0; q < kCols / 32; ++q) tmem_st32(taddr + q * 32, r + q * 32);
+            tmem_st_wait();
+            tc_fence_before();
+            __syncwarp();
+            if ((tid & 31) == 0) mbar_arrive(bar_relu(slot));
+            slot = slot + 1 == kSlots ? 0 : slot + 1;
+            c = (c + 1) & (kChunks - 1);
         }
     } else {
-        // ------------------------------------------------------------ head: one thread per game
-        const int lane_g = tid;                               // game of the tile == TMEM lane
+        // ------------------------------------------------------------ heads: one thread per game
+        const int side = warp >> 2;
+        const int lane_g = tid & (kTileM - 1);                // game of the tile == TMEM lane
         const int lane = tid & 31;
-        const uint32_t tmem_lane = tmem_base + ((uint32_t)(warp * 32) << 16);
-        float* s_obs = reinterpret_cast<float*>(smem + P::kObs) + warp * 32 * KIN;   // this warp's 32 rows
-        mbar_wait(bar_img, 0);
+        const int hw = warp & 3;                              // head warp of the side == lane quadrant
+        const uint32_t tmem_lane = tmem_base + ((uint32_t)(hw * 32) << 16);
+        const uint32_t my_d2 = tmem_lane + d2_col(side), my_obs = tmem_lane + obs_col(side);
+        float* s_obs = reinterpret_cast<float*>(smem + P::kObs) + (side * kTileM + hw * 32) * KIN;   // this warp's 32 rows
+        uint32_t* s_cand = reinterpret_cast<uint32_t*>(smem + P::kCand) + side * A * P::kCandWords * kTileM + lane_g;
+        mbar_wait_c(bar_img, 0);
         const float b2v = reinterpret_cast<const float*>(smem + P::kB2)[0];
         float b2p[A];
 #pragma unroll
         for (int a = 0; a < A; ++a) b2p[a] = reinterpret_cast<const float*>(smem + P::kB2)[1 + a];
-        constexpr int EVS = ev_stride_of(A);
-        const int trs = tr_stride_of(g.C);
+        const uint32_t my_bar_a = bar_a(side), my_bar_d2 = bar_d2(side);
 
         uint32_t ph_d2 = 0;
         int last_valid = -1;
-        for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        for (int64_t k = 0; k < my_pairs; ++k) {
+#ifdef RNAD_TRACE
+            const bool first_pair = k == 0;
+#endif
+            const int64_t tile = ((int64_t)blockIdx.x + k * gridDim.x) * kSides + side;
             const int64_t tile_base = tile * kTileM;
             const int64_t b = tile_base + lane_g;
-            const bool active = b < g.B;
+            const bool active = b < g.B;                      // (a side without a tile plays along with idle lanes)
             int node = active ? 1 : 0;
             int row_action = 0;
             Node<A> n;
@@ -369,50 +489,44 @@ __global__ void __launch_bounds__(kThreads, 2) rollout_tc2_kernel(RolloutArgs g,
             n.rows = n.cols = 1;
             float x[KIN];
 
-            // observation of half-move t -> tensor memory (tf32 A operand of the first layers); critical path
-            auto publish_obs = [&](int t) {
-                const int turn = t & 1;
-                if (turn == 0 && active) load_node<A>(g.ev_tab, node, n);
-                build_obs<A>(n, turn, x);
+            // observation words of half-move t in tf32 (A operand of the first layers) -> tensor memory; critical path
+            auto publish_obs = [&]() {
 #pragma unroll
                 for (int q = 0; q < KP / 8; ++q) {
                     uint32_t v[8];
 #pragma unroll
                     for (int u = 0; u < 8; ++u) {
-                        const int k = 8 * q + u;
-                        v[u] = __float_as_uint(k < KIN ? to_tf32(x[k < KIN ? k : 0]) : ((P::kBiasInK && k == KIN) ? 1.f : 0.f));
+                        const int kk = 8 * q + u;
+                        v[u] = __float_as_uint(kk < KIN ? to_tf32(x[kk < KIN ? kk : 0])
+                                                        : ((P::kBiasInK && kk == KIN) ? 1.f : 0.f));
                     }
-                    tmem_st8(tmem_lane + kObsCol + 8 * q, v);
+                    tmem_st8(my_obs + 8 * q, v);
                 }
+                tmem_ld_wait();          // this thread's read of D2 is complete ...
                 tmem_st_wait();
-                tc_fence_before();       // orders these stores and this thread's tcgen05.ld of D2 before the next MMAs
+                tc_fence_before();       // ... and ordered, with the stores above, before the MMAs the arrival releases
                 __syncwarp();
-                if (lane == 0) mbar_arrive(bar_a);
+                if (lane == 0) mbar_arrive(my_bar_a);
             };
             // the same observation in fp32 -> trajectory; off the critical path.  A warp's 32 rows are one
             // contiguous block of the (T,B,2,A,A) tensor: staged in shared memory, stored as coalesced 16-byte words.
             auto store_obs = [&](int t) {
-                const int64_t row0 = (int64_t)t * g.B + tile_base + warp * 32;
+                const int64_t row0 = (int64_t)t * g.B + tile_base + hw * 32;
                 float* dst = g.out.observations + row0 * KIN;
-                const int rows = (int)max((int64_t)0, min((int64_t)32, g.B - (tile_base + warp * 32)));
-                if (P::kStage && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+                const int rows = (int)max((int64_t)0, min((int64_t)32, g.B - (tile_base + hw * 32)));
+                if ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
                     __syncwarp();        // the previous half-move's copy is done
 #pragma unroll
-                    for (int k = 0; k < KIN; k += 2)
-                        *reinterpret_cast<float2*>(s_obs + lane * KIN + k) = make_float2(x[k], x[k + 1]);
+                    for (int kk = 0; kk < KIN; kk += 2)
+                        *reinterpret_cast<float2*>(s_obs + lane * KIN + kk) = make_float2(x[kk], x[kk + 1]);
                     __syncwarp();
                     const int n_float = rows * KIN;
-                    for (int i = lane * 4; i < n_float; i += 128) {
-                        if (i + 4 <= n_float) {
-                            __stcs(reinterpret_cast<float4*>(dst + i), *reinterpret_cast<const float4*>(s_obs + i));
-                        } else {
-                            for (int k = i; k < n_float; ++k) __stcs(dst + k, s_obs[k]);
-                        }
-                    }
+                    for (int i = lane * 4; i < n_float; i += 128)
+                        __stcs(reinterpret_cast<float4*>(dst + i), *reinterpret_cast<const float4*>(s_obs + i));
                 } else if (active) {
-                    float2* d2 = reinterpret_cast<float2*>(g.out.observations + ((int64_t)t * g.B + b) * KIN);
+                    float2* d = reinterpret_cast<float2*>(g.out.observations + ((int64_t)t * g.B + b) * KIN);
 #pragma unroll
-                    for (int k = 0; k < KIN / 2; ++k) __stcs(d2 + k, make_float2(x[2 * k], x[2 * k + 1]));
+                    for (int kk = 0; kk < KIN / 2; ++kk) __stcs(d + kk, make_float2(x[2 * kk], x[2 * kk + 1]));
                 }
             };
             auto draw = [&](int t) {
@@ -427,61 +541,86 @@ __global__ void __launch_bounds__(kThreads, 2) rollout_tc2_kernel(RolloutArgs g,
                 return u;
             };
 
-            publish_obs(0);
-            store_obs(0);
-            Uniforms2 u = draw(0);
-
-            for (int t = 0; t < g.T; ++t) {
-                const int turn = t & 1;
-                if (node != 0) last_valid = max(last_valid, t);
-                if (tid == 0) TR(1, t, 0);
-                mbar_wait(bar_d2, ph_d2);
-                ph_d2 ^= 1u;
-                tc_fence_after();
-                if (tid == 0) TR(1, t, 1);
-                uint32_t d2[8];
-                tmem_ld8(tmem_lane + kD2Col, d2);
-                tmem_ld_wait();
-                const float value = __uint_as_float(d2[0]) + b2v;
-                float logit[A];
-#pragma unroll
-                for (int a = 0; a < A; ++a) logit[a] = __uint_as_float(d2[1 + a]) + b2p[a];
-                const int n_legal = turn == 0 ? n.rows : n.cols;
-                float policy[A];
-                masked_softmax_fast<A>(logit, n_legal, policy);
-                const int action = sample_icdf(policy, A, u.action);
-                float reward = 0.f;
-                const int node_now = node;
-                if (turn == 0) {
-                    row_action = action;
-                } else if (active) {
-                    int child;
-                    transition(g.tr_tab, A, g.C, node, row_action, action, u.chance, child, reward);
-                    node = child;
+#ifdef RNAD_TC2_NOHEAD
+            // experiment: heads only hand the barriers around (the output is garbage)
+            for (int t = -1; t < g.T; ++t) {
+                if (t >= 0) {
+                    mbar_wait_c(my_bar_d2, ph_d2);
+                    ph_d2 ^= 1u;
+                    tc_fence_after();
                 }
-                if (tid == 0) TR(1, t, 2);
-                if (t + 1 < g.T) publish_obs(t + 1);
-                if (tid == 0) TR(1, t, 3);
-
-                // ---- off the critical path: the tensor core and the epilogue warps are busy with half-move t + 1
-                if (active) write_record<A>(g.out, (int64_t)t * g.B + b, node_now, turn, n_legal, policy, action, value, reward);
                 if (t + 1 < g.T) {
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(my_bar_a);
+                }
+            }
+            continue;
+#endif
+            Uniforms2 u;
+            u.action = u.chance = 0.f;
+            // half-move -1 is the set-up of the tile: it only publishes the root observation
+#pragma unroll 1
+            for (int t = -1; t < g.T; ++t) {
+                const int turn = t & 1;
+                const bool more = t + 1 < g.T;
+                if (t < 0) {
+                    if (active) load_node<A>(g.ev_tab, node, n);
+                    build_obs<A>(n, 0, x);
+                    publish_obs();
+                } else {
+                    if (node != 0) last_valid = max(last_valid, t);
+                    const int n_legal = turn == 0 ? n.rows : n.cols;
+                    // a row half-move does not move the game: the column player's observation is known beforehand
+                    if (turn == 0) build_obs<A>(n, 1, x);
+                    if (lane_g == 0) TR(side, t, 0);
+                    mbar_wait_c(my_bar_d2, ph_d2);
+                    ph_d2 ^= 1u;
+                    tc_fence_after();
+                    if (lane_g == 0) TR(side, t, 1);
+                    uint32_t d2[8], d2b[8];                        // partial sums of the even / odd chunks
+                    tmem_ld8(my_d2, d2);
+                    tmem_ld8(my_d2 + 16, d2b);
+                    if (turn == 0 && more) publish_obs();          // critical path of a row half-move ends here
+                    tmem_ld_wait();
+                    const float value = (__uint_as_float(d2[0]) + __uint_as_float(d2b[0])) + b2v;
+                    float logit[A];
+#pragma unroll
+                    for (int a = 0; a < A; ++a) logit[a] = (__uint_as_float(d2[1 + a]) + __uint_as_float(d2b[1 + a])) + b2p[a];
+                    float policy[A];
+                    masked_softmax_fast<A>(logit, n_legal, policy);
+                    const int action = sample_icdf(policy, A, u.action);
+                    float reward = 0.f;
+                    const int node_now = node;
+                    if (turn == 0) {
+                        row_action = action;
+                    } else {
+                        // the outcome of (node, row_action, action) was gathered during the row half-move
+                        const uint32_t* cand = s_cand + action * P::kCandWords * kTileM;
+#pragma unroll
+                        for (int i = 0; i < A * A; ++i) n.ev[i] = __uint_as_float(cand[(2 + i) * kTileM]);
+                        const uint32_t rc = cand[(2 + A * A) * kTileM];
+                        n.rows = rc & 0xff;
+                        n.cols = rc >> 8;
+                        node = (int)cand[0];
+                        reward = __uint_as_float(cand[kTileM]);
+                        if (more) {
+                            build_obs<A>(n, 0, x);
+                            publish_obs();                         // critical path of a column half-move ends here
+                        }
+                    }
+                    if (lane_g == 0) TR(side, t, 3);
+                    // ---- from here on off the critical path: the tensor core and the epilogue warps are busy
+                    if (active)
+                        write_record<A>(g.out, (int64_t)t * g.B + b, node_now, turn, n_legal, policy, action, value, reward);
+                }
+                if (more) {
                     store_obs(t + 1);
                     u = draw(t + 1);
-                    if (turn == 0 && active) {
-                        // warm L1 for the next half-move's gathers: the transition entries of (node, row_action, *)
-                        // and the node records of their children
-                        const uint32_t* ent = g.tr_tab + ((int64_t)node * A * A + row_action * A) * trs;
-                        for (int c = 0; c < A; ++c)
-                            for (int k = 0; k < g.C; ++k) {
-                                const int child = (int)__ldg(ent + c * trs + g.C + k);
-                                const uint32_t* rec = g.ev_tab + (int64_t)child * EVS;
-                                prefetch_l1(rec);
-                                if (EVS * 4 > 32) prefetch_l1(rec + EVS - 1);
-                            }
-                    }
+                    if (t >= 0 && turn == 0)
+                        gather_candidates<A, C>(g.tr_tab, g.ev_tab, node, row_action, u.chance, active, s_cand, P::kCandWords);
                 }
-                if (tid == 0) TR(1, t, 4);
+                if (t >= 0 && lane_g == 0) TR(side, t, 4);
             }
         }
         last_valid = warp_max(last_valid);
@@ -493,32 +632,27 @@ __global__ void __launch_bounds__(kThreads, 2) rollout_tc2_kernel(RolloutArgs g,
     if (warp == kMmaWarp) tmem_dealloc<kTmemCols>(tmem_base);
 }
 
-template <int A>
+template <int A, int C>
 static int launch(const RolloutArgs& g, uint8_t* workspace, cudaStream_t st) {
     using P = Plan<A>;
     pack_weights_kernel<A><<<32, 256, 0, st>>>(g.w, workspace);
     RNAD_CHECK_LAUNCH("pack_weights_kernel");
-    // Two CTAs per SM share the 512 TMEM columns; pad the shared-memory request so that a
-    // third CTA can never become resident and spin inside tcgen05.alloc.
-    size_t smem = P::kBytes > P::kMinBytes ? P::kBytes : P::kMinBytes;
-    const size_t floor_two_per_sm = 227 * 1024 / 3 + 1024;
-    if (smem < floor_two_per_sm) smem = floor_two_per_sm;
-    if (smem > 227 * 1024) {
-        set_error("rnad_rollout(tf32x2): %zu B of shared memory needed", smem);
-        return RNAD_EUNSUPPORTED;
-    }
-    const int per_sm = 2 * (smem + 1024) <= 228 * 1024 ? 2 : 1;
-    int rc = check_cuda(cudaFuncSetAttribute(rollout_tc2_kernel<A>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
+    // One CTA per SM owns all 512 TMEM columns: ask for more than half of the shared memory so that a second
+    // CTA can never become resident and spin inside tcgen05.alloc.
+    size_t smem = P::kBytes;
+    const size_t floor_one_per_sm = 116 * 1024;
+    if (smem < floor_one_per_sm) smem = floor_one_per_sm;
+    int rc = check_cuda(cudaFuncSetAttribute(rollout_tc2_kernel<A, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
                         "cudaFuncSetAttribute(rollout_tc2, smem)");
     if (rc) return rc;
-    rc = check_cuda(cudaFuncSetAttribute(rollout_tc2_kernel<A>, cudaFuncAttributePreferredSharedMemoryCarveout,
+    rc = check_cuda(cudaFuncSetAttribute(rollout_tc2_kernel<A, C>, cudaFuncAttributePreferredSharedMemoryCarveout,
                                          cudaSharedmemCarveoutMaxShared),
                     "cudaFuncSetAttribute(rollout_tc2, carveout)");
     if (rc) return rc;
-    int64_t blocks = (g.B + kTileM - 1) / kTileM;
-    const int64_t cap = (int64_t)sm_count() * per_sm;
-    if (blocks > cap) blocks = cap;
-    rollout_tc2_kernel<A><<<(int)blocks, kThreads, smem, st>>>(g, workspace);
+    const int64_t tiles = (g.B + kTileM - 1) / kTileM;
+    int64_t blocks = (tiles + kSides - 1) / kSides;
+    if (blocks > sm_count()) blocks = sm_count();
+    rollout_tc2_kernel<A, C><<<(int)blocks, kThreads, smem, st>>>(g, workspace);
     RNAD_CHECK_LAUNCH("rollout_tc2_kernel");
     return RNAD_OK;
 }
@@ -531,6 +665,8 @@ extern "C" __attribute__((visibility("default"))) int rnad_debug_trace(long long
 }
 #endif
 
+bool rollout_tc2_supported(int A, int width, int C) { return rollout_tc_supported(A, width) && C >= 1 && C <= 4; }
+
 int64_t rollout_tc2_workspace_bytes(int A) {
     switch (A) {
         case 2: return tc2::Plan<2>::kImageBytes;
@@ -541,20 +677,21 @@ int64_t rollout_tc2_workspace_bytes(int A) {
 }
 
 int rollout_tc2(const RolloutArgs& g, void* workspace, cudaStream_t st) {
-    if (!rollout_tc_supported(g.A, g.w.width)) {
-        set_error("rnad_rollout(tf32x2): needs width == 256 and 2 <= max_actions <= 4 (got width %d, max_actions %d)",
-                  g.w.width, g.A);
+    if (!rollout_tc2_supported(g.A, g.w.width, g.C)) {
+        set_error("rnad_rollout(tf32x2): needs width == 256, 2 <= max_actions <= 4 and max_transitions <= 4 "
+                  "(got width %d, max_actions %d, max_transitions %d)", g.w.width, g.A, g.C);
         return RNAD_EUNSUPPORTED;
     }
     if (workspace == nullptr || (reinterpret_cast<uintptr_t>(workspace) & 15) != 0) {
         set_error("rnad_rollout(tf32x2): needs a 16-byte aligned workspace of rnad_rollout_workspace_bytes()");
         return RNAD_EINVAL;
     }
-    switch (g.A) {
-        case 2: return tc2::launch<2>(g, (uint8_t*)workspace, st);
-        case 3: return tc2::launch<3>(g, (uint8_t*)workspace, st);
-        case 4: return tc2::launch<4>(g, (uint8_t*)workspace, st);
-    }
+#define RNAD_TC2_CASE(a, c) \
+    if (g.A == a && g.C == c) return tc2::launch<a, c>(g, (uint8_t*)workspace, st);
+    RNAD_TC2_CASE(2, 1) RNAD_TC2_CASE(2, 2) RNAD_TC2_CASE(2, 3) RNAD_TC2_CASE(2, 4)
+    RNAD_TC2_CASE(3, 1) RNAD_TC2_CASE(3, 2) RNAD_TC2_CASE(3, 3) RNAD_TC2_CASE(3, 4)
+    RNAD_TC2_CASE(4, 1) RNAD_TC2_CASE(4, 2) RNAD_TC2_CASE(4, 3) RNAD_TC2_CASE(4, 4)
+#undef RNAD_TC2_CASE
     return RNAD_EINVAL;
 }
 

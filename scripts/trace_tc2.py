@@ -14,14 +14,23 @@ for _ in range(3):
     r.launch()
 torch.cuda.synchronize()
 L = _b200.lib()
-buf = np.zeros((3, 16, 24), dtype=np.int64)
+buf = np.zeros((4, 16, 24), dtype=np.int64)
 L.rnad_debug_trace.argtypes = [ctypes.c_void_p]
 rc = L.rnad_debug_trace(buf.ctypes.data)
 assert rc == 0, rc
 t0 = buf[0, 0, 0]
+# events of a head warp: 0 waiting for D2, 1 D2 ready, 2 action / next node known, 3 next observation published, 4 bookkeeping done
 np.set_printoptions(linewidth=250)
-for role, name in enumerate(["mma", "head(w0)", "epi(w4)"]):
+for role, name in enumerate(["head side 0", "head side 1"]):
     print(name)
     for t in range(r.T):
         row = buf[role, t]
-        print(f"  t={t}", " ".join(f"{(x - t0) if x else -1:6d}" for x in row[:20]))
+        print(f"  t={t}", " ".join(f"{(x - t0) if x else -1:6d}" for x in row[:5]))
+
+# stream items 16..55: MMA warp timestamps relative to "relu seen"
+mma = buf[2].reshape(-1)[:320].reshape(-1, 8)
+fine = buf[3].reshape(-1)[:320].reshape(-1, 8)
+print("item | elected, after MMA2 #1, #4, #8, #12, #16, commit | MMA2 region done | MMA1 region done   (cycles after relu seen)")
+for j in range(24):
+    base = mma[j, 0]
+    print(f"{j+16:4d} | " + " ".join(f"{x-base:6d}" for x in fine[j, :7]) + f" | {mma[j,1]-base:6d} | {mma[j,2]-base:6d}")
