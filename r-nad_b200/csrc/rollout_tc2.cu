@@ -44,9 +44,15 @@ constexpr int kHeadWarps = 4 * kSides;           // warps 0..7: one thread per g
 #ifndef RNAD_TC2_EPI_WARPS
 #define RNAD_TC2_EPI_WARPS 8
 #endif
-constexpr int kEpiWarps = RNAD_TC2_EPI_WARPS;    // relu epilogue warps (8 or 16)
-constexpr int kMmaWarp = kHeadWarps + kEpiWarps;   // first of the two MMA warps (they take alternate stream items)
-constexpr int kMmaWarps = 2;
+// relu epilogue warps: 4 lane quadrants x 2 column halves, and with 16 warps x 2 item parities (each warp then takes
+// every other stream item, and registers are re-allocated between the roles).  Measured on cfg2: 8 warps 0.066 ms,
+// 16 warps 0.072 ms per rollout - more warps lengthen the heads' critical path more than they shorten the epilogue's.
+constexpr int kEpiWarps = RNAD_TC2_EPI_WARPS;
+constexpr int kEpiStride = kEpiWarps / 8;        // an epilogue warp takes every kEpiStride-th stream item
+constexpr int kEpiPerItem = 8;                   // warps working on one stream item
+static_assert(kEpiWarps == 8 || kEpiWarps == 16, "8 or 16 epilogue warps");
+constexpr int kMmaWarp = kHeadWarps + kEpiWarps;   // first of the MMA warps
+constexpr int kMmaWarps = 4;                       // stream item i is issued by MMA warp i % 4, i.e. one warp per chunk index
 constexpr int kThreads = (kMmaWarp + kMmaWarps) * 32;
 constexpr int kChunk = 128;                      // hidden units per pipeline stage
 constexpr int kChunks = 2 * kHidden / kChunk;    // per side and half-move
@@ -56,9 +62,9 @@ constexpr int kTmemCols = 512;
 constexpr int kN2 = 16;                          // N of the second-layer MMA (smallest legal at M = 128)
 constexpr int kK2 = 2 * kHidden;                 // its K: value trunk | policy trunk
 
-// per side: two second-layer accumulators of 16 columns (even / odd chunks, one per MMA warp), then the observations
+// per side: 16 columns of second-layer accumulators (value, logits), then the observations
 __host__ __device__ constexpr int d2_col(int side) { return kSideCol + 64 * side; }
-__host__ __device__ constexpr int obs_col(int side) { return kSideCol + 64 * side + 32; }
+__host__ __device__ constexpr int obs_col(int side) { return kSideCol + 64 * side + 16; }
 
 template <int A>
 struct Plan {
@@ -75,7 +81,7 @@ struct Plan {
     static constexpr int kObs = kImageBytes;                         // fp32 observation staging, [side][128 x KIN]
     static constexpr int kCand = kObs + kSides * kTileM * KIN * 4;   // transition candidates, [side][A][kCandWords][128]
     static constexpr int kBar = kCand + kSides * A * kCandWords * kTileM * 4;
-    static constexpr int kNumBars = 1 + kSides + 2 * kSlots + kSides;   // image, obs-ready[2], d1[3], relu[3], d2[2]
+    static constexpr int kNumBars = 1 + kSides + 4 * kSlots + kSides;   // image, obs-ready[2], d1[6], relu[6], d2[2]
     static constexpr int kTmem = kBar + 8 * kNumBars;
     static constexpr int kBytes = kTmem + 16;
     // the second 8-row group of the W2 operand is read 16 KB behind the first: it must stay inside the allocation
@@ -84,6 +90,7 @@ struct Plan {
     static_assert(kImageBytes % 16 == 0 && kObs % 16 == 0 && kCand % 16 == 0 && kBar % 8 == 0 && (32 * KIN * 4) % 16 == 0,
                   "alignment");
     static_assert(KP <= 32, "observation columns do not fit");
+    static_assert(kMmaWarps == kChunks, "one MMA warp per chunk index");
 };
 
 __host__ __device__ constexpr uint32_t instr_desc(int n) {
@@ -184,6 +191,15 @@ __device__ __forceinline__ bool elect_one() {
         : "=r"(pred));
     return pred != 0;
 }
+
+// register re-allocation between the warp roles (all four warps of a warpgroup execute the same one)
+template <int N>
+__device__ __forceinline__ void regs_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
+template <int N>
+__device__ __forceinline__ void regs_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
+// launch: 896 threads x 72; after re-allocation 8 x 32 x 104 + 16 x 32 x 56 + 4 x 32 x 72 = 64,512 of 65,536
+constexpr int kRegsHead = 104, kRegsEpi = 56;
+static_assert(kHeadWarps % 4 == 0 && kEpiWarps % 4 == 0, "roles must fill whole warpgroups");
 
 #ifdef RNAD_TRACE
 // development aid: cycle stamps of CTA 0's first tile pair.  [role][half-move][event]
@@ -329,9 +345,13 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tc2_kernel(RolloutArgs g,
     const uint32_t bar0 = smem_u32(smem + P::kBar);
     const uint32_t bar_img = bar0;
     auto bar_a = [&](int side) { return bar0 + 8 + 8 * side; };                       // observations of `side` in TMEM
-    auto bar_d1 = [&](int slot) { return bar0 + 8 + 8 * kSides + 8 * slot; };         // MMA1 into the slot complete
-    auto bar_relu = [&](int slot) { return bar0 + 8 + 8 * kSides + 8 * (kSlots + slot); };   // relu written back
-    auto bar_d2 = [&](int side) { return bar0 + 8 + 8 * kSides + 16 * kSlots + 8 * side; };  // value / logits complete
+    // Per stream item i: first layers complete (tcgen05.commit) and relu written back (one arrival per epilogue warp
+    // of the item), barrier i % (2 kSlots) each.  Two barriers per slot: a waiter that skips items (the epilogue warps
+    // take every other item, an MMA warp every fourth) could otherwise see its parity wait for item i satisfied by the
+    // completion of item i - 2 kSlots while item i - kSlots is still in flight.
+    auto bar_d1 = [&](int k) { return bar0 + 8 + 8 * kSides + 8 * k; };
+    auto bar_relu = [&](int k) { return bar0 + 8 + 8 * kSides + 8 * (2 * kSlots + k); };
+    auto bar_d2 = [&](int side) { return bar0 + 8 + 8 * kSides + 32 * kSlots + 8 * side; };  // value / logits complete
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + P::kTmem);
 
     if (warp == kMmaWarp) tmem_alloc<kTmemCols>(tmem_slot);
@@ -339,11 +359,11 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tc2_kernel(RolloutArgs g,
         mbar_init(bar_img, 1);
         for (int s = 0; s < kSides; ++s) {
             mbar_init(bar_a(s), 4);              // one arrival per head warp of the side
-            mbar_init(bar_d2(s), kMmaWarps);     // each MMA warp commits its half of the chunks
+            mbar_init(bar_d2(s), kMmaWarps);     // each MMA warp commits its chunk
         }
-        for (int s = 0; s < kSlots; ++s) {
-            mbar_init(bar_d1(s), 1);             // tcgen05.commit
-            mbar_init(bar_relu(s), kEpiWarps);   // one arrival per epilogue warp
+        for (int s = 0; s < 2 * kSlots; ++s) {
+            mbar_init(bar_d1(s), 1);
+            mbar_init(bar_relu(s), kEpiPerItem);
         }
         mbar_fence_init();
         tma_bulk_load(smem, image, P::kImageBytes, bar_img);
@@ -358,7 +378,7 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tc2_kernel(RolloutArgs g,
     if ((int64_t)blockIdx.x < num_pairs) my_pairs = (num_pairs - 1 - blockIdx.x) / gridDim.x + 1;
 
     if (warp >= kMmaWarp) {
-        // ------------------------------------------------------------ MMA issuers
+        // ------------------------------------------------------------ MMA issuers (keep the launch allocation)
         // The whole warp runs the loop converged and one elected lane issues: the descriptors then live in
         // uniform registers (an `if (lane == 0)` branch makes ptxas wrap every UTCHMMA in a waterfall loop).
         mbar_wait_c(bar_img, 0);
@@ -367,95 +387,125 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tc2_kernel(RolloutArgs g,
         constexpr uint32_t kIdesc1 = instr_desc(kChunk), kIdesc2 = instr_desc(kN2);
         // Stream item i = ((pair * T + t) * kSides + side) * kChunks + c lives in slot i % kSlots.  Its step is
         //     wait relu(i) -> MMA2(i) -> MMA1(i + kSlots) into the slot MMA2(i) has just read -> commit,
-        // and the two MMA warps take alternate items, so that the tensor core always has the other warp's work
-        // queued while one warp sits in a barrier wait.  Chunks of one parity accumulate into their own D2
-        // (MMAs of one thread execute in order; those of different threads are ordered by the barriers only).
-        const int w = warp - kMmaWarp;
-        const int64_t n_items = my_pairs * g.T * kSides * kChunks;
+        // and MMA warp w takes the items with c == w: issuing blocks while the tensor core's queue is full and every
+        // step has barrier latency around it, so several issuers keep the queue fed.  MMAs of one thread execute in
+        // issue order (that covers the slot reuse); MMA2s of different warps all ADD into the side's accumulator,
+        // which the head zeroes after reading it, so their order does not matter.
+        const int w = warp - kMmaWarp;           // == chunk index c of every item this warp issues
+        const uint32_t n_items = (uint32_t)(my_pairs * g.T * kSides * kChunks);
         int seen_hm[kSides] = {-1, -1};
-        auto mma1 = [&](int64_t j) {             // first layers of item j: A = observations in tensor memory
-            const int c = (int)(j & (kChunks - 1)), side = (int)(j / kChunks) & 1, slot = (int)(j % kSlots);
-            const int hm = (int)(j / (kChunks * kSides));   // half-move counter of the side
-            if (hm != seen_hm[side]) {           // the observations of this half-move must have been published
-                mbar_wait_c(bar_a(side), (uint32_t)hm & 1u);   // (each MMA warp checks for itself: they do not order each other)
+        // the observations of half-move `hm` of `side` must have been published before a first-layer MMA reads them
+        // (each MMA warp checks for itself: the warps do not order each other)
+        auto need_obs = [&](int side, int hm) {
+            if (hm != seen_hm[side]) {
+                mbar_wait_c(bar_a(side), (uint32_t)hm & 1u);
                 tc_fence_after();
                 seen_hm[side] = hm;
             }
-            if (elect_one()) {
-#pragma unroll
-                for (int s = 0; s < KP / 8; ++s)
-                    mma_ts(tmem_base + slot * kChunk, tmem_base + obs_col(side) + s * 8,
-                           w1_desc + (uint64_t)((c * (kChunk / 8) * P::kSbo1 + s * 256) >> 4), kIdesc1, s > 0);
-                mma_commit(bar_d1(slot));
-            }
-            __syncwarp();
         };
-        if (w == 0)
-            for (int64_t j = 0; j < kSlots && j < n_items; ++j) mma1(j);
+        // first layers of a chunk: A = observations in tensor memory (called by the elected lane)
+        auto mma1 = [&](int c, int side, int slot, int bar_index) {
+#pragma unroll
+            for (int s = 0; s < KP / 8; ++s)
+                mma_ts(tmem_base + slot * kChunk, tmem_base + obs_col(side) + s * 8,
+                       w1_desc + (uint64_t)((c * (kChunk / 8) * P::kSbo1 + s * 256) >> 4), kIdesc1, s > 0);
+            mma_commit(bar_d1(bar_index));
+        };
+        if (w == 0 && n_items > 0) {             // fill the ring: items 0 .. kSlots-1 are chunks 0 .. 2 of (side 0, half-move 0)
+            need_obs(0, 0);
+            if (elect_one())
+                for (int j = 0; j < kSlots; ++j) mma1(j, 0, j, j);
+            __syncwarp();
+        }
+        // item i = w, w + 4, ...: all index arithmetic incremental (no divisions in the loop)
+        int slot = w % kSlots, rb = w % (2 * kSlots);   // i % 3, i % 6
+        uint32_t par = 0;                                // (i / 6) & 1
+        int side = 0;                                    // (i / 4) & 1
+        const int cj = (w + kSlots) & (kChunks - 1);     // chunk index of item j = i + 3
+        int side_j = (w + kSlots) >> 2, hm_j = 0;        // its side ((j / 4) & 1) and half-move (j / 8), j = w + 3 < 8
 #pragma unroll 1
-        for (int64_t i = w; i < n_items; i += kMmaWarps) {
-            const int c = (int)(i & (kChunks - 1)), side = (int)(i / kChunks) & 1, slot = (int)(i % kSlots);
-            mbar_wait_c(bar_relu(slot), (uint32_t)(i / kSlots) & 1u);
+        for (uint32_t i = w; i < n_items; i += kMmaWarps) {
+            const bool has_j = i + kSlots < n_items;
+            if (has_j) need_obs(side_j, hm_j);
+            mbar_wait_c(bar_relu(rb), par);
             tc_fence_after();
             TRI(2, i, 0);
             if (elect_one()) {
 #pragma unroll
                 for (int s = 0; s < kChunk / 8; ++s)   // second layers: A = relu(hidden) in tensor memory
-                    mma_ts(tmem_base + d2_col(side) + 16 * w, tmem_base + slot * kChunk + s * 8,
-                           w2_desc + (uint64_t)(((c * (kChunk / 8) + s) * 256) >> 4), kIdesc2, (c >= kMmaWarps) || s > 0);
-                if (c + kMmaWarps >= kChunks) mma_commit(bar_d2(side));
+                    mma_ts(tmem_base + d2_col(side), tmem_base + slot * kChunk + s * 8,
+                           w2_desc + (uint64_t)(((w * (kChunk / 8) + s) * 256) >> 4), kIdesc2, true);
+                mma_commit(bar_d2(side));
+                if (has_j) mma1(cj, side_j, slot, rb >= kSlots ? rb - kSlots : rb + kSlots);   // item i + 3, into the slot just read
             }
             __syncwarp();
-            TRI(2, i, 1);
-            if (i + kSlots < n_items) mma1(i + kSlots);
             TRI(2, i, 2);
+            // i += 4
+            slot = slot + 1 == kSlots ? 0 : slot + 1;
+            rb += kMmaWarps;
+            if (rb >= 2 * kSlots) {
+                rb -= 2 * kSlots;
+                par ^= 1u;
+            }
+            side ^= 1;
+            side_j ^= 1;
+            if (side_j == 0) ++hm_j;             // j / 8 advances whenever j / 4 becomes even
         }
     } else if (warp >= kHeadWarps) {
         // ------------------------------------------------------------ epilogue of the first layers
+        if (kEpiWarps == 16) regs_dec<kRegsEpi>();
         const int e = warp - kHeadWarps;
-        constexpr int kPart = kEpiWarps / 4;                 // warps sharing a lane quadrant split the chunk's columns
-        constexpr int kCols = kChunk / kPart;
-        const uint32_t tmem_mine = tmem_base + ((uint32_t)((e & 3) * 32) << 16) + (uint32_t)((e >> 2) * kCols);
-        const float* b1 = reinterpret_cast<const float*>(smem + P::kB1) + (e >> 2) * kCols;
+        const int quad = e & 3, half = (e >> 2) & 1, parity = e >> 3;   // lane quadrant, 64-column half, item parity
+        constexpr int kCols = kChunk / 2;
+        const uint32_t tmem_mine = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(half * kCols);
+        const float* b1 = reinterpret_cast<const float*>(smem + P::kB1) + half * kCols;
         if (!P::kBiasInK) mbar_wait_c(bar_img, 0);
-        const int64_t n_items = my_pairs * g.T * kSides * kChunks;
-        uint32_t ph_d1 = 0;
-        int slot = 0, c = 0;
+        const uint32_t n_items = (uint32_t)(my_pairs * g.T * kSides * kChunks);
+        int slot = parity, rb = parity, c = parity;      // i % 3, i % 6, i % 4 of item i = parity, parity + kEpiStride, ...
+        uint32_t par = 0;                                // (i / 6) & 1
 #pragma unroll 1
-        for (int64_t i = 0; i < n_items; ++i) {
-            mbar_wait_c(bar_d1(slot), (ph_d1 >> slot) & 1u);
-            ph_d1 ^= 1u << slot;
+        for (uint32_t i = parity; i < n_items; i += kEpiStride) {
+            mbar_wait_c(bar_d1(rb), par);
             tc_fence_after();
             if (e == 0) TRI(2, i, 3);
             const uint32_t taddr = tmem_mine + slot * kChunk;
-            uint32_t r[kCols];
 #pragma unroll
-            for (int q = 0; q < kCols / 32; ++q) tmem_ld32p(taddr + q * 32, r + q * 32);
-            tmem_ld_wait();
-            if (!P::kBiasInK) {
-                const float4* bias = reinterpret_cast<const float4*>(b1 + c * kChunk);
+            for (int q = 0; q < kCols / 32; ++q) {       // 32 columns at a time: 32 data registers
+                uint32_t r[32];
+                tmem_ld32p(taddr + q * 32, r);
+                tmem_ld_wait();
+                if (!P::kBiasInK) {
+                    const float4* bias = reinterpret_cast<const float4*>(b1 + c * kChunk + q * 32);
 #pragma unroll
-                for (int k = 0; k < kCols / 4; ++k) {
-                    const float4 bb = bias[k];
-                    r[4 * k + 0] = __float_as_uint(__uint_as_float(r[4 * k + 0]) + bb.x);
-                    r[4 * k + 1] = __float_as_uint(__uint_as_float(r[4 * k + 1]) + bb.y);
-                    r[4 * k + 2] = __float_as_uint(__uint_as_float(r[4 * k + 2]) + bb.z);
-                    r[4 * k + 3] = __float_as_uint(__uint_as_float(r[4 * k + 3]) + bb.w);
+                    for (int k = 0; k < 8; ++k) {
+                        const float4 bb = bias[k];
+                        r[4 * k + 0] = __float_as_uint(__uint_as_float(r[4 * k + 0]) + bb.x);
+                        r[4 * k + 1] = __float_as_uint(__uint_as_float(r[4 * k + 1]) + bb.y);
+                        r[4 * k + 2] = __float_as_uint(__uint_as_float(r[4 * k + 2]) + bb.z);
+                        r[4 * k + 3] = __float_as_uint(__uint_as_float(r[4 * k + 3]) + bb.w);
+                    }
                 }
+#pragma unroll
+                for (int k = 0; k < 32; ++k) r[k] = __float_as_uint(fmaxf(__uint_as_float(r[k]), 0.f));
+                tmem_st32(taddr + q * 32, r);
             }
-#pragma unroll
-            for (int k = 0; k < kCols; ++k) r[k] = __float_as_uint(fmaxf(__uint_as_float(r[k]), 0.f));
-#pragma unroll
-            for (int q = 0; q < kCols / 32; ++q) tmem_st32(taddr + q * 32, r + q * 32);
             tmem_st_wait();
             tc_fence_before();
             __syncwarp();
-            if ((tid & 31) == 0) mbar_arrive(bar_relu(slot));
-            slot = slot + 1 == kSlots ? 0 : slot + 1;
-            c = (c + 1) & (kChunks - 1);
+            if ((tid & 31) == 0) mbar_arrive(bar_relu(rb));
+            if (e == 0) TRI(2, i, 4);
+            // i += kEpiStride
+            slot = slot + kEpiStride >= kSlots ? slot + kEpiStride - kSlots : slot + kEpiStride;
+            rb += kEpiStride;
+            if (rb >= 2 * kSlots) {
+                rb -= 2 * kSlots;
+                par ^= 1u;
+            }
+            c = (c + kEpiStride) & (kChunks - 1);
         }
     } else {
         // ------------------------------------------------------------ heads: one thread per game
+        if (kEpiWarps == 16) regs_inc<kRegsHead>();
         const int side = warp >> 2;
         const int lane_g = tid & (kTileM - 1);                // game of the tile == TMEM lane
         const int lane = tid & 31;
@@ -491,6 +541,11 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tc2_kernel(RolloutArgs g,
 
             // observation words of half-move t in tf32 (A operand of the first layers) -> tensor memory; critical path
             auto publish_obs = [&]() {
+                tmem_ld_wait();          // this thread's read of the accumulators is complete before they are cleared
+                {
+                    const uint32_t zero[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+                    tmem_st8(my_d2, zero);   // the second-layer MMAs of the next half-move only ever accumulate
+                }
 #pragma unroll
                 for (int q = 0; q < KP / 8; ++q) {
                     uint32_t v[8];
@@ -502,9 +557,8 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tc2_kernel(RolloutArgs g,
                     }
                     tmem_st8(my_obs + 8 * q, v);
                 }
-                tmem_ld_wait();          // this thread's read of D2 is complete ...
                 tmem_st_wait();
-                tc_fence_before();       // ... and ordered, with the stores above, before the MMAs the arrival releases
+                tc_fence_before();       // orders the stores above before the MMAs the arrival releases
                 __syncwarp();
                 if (lane == 0) mbar_arrive(my_bar_a);
             };
@@ -578,15 +632,14 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tc2_kernel(RolloutArgs g,
                     ph_d2 ^= 1u;
                     tc_fence_after();
                     if (lane_g == 0) TR(side, t, 1);
-                    uint32_t d2[8], d2b[8];                        // partial sums of the even / odd chunks
+                    uint32_t d2[8];
                     tmem_ld8(my_d2, d2);
-                    tmem_ld8(my_d2 + 16, d2b);
                     if (turn == 0 && more) publish_obs();          // critical path of a row half-move ends here
                     tmem_ld_wait();
-                    const float value = (__uint_as_float(d2[0]) + __uint_as_float(d2b[0])) + b2v;
+                    const float value = __uint_as_float(d2[0]) + b2v;
                     float logit[A];
 #pragma unroll
-                    for (int a = 0; a < A; ++a) logit[a] = (__uint_as_float(d2[1 + a]) + __uint_as_float(d2b[1 + a])) + b2p[a];
+                    for (int a = 0; a < A; ++a) logit[a] = __uint_as_float(d2[1 + a]) + b2p[a];
                     float policy[A];
                     masked_softmax_fast<A>(logit, n_legal, policy);
                     const int action = sample_icdf(policy, A, u.action);

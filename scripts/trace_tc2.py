@@ -27,10 +27,9 @@ for role, name in enumerate(["head side 0", "head side 1"]):
         row = buf[role, t]
         print(f"  t={t}", " ".join(f"{(x - t0) if x else -1:6d}" for x in row[:5]))
 
-# stream items 16..55: MMA warp timestamps relative to "relu seen"
+# stream items 16..55, MMA warp (item % 2): absolute "relu seen", then cycles after it
 mma = buf[2].reshape(-1)[:320].reshape(-1, 8)
-fine = buf[3].reshape(-1)[:320].reshape(-1, 8)
-print("item | elected, after MMA2 #1, #4, #8, #12, #16, commit | MMA2 region done | MMA1 region done   (cycles after relu seen)")
-for j in range(24):
+print("item warp side c | relu seen (abs) | MMA2 issued | obs barrier passed | MMA1(+3) issued")
+for j in range(40):
     base = mma[j, 0]
-    print(f"{j+16:4d} | " + " ".join(f"{x-base:6d}" for x in fine[j, :7]) + f" | {mma[j,1]-base:6d} | {mma[j,2]-base:6d}")
+    print(f"{j+16:4d} {(j+16)%2:4d} {((j+16)//4)%2:4d} {(j+16)%4} | {base-t0:9d} | {mma[j,1]-base:6d} | {mma[j,3]-base:6d} | {mma[j,2]-base:6d}")
