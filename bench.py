@@ -272,16 +272,22 @@ def run_native(args):
     assert int(runner.t_last.item()) == T - 1
 
     # ---- e2e: public API with host buffers
-    pinned_w = {k: v.pin_memory() for k, v in weights_cpu.items()}
+    # the actor's parameters become views of one flat device buffer, so that a fresh set of weights from the host
+    # (a learner elsewhere, a checkpoint) is ONE pinned host -> device copy
+    flat_host = torch.cat([v.flatten() for v in weights_cpu.values()]).pin_memory()
+    flat_dev = torch.empty_like(flat_host, device=dev)
+    flat_dev.copy_(flat_host)
+    offset = 0
+    with torch.no_grad():
+        for p in net.parameters():               # registration order == state_dict order
+            p.data = flat_dev[offset: offset + p.numel()].view_as(p)
+            offset += p.numel()
     returns_host = torch.empty(batch, dtype=torch.float32).pin_memory()
-    state = dict(net.named_parameters())
-    h2d_bytes = sum(v.numel() * 4 for v in pinned_w.values())
+    h2d_bytes = flat_host.numel() * 4
     d2h_bytes = batch * 4 + 4                   # per-game returns + t_eff
 
     def e2e_step():
-        with torch.no_grad():
-            for k, v in pinned_w.items():
-                state[k].copy_(v, non_blocking=True)
+        flat_dev.copy_(flat_host, non_blocking=True)
         ep = Episodes(tree, batch)
         ep.generate(net, precision=precision)
         returns_host.copy_(ep.rewards.sum(0), non_blocking=True)
@@ -431,7 +437,7 @@ def main():
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--config", default="cfg2", choices=sorted(CONFIGS))
     ap.add_argument("--batch", type=int, default=0, help="games per GPU (default: the config's)")
-    ap.add_argument("--precision", default="tf32", choices=["tf32", "tf32x2", "fp32"])
+    ap.add_argument("--precision", default="tf32x2", choices=["tf32", "tf32x2", "fp32"])
     ap.add_argument("--cpu-budget", type=float, default=15.0, help="seconds of CPU work for cpu_baseline")
     ap.add_argument("--reference-batch", type=int, default=65536)
     args = ap.parse_args()

@@ -25,6 +25,7 @@ PRECISIONS = {"fp32": PREC_FP32, "tf32": PREC_TF32, "tf32x2": PREC_TF32X2}
 EXPORTS = (
     "rnad_last_error", "rnad_version", "rnad_device_sm_count", "rnad_packed_strides", "rnad_tree_pack",
     "rnad_observe", "rnad_step", "rnad_sample_categorical", "rnad_rollout", "rnad_rollout_workspace_bytes", "rnad_rollout_tc_supported",
+    "rnad_rollout_tc2_supported",
     "rnad_process_policy", "rnad_vtrace", "rnad_learner_targets_workspace", "rnad_count_played",
     "rnad_learner_targets", "rnad_learner_mlp_supported", "rnad_learner_mlp_workspace_bytes",
     "rnad_learner_param_count", "rnad_learner_forward", "rnad_learner_backward",
@@ -109,7 +110,7 @@ def lib():
         POINTER(LearnerFwdOut), c_void_p, c_void_p]
     L.rnad_learner_backward.argtypes = [c_void_p, c_int64, c_int, POINTER(MlpWeights), c_void_p, c_void_p, c_void_p,
                                         c_void_p, c_void_p]
-    no_errcheck = ("rnad_version", "rnad_device_sm_count", "rnad_rollout_tc_supported", "rnad_learner_mlp_supported",
+    no_errcheck = ("rnad_version", "rnad_device_sm_count", "rnad_rollout_tc_supported", "rnad_rollout_tc2_supported", "rnad_learner_mlp_supported",
                    "rnad_learner_param_count")
     for name in EXPORTS:
         fn = getattr(L, name)

@@ -140,6 +140,21 @@ class States:
         return rewards
 
 
+_scratch_cache = {}
+
+
+def _rollout_scratch(dev, a, width, prec):
+    """Per (device, stream, net shape, engine): the t_eff word and the kernel workspace, reused in stream order."""
+    key = (dev.index if dev.index is not None else torch.cuda.current_device(), _b200.stream(), a, width, prec)
+    hit = _scratch_cache.get(key)
+    if hit is None:
+        ws_bytes = int(_b200.lib().rnad_rollout_workspace_bytes(a, width, prec))
+        hit = (torch.empty(1, dtype=torch.int32, device=dev),
+               torch.empty(ws_bytes, dtype=torch.uint8, device=dev) if ws_bytes else None)
+        _scratch_cache[key] = hit
+    return hit
+
+
 class Episodes:
     """A batch of rollout trajectories from the root; tensors are time-major (T, B, ...)."""
 
@@ -164,17 +179,40 @@ class Episodes:
         self.values: torch.Tensor = None
         self.masks: torch.Tensor = None
 
-        self.q_estimates: torch.Tensor = None
-        self.v_estimates: torch.Tensor = None
+        self._q_estimates: torch.Tensor = None
+        self._v_estimates: torch.Tensor = None
+
+    # The reference fills these two with zeros after every rollout (episode.py:226-227) and never reads them on the
+    # training path; here they are materialised on first access.
+    @property
+    def q_estimates(self) -> torch.Tensor:
+        if self._q_estimates is None and self.policy is not None:
+            self._q_estimates = torch.zeros_like(self.policy)
+        return self._q_estimates
+
+    @q_estimates.setter
+    def q_estimates(self, value):
+        self._q_estimates = value
+
+    @property
+    def v_estimates(self) -> torch.Tensor:
+        if self._v_estimates is None and self.rewards is not None:
+            self._v_estimates = torch.zeros_like(self.rewards)
+        return self._v_estimates
+
+    @v_estimates.setter
+    def v_estimates(self, value):
+        self._v_estimates = value
 
     # ----------------------------------------------------------------- rollout
 
     def generate(self, net: torch.nn.Module, precision: str = None, uniforms: torch.Tensor = None):
         """
         Plays the batch to the end with `net` as the actor (episode.py:175-230).
-        precision: "tf32" (tcgen05 tensor cores) | "fp32" (CUDA cores) | None = the
-        net's `rollout_precision`, else $RNAD_ROLLOUT_PRECISION, else tf32 where the
-        tensor-core engine supports the net shape.  uniforms: optional (T, B, 2)
+        precision: "tf32x2" (both layers of the net on tcgen05 tensor cores) | "tf32" (first
+        layers on tcgen05, second on the CUDA cores) | "fp32" (CUDA cores throughout) | None =
+        the net's `rollout_precision`, else $RNAD_ROLLOUT_PRECISION, else the fastest engine
+        that supports the net and tree shape.  uniforms: optional (T, B, 2)
         injected action / chance uniforms (parity tests).
         """
         from nn.net import MLP
@@ -198,41 +236,47 @@ class Episodes:
         if precision is None:
             precision = getattr(net, "rollout_precision", None) or os.environ.get("RNAD_ROLLOUT_PRECISION")
         if precision is None:
-            precision = "tf32" if L.rnad_rollout_tc_supported(a, net.width) else "fp32"
+            if L.rnad_rollout_tc2_supported(a, net.width, packed.C):
+                precision = "tf32x2"
+            else:
+                precision = "tf32" if L.rnad_rollout_tc_supported(a, net.width) else "fp32"
         t_max = packed.max_half_moves
         w = _b200.mlp_weights(net, dev)
+        prec = _b200.PRECISIONS[precision]
 
         with torch.cuda.device(dev):
-            out = {
-                "indices": torch.empty((t_max, b), dtype=torch.int64, device=dev),
-                "turns": torch.empty((t_max, b), dtype=torch.int64, device=dev),
-                "observations": torch.empty((t_max, b, 2, a, a), dtype=torch.float32, device=dev),
-                "policy": torch.empty((t_max, b, a), dtype=torch.float32, device=dev),
-                "actions": torch.empty((t_max, b, a), dtype=torch.float32, device=dev),
-                "rewards": torch.empty((t_max, b), dtype=torch.float32, device=dev),
-                "values": torch.empty((t_max, b), dtype=torch.float32, device=dev),
-                "masks": torch.empty((t_max, b, a), dtype=torch.float32, device=dev),
-            }
+            # one allocation for the whole trajectory: the eight (T, B, ...) tensors are views of it
+            fields = (("indices", torch.int64, ()), ("turns", torch.int64, ()), ("observations", torch.float32, (2, a, a)),
+                      ("policy", torch.float32, (a,)), ("actions", torch.float32, (a,)), ("rewards", torch.float32, ()),
+                      ("values", torch.float32, ()), ("masks", torch.float32, (a,)))
+            offsets, total = [], 0
+            for _, dtype, tail in fields:
+                offsets.append(total)
+                n_bytes = t_max * b * int(numpy.prod(tail, dtype=numpy.int64)) * (8 if dtype == torch.int64 else 4)
+                total += (n_bytes + 255) // 256 * 256
+            arena = torch.empty(total, dtype=torch.uint8, device=dev)
+            out = {}
+            for (key, dtype, tail), off in zip(fields, offsets):
+                n_bytes = t_max * b * int(numpy.prod(tail, dtype=numpy.int64)) * (8 if dtype == torch.int64 else 4)
+                out[key] = arena[off: off + n_bytes].view(dtype).view((t_max, b) + tail)
             traj = _b200.Trajectory(**{k: v.data_ptr() for k, v in out.items()})
-            t_last = torch.full((1,), -1, dtype=torch.int32, device=dev)
             if uniforms is not None:
                 uniforms = uniforms.to(device=dev, dtype=torch.float32).contiguous()
                 if uniforms.shape[0] < t_max or tuple(uniforms.shape[1:]) != (b, 2):
                     raise _b200.RnadError(f"uniforms must be ({t_max}+, {b}, 2), got {tuple(uniforms.shape)}")
                 uniforms = uniforms[:t_max].contiguous()
-            ws_bytes = int(L.rnad_rollout_workspace_bytes(a, net.width, _b200.PRECISIONS[precision]))
-            workspace = torch.empty(ws_bytes, dtype=torch.uint8, device=dev) if ws_bytes else None
+            t_last, workspace = _rollout_scratch(dev, a, net.width, prec)
+            t_last.fill_(-1)
             L.rnad_rollout(_b200.ptr(packed.ev_tab), _b200.ptr(packed.tr_tab), a, packed.C, ctypes.byref(w), b, t_max,
-                           self.states.seed, self.states.game_offset, _b200.ptr(uniforms),
-                           _b200.PRECISIONS[precision], ctypes.byref(traj), _b200.ptr(t_last), _b200.ptr(workspace),
-                           _b200.stream())
+                           self.states.seed, self.states.game_offset, _b200.ptr(uniforms), prec, ctypes.byref(traj),
+                           _b200.ptr(t_last), _b200.ptr(workspace), _b200.stream())
             self.t_eff = int(t_last.item())          # the rollout's only host synchronisation
         self.precision = precision
         n = self.t_eff + 1
         for key, value in out.items():
             setattr(self, key, value[:n])
-        self.q_estimates = torch.zeros_like(self.policy)
-        self.v_estimates = torch.zeros_like(self.rewards)
+        self._q_estimates = None
+        self._v_estimates = None
         self.states._idx.zero_()
         self.states._moved = True
         self.states._terminal = True
