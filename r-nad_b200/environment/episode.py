@@ -145,7 +145,8 @@ _scratch_cache = {}
 
 def _rollout_scratch(dev, a, width, prec):
     """Per (device, stream, net shape, engine): the t_eff word and the kernel workspace, reused in stream order."""
-    key = (dev.index if dev.index is not None else torch.cuda.current_device(), _b200.stream(), a, width, prec)
+    key = (dev.index if dev.index is not None else torch.cuda.current_device(),
+           int(torch.cuda.current_stream(dev).cuda_stream), a, width, prec)
     hit = _scratch_cache.get(key)
     if hit is None:
         ws_bytes = int(_b200.lib().rnad_rollout_workspace_bytes(a, width, prec))
