@@ -48,7 +48,11 @@ CONFIGS = {
     "cfg1": (2, 2, 1, 256),
     "cfg2": (4, 3, 2, 65536),
     "cfg2small": (3, 3, 2, 8192),
+    # full regular tree of 14,900,789 nodes (7.9 GB in the reference layout, HBM-resident gathers); built on the GPU by
+    # the level-synchronous generator (environment/fast_tree.py) - the reference generator would need about two days
+    "cfg3": (6, 3, 3, 262144),
 }
+FAST_TREE_CONFIGS = ("cfg3",)
 
 
 def algorithmic_bytes_per_env_step(a, c):
@@ -244,13 +248,21 @@ def run_native(args):
     depth, a, c, batch = CONFIGS[args.config]
     if args.batch:
         batch = args.batch
-    tree_cpu = make_tree(depth, a, c, seed=0)
-    tables = {"index": tree_cpu.index_tensor.clone(), "value": tree_cpu.value_tensor.clone(),
-              "chance": tree_cpu.chance_tensor.clone(), "expected_value": tree_cpu.expected_value_tensor.clone(),
-              "legal": tree_cpu.legal_tensor.clone()}
-    n_nodes = int(tree_cpu.index_tensor.shape[0])
-    tree = tree_cpu
-    tree.to(dev)
+    if args.config in FAST_TREE_CONFIGS:
+        from environment.tree import Tree
+
+        tree = Tree(device=dev, max_actions=a, max_transitions=c, depth_bound=depth)
+        tree.generate_fast(seed=0)
+        tables = None                            # copied to the host only if the CPU baseline runs
+        n_nodes = int(tree.index_tensor.shape[0])
+    else:
+        tree_cpu = make_tree(depth, a, c, seed=0)
+        tables = {"index": tree_cpu.index_tensor.clone(), "value": tree_cpu.value_tensor.clone(),
+                  "chance": tree_cpu.chance_tensor.clone(), "expected_value": tree_cpu.expected_value_tensor.clone(),
+                  "legal": tree_cpu.legal_tensor.clone()}
+        n_nodes = int(tree_cpu.index_tensor.shape[0])
+        tree = tree_cpu
+        tree.to(dev)
     torch.manual_seed(1234)
     net = MLP(a, 256, device=dev)
     weights_cpu = {k: v.detach().cpu().clone() for k, v in net.state_dict().items()}
@@ -332,12 +344,17 @@ def run_native(args):
         achieved_gbs = bytes_per_launch / per_launch_s / 1e9
         tflops = flops_per_env_step(a) * env_steps / per_launch_s / 1e12
         cpu = None
-        if world == 1 or True:
+        if world == 1 and args.cpu_budget > 0:   # rank 0 at N = 1 only
             threads = os.cpu_count() or 1
-            cpu_value, cpu_rollouts, cpu_elapsed = cpu_rollout_baseline(tables, weights_cpu, a, batch, T,
+            if tables is None:
+                tables = {"index": tree.index_tensor.cpu(), "value": tree.value_tensor.cpu(),
+                          "chance": tree.chance_tensor.cpu(), "expected_value": tree.expected_value_tensor.cpu(),
+                          "legal": tree.legal_tensor.cpu()}
+            cpu_batch = min(batch, 65536)
+            cpu_value, cpu_rollouts, cpu_elapsed = cpu_rollout_baseline(tables, weights_cpu, a, cpu_batch, T,
                                                                         args.cpu_budget, threads)
             cpu = {"value": cpu_value, "unit": "env_steps/s", "cores": threads, "kind": "port",
-                   "sample": f"{cpu_rollouts} rollouts of {batch} games x {T} half-moves on the same tree and net "
+                   "sample": f"{cpu_rollouts} rollouts of {cpu_batch} games x {T} half-moves on the same tree and net "
                              f"({cpu_elapsed:.1f} s, torch-CPU ops, {threads} threads)"}
         result = {
             "metric": "self_play_env_steps_per_sec", "value": value, "unit": "env_steps/s",
@@ -393,7 +410,13 @@ def run_reference(args):
     depth, a, c, batch = CONFIGS[args.config]
     if args.batch:
         batch = args.batch
-    tree = make_tree(depth, a, c, seed=0)
+    if args.config in FAST_TREE_CONFIGS:
+        from environment.tree import Tree
+
+        tree = Tree(max_actions=a, max_transitions=c, depth_bound=depth)
+        tree.generate_fast(seed=0)               # on the host cores: minutes for the 14.9 M-node tree
+    else:
+        tree = make_tree(depth, a, c, seed=0)
     tables = {"index": tree.index_tensor, "value": tree.value_tensor, "chance": tree.chance_tensor,
               "expected_value": tree.expected_value_tensor, "legal": tree.legal_tensor}
     torch.manual_seed(1234)

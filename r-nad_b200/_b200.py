@@ -195,7 +195,7 @@ class PackedTree:
             raise RnadError("tree has a legal mask that is not a prefix rectangle (reference tree.py:133 always builds one)")
         if flag == 2:
             raise RnadError("tree has a child index outside [0, S)")
-        self.max_half_moves = 2 * _tree_depth(idx)
+        self.max_half_moves = 2 * (getattr(tree, "_depth_hint", None) or _tree_depth(idx))
 
     def nbytes(self):
         return self.ev_tab.numel() * 4 + self.tr_tab.numel() * 4

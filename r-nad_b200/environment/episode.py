@@ -22,6 +22,7 @@ with Philox4x32-10 and select by inverse CDF (oracle/rnad_oracle.py pins both).
 """
 
 import ctypes
+import math
 import os
 import random
 import time
@@ -36,8 +37,22 @@ from environment.tree import Tree
 _game_offset_rank_stride = 1 << 40   # disjoint Philox game ids per data-parallel rank
 
 
+_seed_state = [None, 0]   # torch.initial_seed() the counter belongs to, batches drawn since
+
+
 def _fresh_seed() -> int:
-    return int(torch.randint(0, 2 ** 62, (1,), dtype=torch.int64).item())
+    """
+    A new 62-bit rollout seed per batch, a pure function of torch's seed (so `torch.manual_seed` makes runs
+    reproducible) and of how many batches were drawn since - splitmix64, no tensor op and no device round trip.
+    """
+    base = torch.initial_seed()
+    if _seed_state[0] != base:
+        _seed_state[0], _seed_state[1] = base, 0
+    _seed_state[1] += 1
+    z = (base + _seed_state[1] * 0x9E3779B97F4A7C15) & 0xFFFFFFFFFFFFFFFF
+    z = ((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9) & 0xFFFFFFFFFFFFFFFF
+    z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & 0xFFFFFFFFFFFFFFFF
+    return (z ^ (z >> 31)) >> 2
 
 
 def _rank() -> int:
@@ -52,7 +67,8 @@ class States:
     def __init__(self, tree: Tree, batch_size, seed=None):
         self.tree = tree
         self.batch_size = batch_size
-        self._idx = torch.ones((batch_size,), dtype=torch.int32, device=tree.device)
+        self._idx_tensor = None      # (B,) int32 node ids, created on first use:
+        self._idx_fill = 1           # every game starts at the root, node 1 (episode.py:22)
         self._moved = False          # reference: indices is int32 until the first transition, int64 after
         self._turn = 0
         self.row_actions = None
@@ -62,6 +78,16 @@ class States:
         self._t = 0
         self.seed = _fresh_seed() if seed is None else int(seed)
         self.game_offset = _rank() * _game_offset_rank_stride
+
+    @property
+    def _idx(self) -> torch.Tensor:
+        if self._idx_tensor is None:
+            self._idx_tensor = torch.full((self.batch_size,), self._idx_fill, dtype=torch.int32, device=self.tree.device)
+        return self._idx_tensor
+
+    @_idx.setter
+    def _idx(self, value: torch.Tensor):
+        self._idx_tensor = value
 
     # -- reference attributes ------------------------------------------------
     @property
@@ -218,15 +244,16 @@ class Episodes:
         """
         from nn.net import MLP
 
-        net.eval()
         time_start = time.perf_counter()
         if type(net) is MLP:
-            self._generate_fused(net, precision, uniforms)
+            self._generate_fused(net, precision, uniforms)     # the kernel reads the weights: no mode to switch
         else:
+            net.eval()
             self._generate_stepwise(net)
         self.generation_time = time.perf_counter() - time_start
         self.finished = True
-        net.train()
+        if not net.training or type(net) is not MLP:
+            net.train()                                        # the reference leaves the actor in training mode
 
     def _generate_fused(self, net, precision, uniforms):
         L = _b200.lib()
@@ -253,12 +280,12 @@ class Episodes:
             offsets, total = [], 0
             for _, dtype, tail in fields:
                 offsets.append(total)
-                n_bytes = t_max * b * int(numpy.prod(tail, dtype=numpy.int64)) * (8 if dtype == torch.int64 else 4)
+                n_bytes = t_max * b * math.prod(tail) * (8 if dtype == torch.int64 else 4)
                 total += (n_bytes + 255) // 256 * 256
             arena = torch.empty(total, dtype=torch.uint8, device=dev)
             out = {}
             for (key, dtype, tail), off in zip(fields, offsets):
-                n_bytes = t_max * b * int(numpy.prod(tail, dtype=numpy.int64)) * (8 if dtype == torch.int64 else 4)
+                n_bytes = t_max * b * math.prod(tail) * (8 if dtype == torch.int64 else 4)
                 out[key] = arena[off: off + n_bytes].view(dtype).view((t_max, b) + tail)
             traj = _b200.Trajectory(**{k: v.data_ptr() for k, v in out.items()})
             if uniforms is not None:
@@ -278,7 +305,7 @@ class Episodes:
             setattr(self, key, value[:n])
         self._q_estimates = None
         self._v_estimates = None
-        self.states._idx.zero_()
+        self.states._idx_tensor, self.states._idx_fill = None, 0    # every game ended on the absorbing node
         self.states._moved = True
         self.states._terminal = True
 

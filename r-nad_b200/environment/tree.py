@@ -124,6 +124,7 @@ class Tree:
         self.col_actions_lambda = col_actions_lambda or (lambda node: node.col_actions)
         self.depth_bound_lambda = depth_bound_lambda or (lambda node: node.depth_bound - 1)
         self._packed = None
+        self._depth_hint = None      # number of levels, when the generator knows it
 
     # ------------------------------------------------------------------ build
 
@@ -222,6 +223,18 @@ class Tree:
         if self.is_root:
             self.hash = torch.randint(-(2 ** 63), 2 ** 63 - 1, size=(1,)).item()
         self._packed = None
+
+    def generate_fast(self, seed: int = 0, child_spec=None, **kwargs):
+        """
+        Level-synchronous, batched construction on `self.device` (environment/fast_tree.py): the way to build the
+        large trees the recursive generator cannot (millions of nodes).  Level-order node ids; ignores the three
+        per-node Python lambdas (`child_spec` is their vectorised counterpart).
+        """
+        from environment.fast_tree import generate_fast
+
+        if not self.is_root:
+            raise Exception("generate_fast builds whole trees (is_root=True)")
+        return generate_fast(self, seed=seed, child_spec=child_spec, **kwargs)
 
     # --------------------------------------------------------------- checks
 
