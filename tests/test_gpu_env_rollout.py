@@ -127,9 +127,13 @@ def test_mlp_forward_matches_reference(golden):
 # --------------------------------------------------------------------- K2
 
 TOL = {"fp32": dict(rtol=1e-5, atol=2e-6), "tf32": dict(rtol=0, atol=4e-3), "tf32x2": dict(rtol=0, atol=6e-3)}
-# the tensor-core engines against their own numerics restated on the CPU (oracle.mlp_forward_tc): what is left
-# is fp32 accumulation order inside the MMAs
-TOL_TC = dict(rtol=0, atol=1e-4)
+# The tensor-core engines against their own numerics restated on the CPU (oracle.mlp_forward_tc).  What is left is the
+# fp32 accumulation order inside the MMAs: ~1e-7 typically (the MEAN error bound below), and - rarely - a hidden
+# activation that the two orders put on different sides of a tf32 truncation boundary (one tf32 ulp, 2^-10, of one of
+# the 512 terms of a second-layer dot product: the MAX error bound).  Measured on 360,000 rows: mean 3.5e-7, max 2.2e-4;
+# rounding instead of truncating the activations in the emulation gives mean 2.4e-4.
+TOL_TC = dict(rtol=0, atol=5e-4)
+TOL_TC_MEAN = 5e-6
 SECOND_LAYER = {"tf32": "fp32", "tf32x2": "tf32"}
 
 
@@ -162,6 +166,8 @@ def check_rollout_against_oracle(ep, tables, w, seed=None, uniforms=None, game_o
             _, policy_tc, value_tc, _, _, _ = orc.mlp_forward_tc(w, obs.reshape(B, -1), SECOND_LAYER[precision])
             close(cpu(ep.policy[s]), policy_tc, **TOL_TC)
             close(cpu(ep.values[s]), value_tc[:, 0], **TOL_TC)
+            assert float((cpu(ep.values[s]).double() - value_tc[:, 0]).abs().mean()) < TOL_TC_MEAN
+            assert float((cpu(ep.policy[s]).double() - policy_tc).abs().mean()) < TOL_TC_MEAN
         pol_gpu = cpu(ep.policy[s])
         assert bool((pol_gpu[orc.mover_mask(obs) == 0] == 0).all())
         close(pol_gpu.sum(-1), torch.ones(B), rtol=0, atol=1e-6)
