@@ -469,15 +469,16 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tc2_kernel(RolloutArgs g,
             tc_fence_after();
             if (e == 0) TRI(2, i, 3);
             const uint32_t taddr = tmem_mine + slot * kChunk;
+            if (kEpiWarps == 8) {
+                // both 32-column loads in flight, one wait
+                uint32_t r[kCols];
 #pragma unroll
-            for (int q = 0; q < kCols / 32; ++q) {       // 32 columns at a time: 32 data registers
-                uint32_t r[32];
-                tmem_ld32p(taddr + q * 32, r);
+                for (int q = 0; q < kCols / 32; ++q) tmem_ld32p(taddr + q * 32, r + q * 32);
                 tmem_ld_wait();
                 if (!P::kBiasInK) {
-                    const float4* bias = reinterpret_cast<const float4*>(b1 + c * kChunk + q * 32);
+                    const float4* bias = reinterpret_cast<const float4*>(b1 + c * kChunk);
 #pragma unroll
-                    for (int k = 0; k < 8; ++k) {
+                    for (int k = 0; k < kCols / 4; ++k) {
                         const float4 bb = bias[k];
                         r[4 * k + 0] = __float_as_uint(__uint_as_float(r[4 * k + 0]) + bb.x);
                         r[4 * k + 1] = __float_as_uint(__uint_as_float(r[4 * k + 1]) + bb.y);
@@ -486,8 +487,30 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tc2_kernel(RolloutArgs g,
                     }
                 }
 #pragma unroll
-                for (int k = 0; k < 32; ++k) r[k] = __float_as_uint(fmaxf(__uint_as_float(r[k]), 0.f));
-                tmem_st32(taddr + q * 32, r);
+                for (int k = 0; k < kCols; ++k) r[k] = __float_as_uint(fmaxf(__uint_as_float(r[k]), 0.f));
+#pragma unroll
+                for (int q = 0; q < kCols / 32; ++q) tmem_st32(taddr + q * 32, r + q * 32);
+            } else {
+#pragma unroll
+                for (int q = 0; q < kCols / 32; ++q) {   // 32 columns at a time: 32 data registers (the 16-warp budget)
+                    uint32_t r[32];
+                    tmem_ld32p(taddr + q * 32, r);
+                    tmem_ld_wait();
+                    if (!P::kBiasInK) {
+                        const float4* bias = reinterpret_cast<const float4*>(b1 + c * kChunk + q * 32);
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) {
+                            const float4 bb = bias[k];
+                            r[4 * k + 0] = __float_as_uint(__uint_as_float(r[4 * k + 0]) + bb.x);
+                            r[4 * k + 1] = __float_as_uint(__uint_as_float(r[4 * k + 1]) + bb.y);
+                            r[4 * k + 2] = __float_as_uint(__uint_as_float(r[4 * k + 2]) + bb.z);
+                            r[4 * k + 3] = __float_as_uint(__uint_as_float(r[4 * k + 3]) + bb.w);
+                        }
+                    }
+#pragma unroll
+                    for (int k = 0; k < 32; ++k) r[k] = __float_as_uint(fmaxf(__uint_as_float(r[k]), 0.f));
+                    tmem_st32(taddr + q * 32, r);
+                }
             }
             tmem_st_wait();
             tc_fence_before();
