@@ -48,8 +48,13 @@ constexpr int kHeadWarps = 4 * kSides;           // warps 0..7: one thread per g
 // every other stream item, and registers are re-allocated between the roles).  Measured on cfg2: 8 warps 0.066 ms,
 // 16 warps 0.072 ms per rollout - more warps lengthen the heads' critical path more than they shorten the epilogue's.
 constexpr int kEpiWarps = RNAD_TC2_EPI_WARPS;
-constexpr int kEpiStride = kEpiWarps / 8;        // an epilogue warp takes every kEpiStride-th stream item
-constexpr int kEpiPerItem = 8;                   // warps working on one stream item
+#ifndef RNAD_TC2_EPI_WIDE
+#define RNAD_TC2_EPI_WIDE 0
+#endif
+// RNAD_TC2_EPI_WIDE (8 warps only): a warp takes all 128 columns of its lane quadrant, of every other stream item
+constexpr bool kEpiWide = RNAD_TC2_EPI_WIDE != 0 && kEpiWarps == 8;
+constexpr int kEpiStride = kEpiWide ? 2 : kEpiWarps / 8;   // an epilogue warp takes every kEpiStride-th stream item
+constexpr int kEpiPerItem = kEpiWide ? 4 : 8;              // warps working on one stream item
 static_assert(kEpiWarps == 8 || kEpiWarps == 16, "8 or 16 epilogue warps");
 constexpr int kMmaWarp = kHeadWarps + kEpiWarps;   // first of the MMA warps
 constexpr int kMmaWarps = 4;                       // stream item i is issued by MMA warp i % 4, i.e. one warp per chunk index
@@ -455,7 +460,8 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tc2_kernel(RolloutArgs g,
         // ------------------------------------------------------------ epilogue of the first layers
         if (kEpiWarps == 16) regs_dec<kRegsEpi>();
         const int e = warp - kHeadWarps;
-        const int quad = e & 3, half = (e >> 2) & 1, parity = e >> 3;   // lane quadrant, 64-column half, item parity
+        // lane quadrant, 64-column half, item parity
+        const int quad = e & 3, half = kEpiWide ? 0 : (e >> 2) & 1, parity = kEpiWide ? (e >> 2) & 1 : e >> 3;
         constexpr int kCols = kChunk / 2;
         const uint32_t tmem_mine = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(half * kCols);
         const float* b1 = reinterpret_cast<const float*>(smem + P::kB1) + half * kCols;
@@ -470,13 +476,16 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tc2_kernel(RolloutArgs g,
             if (e == 0) TRI(2, i, 3);
             const uint32_t taddr = tmem_mine + slot * kChunk;
             if (kEpiWarps == 8) {
+#pragma unroll
+              for (int hh = 0; hh < (kEpiWide ? 2 : 1); ++hh) {
                 // both 32-column loads in flight, one wait
+                const uint32_t taddr = tmem_mine + slot * kChunk + hh * kCols;
                 uint32_t r[kCols];
 #pragma unroll
                 for (int q = 0; q < kCols / 32; ++q) tmem_ld32p(taddr + q * 32, r + q * 32);
                 tmem_ld_wait();
                 if (!P::kBiasInK) {
-                    const float4* bias = reinterpret_cast<const float4*>(b1 + c * kChunk);
+                    const float4* bias = reinterpret_cast<const float4*>(b1 + c * kChunk + hh * kCols);
 #pragma unroll
                     for (int k = 0; k < kCols / 4; ++k) {
                         const float4 bb = bias[k];
@@ -490,6 +499,7 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tc2_kernel(RolloutArgs g,
                 for (int k = 0; k < kCols; ++k) r[k] = __float_as_uint(fmaxf(__uint_as_float(r[k]), 0.f));
 #pragma unroll
                 for (int q = 0; q < kCols / 32; ++q) tmem_st32(taddr + q * 32, r + q * 32);
+              }
             } else {
 #pragma unroll
                 for (int q = 0; q < kCols / 32; ++q) {   // 32 columns at a time: 32 data registers (the 16-warp budget)
