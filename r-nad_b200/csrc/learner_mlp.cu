@@ -18,6 +18,8 @@
 // In the reference these are 8 x T small GEMMs + ~40 elementwise launches forward and
 // autograd's mirror image backward, with the (T*B x 256) activations written to and
 // re-read from HBM about ten times per update.
+#include <cstdlib>
+
 #include "tc_common.cuh"
 
 namespace rnad {
@@ -533,6 +535,317 @@ __global__ void __launch_bounds__(kLearnThreads, 1) learner_bwd_kernel(const flo
     if (warp == 0) tmem_dealloc<512>(tmem_base);
 }
 
+// -------------------------------------------------------- backward on the tensor core
+//
+// dW1 = dh^T x, db1 = dh^T 1 and dW2 = relu(h)^T g are contractions over the ROWS of a tile, while tensor memory
+// holds an accumulator with rows as lanes.  So the trunks are recomputed TRANSPOSED: H^T[j][n] = W1[j,:] . X^T[:,n]
+// (A operand = the first-layer weights, B operand = the observation tile, both K-major in shared memory) puts hidden
+// unit j on lane j and row n on column n.  The thread of lane j turns its columns into relu(h)^T and
+// dh^T = ((g W2) * [h > 0])^T in place, and those are A operands *in tensor memory* (K = rows) for
+//     D_w1[j][c] += sum_n dh^T[j][n]   BX[c][n]      BX rows: x^T (2A^2 rows), ones     -> dW1, db1
+//     D_w2[j][c] += sum_n relu^T[j][n] BG[c][n]      BG rows: d_v, d_logit[0..A)        -> dW2
+// whose accumulators stay in tensor memory over all tiles of the CTA.  No activation ever leaves the SM and the
+// CUDA cores do ~9 instructions per (row, hidden unit) instead of ~40.  Deterministic (fixed order everywhere).
+
+constexpr int kBwdTcThreads = 512;   // four threads per hidden unit (TMEM lane), 32 rows (columns) each
+
+template <int A>
+struct BwdTcPlan : Shape<A> {
+    using S = Shape<A>;
+    static constexpr int kNX = round_up(S::KIN + 1, 16);               // rows of BX = N of the dW1 / db1 MMA
+    static constexpr int kNG = 16;                                     // rows of BG = N of the dW2 MMA
+    static constexpr int kLbo = 144;                                   // K-chunk stride of BX / BG: 128 + 16 bytes of padding make the
+                                                                       // transposing stores (32 rows n of one operand row c) conflict-free
+    static constexpr int kSboT = (kTileM / 4) * kLbo;                  // 8-row groups of BX / BG
+    static constexpr int kB = 0;                                       // image: both trunks' first layers [256 x KP] tf32, K-major
+    static constexpr int kB1 = kB + 2 * S::kTrunkBytes;                //        their biases, 2 x 256 f32
+    static constexpr int kImageBytes = kB1 + 2 * kHidden * 4;          // (same image as pack_bwd_image_kernel writes)
+    static constexpr int kX = kImageBytes;                             // observation tile [128 x KP] tf32, K-major
+    static constexpr int kBX = kX + kTileM * S::KP * 4;
+    static constexpr int kBG = kBX + (kNX / 8) * kSboT;
+    static constexpr int kG = kBG + (kNG / 8) * kSboT;                 // g[n][8] fp32: d_v, d_logit[0..A)
+    static constexpr int kRed = kG + kTileM * 32;                      // [4 warps][8] partial sums of g (output-bias gradients)
+    static constexpr int kBar = kRed + 4 * 32;
+    static constexpr int kTmem = kBar + 32;
+    static constexpr int kBytes = kTmem + 16;
+    // tensor memory: [0,128) H^T -> relu^T, [128,256) dh^T, then 4 x kNX columns of D_w1 and 4 x 16 of D_w2
+    static constexpr int kColW1 = 256, kColW2 = 256 + 4 * kNX;
+    static_assert(kColW2 + 4 * kNG <= 512, "accumulators do not fit tensor memory");
+    static_assert(kBytes <= 227 * 1024, "shared memory plan does not fit");
+    static_assert(kX % 16 == 0 && kBX % 16 == 0 && kBG % 16 == 0 && kG % 16 == 0 && kBar % 8 == 0, "alignment");
+};
+
+__host__ __device__ constexpr uint32_t idesc_tf32(int n) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
+}
+
+__device__ __forceinline__ uint64_t desc_lbo_sbo(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+    d |= (uint64_t)(lbo_bytes >> 4) << 16;
+    d |= (uint64_t)(sbo_bytes >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    return d;
+}
+
+__device__ __forceinline__ void mma_ss_n(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, bool acc) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+        "}\n" ::"r"(d_tmem),
+        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"((uint32_t)acc)
+        : "memory");
+}
+__device__ __forceinline__ void mma_ts_n(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, bool acc) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t"
+        "}\n" ::"r"(d_tmem),
+        "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"((uint32_t)acc)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st32r(uint32_t taddr, const uint32_t* r) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+        "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+        "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]),
+        "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]),
+        "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait_all() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+template <int A>
+__global__ void __launch_bounds__(kBwdTcThreads, 1) learner_bwd_tc_kernel(const float* __restrict__ obs, int64_t N,
+                                                                           const uint8_t* __restrict__ image,
+                                                                           rnad_mlp_weights w,
+                                                                           const float* __restrict__ d_logit,
+                                                                           const float* __restrict__ d_v,
+                                                                           float* __restrict__ partials) {
+    using P = BwdTcPlan<A>;
+    constexpr int KIN = P::KIN, KP = P::KP;
+    static_assert(A <= 4, "g[n] is staged as 8 floats");
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const int tid = threadIdx.x, warp = tid >> 5, lane32 = tid & 31;
+    const int quad = warp & 3, cpart = warp >> 2;             // TMEM lane quadrant (hidden units), 32-column (row) part
+    const int j_local = quad * 32 + lane32;                   // hidden unit of the current 128-unit half == TMEM lane
+    const uint32_t bar_img = smem_u32(smem + P::kBar), bar_mma = bar_img + 8;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + P::kTmem);
+
+    if (warp == 0) tmem_alloc<512>(tmem_slot);
+    if (tid == 0) {
+        mbar_init(bar_img, 1);
+        mbar_init(bar_mma, 1);
+        mbar_fence_init();
+        tma_bulk_load(smem, image, P::kImageBytes, bar_img);
+    }
+    // operand rows that are never written stay zero
+    for (int i = tid; i < ((P::kNX + P::kNG) / 8) * P::kSboT / 4; i += kBwdTcThreads) reinterpret_cast<uint32_t*>(smem + P::kBX)[i] = 0u;
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    mbar_wait(bar_img, 0);
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tmem_lane = tmem_base + ((uint32_t)(quad * 32) << 16);
+    {   // clear the gradient accumulators: columns [256, 512), 64 per thread of a lane
+        uint32_t zero[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) zero[i] = 0u;
+#pragma unroll
+        for (int q = 0; q < 2; ++q) tmem_st32r(tmem_lane + 256 + cpart * 64 + q * 32, zero);
+        tmem_st_wait_all();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+
+    const float* b1 = reinterpret_cast<const float*>(smem + P::kB1);
+    float* s_g = reinterpret_cast<float*>(smem + P::kG);
+    auto off_t = [](int c, int n) { return (c >> 3) * P::kSboT + (n >> 2) * P::kLbo + (c & 7) * 16 + (n & 3) * 4; };
+    float gsum[1 + A];
+#pragma unroll
+    for (int a = 0; a <= A; ++a) gsum[a] = 0.f;
+    // this lane's hidden units (one per 128-unit half): second-layer weights and first-layer bias, loaded once
+    float w2v_j[2], w2p_j[2][A], bias_v[2], bias_p[2];
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+        const int j = half * 128 + j_local;
+        w2v_j[half] = __ldg(w.value_fc1_w + j);
+#pragma unroll
+        for (int a = 0; a < A; ++a) w2p_j[half][a] = __ldg(w.policy_fc1_w + a * kHidden + j);
+        bias_v[half] = P::kBiasInK ? 0.f : b1[j];
+        bias_p[half] = P::kBiasInK ? 0.f : b1[kHidden + j];
+    }
+
+    uint32_t phase = 0;
+    const int64_t num_tiles = (N + kTileM - 1) / kTileM;
+    for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        // ---- the tile's operands: observation tile (B of the recompute), x^T | 1 and g^T (B of the gradient MMAs)
+        if (tid < kTileM) {
+            const int n = tid;
+            const int64_t row = tile * kTileM + n;
+            const bool active = row < N;
+            float x[KIN];
+            load_row<KIN>(obs, row, active, x);
+            store_operand_row<KIN, KP, P::kBiasInK>(smem + P::kX, n, x);
+#pragma unroll
+            for (int k = 0; k < KIN; ++k) *reinterpret_cast<float*>(smem + P::kBX + off_t(k, n)) = to_tf32(x[k]);
+            *reinterpret_cast<float*>(smem + P::kBX + off_t(KIN, n)) = 1.f;
+            float g[1 + A];
+            g[0] = active ? d_v[row] : 0.f;
+#pragma unroll
+            for (int a = 0; a < A; ++a) g[1 + a] = active ? d_logit[row * A + a] : 0.f;
+#pragma unroll
+            for (int a = 0; a <= A; ++a) {
+                *reinterpret_cast<float*>(smem + P::kBG + off_t(a, n)) = to_tf32(g[a]);
+                s_g[n * 8 + a] = g[a];
+                gsum[a] += g[a];
+            }
+            fence_async_smem();
+        }
+        tc_fence_before();
+        __syncthreads();
+
+        // H^T = W1[trunk, half] . X^T   (M = hidden units, N = rows, K = inputs), into columns [0, 128)
+        auto recompute = [&](int th) {
+            const int trunk = th >> 1, half = th & 1;
+            const uint32_t a_base = smem_u32(smem + P::kB) + trunk * P::kTrunkBytes + half * (128 / 8) * ((KP / 4) * 128);
+            const uint32_t b_base = smem_u32(smem + P::kX);
+#pragma unroll
+            for (int ks = 0; ks < KP / 8; ++ks)
+                mma_ss_n(tmem_base, make_desc<KP>(a_base + ks * 256), make_desc<KP>(b_base + ks * 256), idesc_tf32(128), ks > 0);
+        };
+        if (tid == 0) {
+            tc_fence_after();
+            recompute(0);
+            mma_commit(bar_mma);
+        }
+#pragma unroll 1
+        for (int th = 0; th < 4; ++th) {                      // (trunk, 128-unit half)
+            const int trunk = th >> 1, half = th & 1;
+            float w2[A > 1 ? A : 1];
+            if (trunk == 0) {
+                w2[0] = half ? w2v_j[1] : w2v_j[0];
+            } else {
+#pragma unroll
+                for (int a = 0; a < A; ++a) w2[a] = half ? w2p_j[1][a] : w2p_j[0][a];
+            }
+            const float bias_j = trunk == 0 ? (half ? bias_v[1] : bias_v[0]) : (half ? bias_p[1] : bias_p[0]);
+            mbar_wait(bar_mma, phase);                        // H^T of this stage (and the gradient MMAs of the previous one)
+            phase ^= 1u;
+            tc_fence_after();
+            // ---- this thread's 32 rows of its hidden unit: relu^T in place, dh^T next to it
+            uint32_t hr[32], dh[32];
+            tmem_ld32(tmem_lane + cpart * 32, hr);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+                const int n = cpart * 32 + i;
+                const float h = __uint_as_float(hr[i]) + bias_j;
+                const float4 g0 = *reinterpret_cast<const float4*>(s_g + n * 8);
+                float s;
+                if (trunk == 0) {
+                    s = g0.x * w2[0];
+                } else {
+                    s = g0.y * w2[0];
+                    if (A > 1) s = fmaf(g0.z, w2[A > 1 ? 1 : 0], s);
+                    if (A > 2) s = fmaf(g0.w, w2[A > 2 ? 2 : 0], s);
+                    if (A > 3) s = fmaf(s_g[n * 8 + 4], w2[A > 3 ? 3 : 0], s);
+                }
+                const bool on = h > 0.f;
+                hr[i] = __float_as_uint(on ? to_tf32(h) : 0.f);
+                dh[i] = __float_as_uint(on ? to_tf32(s) : 0.f);
+            }
+            tmem_st32r(tmem_lane + cpart * 32, hr);
+            tmem_st32r(tmem_lane + 128 + cpart * 32, dh);
+            tmem_st_wait_all();
+            tc_fence_before();
+            __syncthreads();
+            // ---- D_w2 += relu^T BG^T, D_w1 += dh^T BX^T (K = the 128 rows of the tile), then the next stage's H^T:
+            //      the tensor core executes one thread's MMAs in order, so the recompute may overwrite relu^T right
+            //      behind the MMAs that read it, and one commit covers the three groups
+            if (tid == 0) {
+                tc_fence_after();
+                const uint64_t bx = desc_lbo_sbo(smem_u32(smem + P::kBX), P::kLbo, P::kSboT);
+                const uint64_t bg = desc_lbo_sbo(smem_u32(smem + P::kBG), P::kLbo, P::kSboT);
+#pragma unroll
+                for (int ks = 0; ks < kTileM / 8; ++ks)
+                    mma_ts_n(tmem_base + P::kColW2 + th * P::kNG, tmem_base + ks * 8, bg + (uint64_t)((ks * 2 * P::kLbo) >> 4),
+                             idesc_tf32(P::kNG), true);
+#pragma unroll
+                for (int ks = 0; ks < kTileM / 8; ++ks)
+                    mma_ts_n(tmem_base + P::kColW1 + th * P::kNX, tmem_base + 128 + ks * 8, bx + (uint64_t)((ks * 2 * P::kLbo) >> 4),
+                             idesc_tf32(P::kNX), true);
+                if (th < 3) recompute(th + 1);
+                mma_commit(bar_mma);
+            }
+        }
+        mbar_wait(bar_mma, phase);                            // the last gradient MMAs have read the tile's operands
+        phase ^= 1u;
+        tc_fence_after();
+        __syncthreads();
+    }
+
+    // ---- this CTA's partial gradient, flat in state_dict order
+    float* dst = partials + (int64_t)blockIdx.x * P::kParams;
+    if (cpart == 0) {
+#pragma unroll 1
+        for (int th = 0; th < 4; ++th) {
+            const int trunk = th >> 1, j = (th & 1) * 128 + j_local;
+            uint32_t acc[P::kNX];
+#pragma unroll
+            for (int q = 0; q < P::kNX / 16; ++q) tmem_ld16(tmem_lane + P::kColW1 + th * P::kNX + q * 16, acc + q * 16);
+            tmem_ld_wait();
+            float* w1_dst = dst + (trunk == 0 ? P::kOffV0w : P::kOffP0w) + j * KIN;
+#pragma unroll
+            for (int k = 0; k < KIN; ++k) w1_dst[k] = __uint_as_float(acc[k]);
+            dst[(trunk == 0 ? P::kOffV0b : P::kOffP0b) + j] = __uint_as_float(acc[KIN]);
+            uint32_t acc2[16];
+            tmem_ld16(tmem_lane + P::kColW2 + th * P::kNG, acc2);
+            tmem_ld_wait();
+            if (trunk == 0) {
+                dst[P::kOffV1w + j] = __uint_as_float(acc2[0]);
+            } else {
+#pragma unroll
+                for (int a = 0; a < A; ++a) dst[P::kOffP1w + a * kHidden + j] = __uint_as_float(acc2[1 + a]);
+            }
+        }
+    }
+    // output-bias gradients: sums of g over the CTA's rows (threads 0..127 each own one row of every tile)
+    float* s_red = reinterpret_cast<float*>(smem + P::kRed);
+    if (tid < kTileM) {
+#pragma unroll
+        for (int a = 0; a <= A; ++a) {
+            const float v = warp_sum(gsum[a]);
+            if (lane32 == 0) s_red[warp * 8 + a] = v;
+        }
+    }
+    __syncthreads();
+    if (tid <= A) {
+        const float v = (s_red[0 * 8 + tid] + s_red[1 * 8 + tid]) + (s_red[2 * 8 + tid] + s_red[3 * 8 + tid]);
+        if (tid == 0) dst[P::kOffV1b] = v;
+        else dst[P::kOffP1b + tid - 1] = v;
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc<512>(tmem_base);
+}
+
 __global__ void reduce_partials_kernel(const float* __restrict__ partials, int n_parts, int n_params,
                                        float* __restrict__ flat_grad) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -578,17 +891,29 @@ template <int A>
 int launch_backward(const float* obs, int64_t N, const rnad_mlp_weights& w, const float* d_logit, const float* d_v,
                     float* flat_grad, uint8_t* workspace, cudaStream_t st) {
     using P = BwdPlan<A>;
+    using PT = BwdTcPlan<A>;
+    static_assert(PT::kImageBytes == P::kImageBytes && PT::kB1 == P::kB1, "both backward kernels read the same weight image");
     uint8_t* image = workspace + round_up(FwdPlan<A>::kImageBytes, 256);
     float* partials = reinterpret_cast<float*>(image + round_up(P::kImageBytes, 256));
     pack_bwd_image_kernel<A><<<24, 256, 0, st>>>(w, image);
     RNAD_CHECK_LAUNCH("pack_bwd_image_kernel");
-    int rc = prepare<A>(learner_bwd_kernel<A>, P::kBytes, "cudaFuncSetAttribute(learner_bwd)");
-    if (rc) return rc;
     int64_t blocks = (N + kTileM - 1) / kTileM;
     const int cap = sm_count() < kMaxBwdCtas ? sm_count() : kMaxBwdCtas;
     if (blocks > cap) blocks = cap;
-    learner_bwd_kernel<A><<<(int)blocks, kLearnThreads, P::kBytes, st>>>(obs, N, image, w, d_logit, d_v, partials);
-    RNAD_CHECK_LAUNCH("learner_bwd_kernel");
+    static const bool cuda_core_reduction = getenv("RNAD_LEARNER_BWD_CUDA_CORES") != nullptr;   // the previous kernel, for A/B runs
+    if (cuda_core_reduction) {
+        int rc = prepare<A>(learner_bwd_kernel<A>, P::kBytes, "cudaFuncSetAttribute(learner_bwd)");
+        if (rc) return rc;
+        learner_bwd_kernel<A><<<(int)blocks, kLearnThreads, P::kBytes, st>>>(obs, N, image, w, d_logit, d_v, partials);
+        RNAD_CHECK_LAUNCH("learner_bwd_kernel");
+    } else {
+        // one CTA per SM owns all 512 TMEM columns: request more than half of the shared memory
+        const size_t smem = PT::kBytes > 116 * 1024 ? PT::kBytes : 116 * 1024;
+        int rc = prepare<A>(learner_bwd_tc_kernel<A>, smem, "cudaFuncSetAttribute(learner_bwd_tc)");
+        if (rc) return rc;
+        learner_bwd_tc_kernel<A><<<(int)blocks, kBwdTcThreads, smem, st>>>(obs, N, image, w, d_logit, d_v, partials);
+        RNAD_CHECK_LAUNCH("learner_bwd_tc_kernel");
+    }
     reduce_partials_kernel<<<(P::kParams + 255) / 256, 256, 0, st>>>(partials, (int)blocks, P::kParams, flat_grad);
     RNAD_CHECK_LAUNCH("reduce_partials_kernel");
     return RNAD_OK;
