@@ -143,21 +143,38 @@ def ptr(t, dtype=None):
     return c_void_p(t.data_ptr())
 
 
+_LAYERS = ("value_fc0", "value_fc1", "policy_fc0", "policy_fc1")
+
+
 def mlp_weights(net, device=None):
-    """rnad_mlp_weights for an nn.net.MLP (fp32, contiguous, on one CUDA device); keeps the tensors alive on the struct."""
+    """
+    rnad_mlp_weights for an nn.net.MLP (fp32, contiguous, on one CUDA device); keeps the tensors alive on the struct.
+    The struct is cached on the net and rebuilt only when a parameter's storage changed.
+    """
+    tensors = []
+    for layer in _LAYERS:
+        lin = getattr(net, layer)
+        tensors.append(lin.weight)
+        tensors.append(lin.bias)
+    key = tuple(t.data_ptr() for t in tensors) + (str(device),)
+    cached = net.__dict__.get("_b200_weights")
+    if cached is not None and cached[0] == key:
+        return cached[1]
     w = MlpWeights()
     keep = []
-    for layer in ("value_fc0", "value_fc1", "policy_fc0", "policy_fc1"):
+    for layer in _LAYERS:
         lin = getattr(net, layer)
         for suffix, tensor in (("w", lin.weight), ("b", lin.bias)):
             tensor = tensor.detach()
             if tensor.dtype != torch.float32 or not tensor.is_cuda or (device is not None and tensor.device != device):
                 raise RnadError(f"{layer}: the kernels need fp32 weights on {device or 'a CUDA device'}")
-            tensor = tensor.contiguous()
+            if not tensor.is_contiguous():
+                raise RnadError(f"{layer}: the kernels need contiguous weights")
             keep.append(tensor)
             setattr(w, f"{layer}_{suffix}", tensor.data_ptr())
     w.width = net.width
     w._keep = keep
+    net.__dict__["_b200_weights"] = (key, w)
     return w
 
 

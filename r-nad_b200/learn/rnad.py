@@ -38,6 +38,52 @@ import nn.net as net
 import util.metric as metric
 
 
+class _GraphedTail:
+    """
+    The optimizer tail of one learner step (clip_grad_norm_, Adam, target-net average) as a CUDA graph.
+    The first step after (re)building runs eagerly - it creates Adam's state - the second one captures, and from
+    then on a step is one graph launch.  Anything the graph bakes in is part of the key: the optimizer object and
+    its hyper-parameters, the parameter / gradient / target storages, the clip and averaging constants.
+    """
+
+    def __init__(self, trial):
+        self.key = self._key(trial)
+        self.graph = None
+        self.warm = False
+        for group in trial.optimizer.param_groups:      # step counts live on the device, so that step() never syncs
+            if not group.get("capturable", False):
+                group["capturable"] = True
+                for p in group["params"]:
+                    st = trial.optimizer.state.get(p)
+                    if st and "step" in st:
+                        st["step"] = torch.as_tensor(st["step"], dtype=torch.float32).to(p.device)
+
+    @staticmethod
+    def _key(trial):
+        params = list(trial.net.parameters())
+        return (id(trial.optimizer), id(trial.net), id(trial.net_target),
+                tuple(p.data_ptr() for p in params), tuple(p.grad.data_ptr() if p.grad is not None else 0 for p in params),
+                tuple(p.data_ptr() for p in trial.net_target.parameters()),
+                tuple((g["lr"], tuple(g["betas"]), g["eps"], g["weight_decay"]) for g in trial.optimizer.param_groups),
+                float(trial.grad_clip), float(trial.gamma_averaging), torch.cuda.current_device())
+
+    def matches(self, trial):
+        return self.key == self._key(trial)
+
+    def step(self, trial):
+        if self.graph is not None:
+            self.graph.replay()
+        elif not self.warm:
+            trial._eager_tail(clip=True)
+            self.warm = True
+        else:
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                trial._eager_tail(clip=True)
+            self.graph = graph
+            graph.replay()
+
+
 class RNaD:
     def __init__(
         self,
@@ -125,6 +171,9 @@ class RNaD:
         self.nashconv_history = []   # (total_steps, NashConv of the target net)
         self.learner_engine = None   # None = auto: "fused" tensor-core kernels where supported, else "torch"
         self._fused = None
+        self.graph_optimizer_tail = os.environ.get("RNAD_GRAPH_TAIL", "1") != "0"   # see _GraphedTail
+        self._tail = None
+        self._defer_clip = False
 
     # ------------------------------------------------------------------ nets
 
@@ -309,21 +358,14 @@ class RNaD:
                     "actor_learner_kld": metric.kld(pi, episodes.policy, valid, legal_actions=masks),
                 })
 
-        nn.utils.clip_grad_norm_(self.net.parameters(), self.grad_clip)
+        if not self._defer_clip:
+            nn.utils.clip_grad_norm_(self.net.parameters(), self.grad_clip)
 
-    def learner_step(self, alpha: float, buffer: "episode.Buffer" = None, log: dict = None):
-        """One iteration of the rnad.py:495 loop body without the schedule bookkeeping: rollout, learn, Adam, EMA."""
-        if buffer is None:
-            buffer = self.__dict__.setdefault("_buffer", episode.Buffer(self.n_batches_per_buffer))
-        if self.total_steps % self.buffer_mod == 0:
-            episodes = episode.Episodes(self.tree, self.batch_size)
-            episodes.generate(self.net)
-            buffer.append(episodes)
-        episodes_sample = buffer.sample(self.batch_size)
-        self.__learn(episodes_sample, alpha, log=log)
+    def _eager_tail(self, clip: bool):
+        """clip_grad_norm_ (rnad.py:456), Adam (514-515), target <- g * net + (1 - g) * target (516-523)."""
+        if clip:
+            nn.utils.clip_grad_norm_(self.net.parameters(), self.grad_clip)
         self.optimizer.step()
-        self.optimizer.zero_grad()
-        # target <- gamma_averaging * net + (1 - gamma_averaging) * target   (rnad.py:516-523)
         with torch.no_grad():
             g = self.gamma_averaging
             src, dst = self.net.state_dict(), self.net_target.state_dict()
@@ -335,6 +377,32 @@ class RNaD:
             for k, t in dst.items():
                 if not t.is_floating_point():   # e.g. BatchNorm's num_batches_tracked
                     t.copy_(g * src[k] + (1 - g) * t)
+
+    def learner_step(self, alpha: float, buffer: "episode.Buffer" = None, log: dict = None):
+        """One iteration of the rnad.py:495 loop body without the schedule bookkeeping: rollout, learn, Adam, EMA."""
+        if buffer is None:
+            buffer = self.__dict__.setdefault("_buffer", episode.Buffer(self.n_batches_per_buffer))
+        if self.total_steps % self.buffer_mod == 0:
+            episodes = episode.Episodes(self.tree, self.batch_size)
+            episodes.generate(self.net)
+            buffer.append(episodes)
+        episodes_sample = buffer.sample(self.batch_size)
+        # With the fused learner engine the gradients live in one persistent flat buffer, so everything after them -
+        # clipping, Adam, the target-net average: ~20 small launches - has fixed addresses and replays as ONE CUDA graph.
+        graphed = (self.graph_optimizer_tail and log is None and isinstance(self.optimizer, torch.optim.Adam)
+                   and fused.engine_for(self.net, self.learner_engine) == "fused")
+        self._defer_clip = graphed
+        try:
+            self.__learn(episodes_sample, alpha, log=log)
+        finally:
+            self._defer_clip = False
+        if graphed:
+            if self._tail is None or not self._tail.matches(self):
+                self._tail = _GraphedTail(self)
+            self._tail.step(self)
+        else:
+            self._eager_tail(clip=False)
+            self.optimizer.zero_grad()
         return episodes_sample
 
     def __resume(self, max_updates=10 ** 6, checkpoint_mod=1000, expl_mod=1, log_mod=20) -> None:
