@@ -51,8 +51,11 @@ CONFIGS = {
     # full regular tree of 14,900,789 nodes (7.9 GB in the reference layout, HBM-resident gathers); built on the GPU by
     # the level-synchronous generator (environment/fast_tree.py) - the reference generator would need about two days
     "cfg3": (6, 3, 3, 262144),
+    # BASELINE config 4, per-GPU share (1,048,576 games over 8 GPUs): depth 8, A = 4, C = 2 thinned like main.py
+    # (transition_threshold 0.3, depth_bound - 1 - 2 * (random() < 0.5)); the full regular tree would be 3.5e10 nodes
+    "cfg4": (8, 4, 2, 131072),
 }
-FAST_TREE_CONFIGS = ("cfg3",)
+FAST_TREE_CONFIGS = ("cfg3", "cfg4")
 
 
 def algorithmic_bytes_per_env_step(a, c):
@@ -95,6 +98,20 @@ def profiled_dram_traffic(kernel, config):
                 return None
             total += float(cells[2]) * scale
     return total or None
+
+
+def fast_tree(config, depth, a, c, device):
+    """The large configurations' trees, built level by level on `device` (environment/fast_tree.py)."""
+    from environment.fast_tree import depth_jitter
+    from environment.tree import Tree
+
+    if config == "cfg4":
+        tree = Tree(device=device, max_actions=a, max_transitions=c, depth_bound=depth, transition_threshold=0.3)
+        tree.generate_fast(seed=0, child_spec=depth_jitter(0.5))
+    else:
+        tree = Tree(device=device, max_actions=a, max_transitions=c, depth_bound=depth)
+        tree.generate_fast(seed=0)
+    return tree
 
 
 def measured_peaks():
@@ -271,8 +288,7 @@ def run_native(args):
     if args.config in FAST_TREE_CONFIGS:
         from environment.tree import Tree
 
-        tree = Tree(device=dev, max_actions=a, max_transitions=c, depth_bound=depth)
-        tree.generate_fast(seed=0)
+        tree = fast_tree(args.config, depth, a, c, dev)
         tables = None                            # copied to the host only if the CPU baseline runs
         n_nodes = int(tree.index_tensor.shape[0])
     else:
@@ -289,7 +305,7 @@ def run_native(args):
     precision = args.precision
     runner = RolloutRunner(tree, net, batch, precision)
     T = runner.T
-    env_steps = batch * T                       # regular tree: every (t, b) slot is a valid env step
+    env_steps = batch * T                       # regular tree: every (t, b) slot is a valid env step (ragged: counted below)
 
     flush_buf = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)
 
@@ -302,6 +318,9 @@ def run_native(args):
     # ---- value: kernel throughput, everything resident
     kernel_ms, _ = timed_steps(runner.launch, args.steps, args.warmup, flush, barrier)
     assert int(runner.t_last.item()) == T - 1
+    # one env step = one VALID (t, b) slot: all of them on a regular tree, counted on the last rollout of a ragged one
+    env_steps = int((runner.out["indices"] != 0).sum().item())
+    assert env_steps == batch * T or args.config == "cfg4"
 
     # ---- e2e: public API with host buffers
     # the actor's parameters become views of one flat device buffer, so that a fresh set of weights from the host
@@ -434,8 +453,7 @@ def run_reference(args):
     if args.config in FAST_TREE_CONFIGS:
         from environment.tree import Tree
 
-        tree = Tree(max_actions=a, max_transitions=c, depth_bound=depth)
-        tree.generate_fast(seed=0)               # on the host cores: minutes for the 14.9 M-node tree
+        tree = fast_tree(args.config, depth, a, c, torch.device("cpu"))   # on the host cores: minutes for the largest trees
     else:
         tree = make_tree(depth, a, c, seed=0)
     tables = {"index": tree.index_tensor, "value": tree.value_tensor, "chance": tree.chance_tensor,

@@ -209,11 +209,40 @@ class Episodes:
         self._q_estimates: torch.Tensor = None
         self._v_estimates: torch.Tensor = None
 
+    # After a fused rollout the trajectory length t_eff is still on the device.  Reading it is the rollout's only host
+    # synchronisation, and it is deferred until somebody asks: `t_eff` and the eight (t_eff + 1, B, ...) tensors resolve
+    # on first access (the kernel wrote all `t_max` half-moves; slots past t_eff sit on the absorbing node, index 0).
+    # The learner's fast path never asks - it takes the full-length tensors from `full()` and lets the validity mask
+    # `indices != 0` do the rest - so rollout, learner passes and optimizer are enqueued without a single host wait.
+    _LAZY = ("t_eff", "indices", "turns", "observations", "policy", "actions", "rewards", "values", "masks")
+
+    def __getattr__(self, name):
+        # only reached when normal lookup fails, i.e. for a lazy attribute that has not been resolved yet
+        if name in Episodes._LAZY and "_pending" in self.__dict__:
+            self._resolve()
+            return self.__dict__[name]
+        raise AttributeError(name)
+
+    def _resolve(self):
+        pending = self.__dict__.pop("_pending", None)
+        if pending is None:
+            return
+        full, t_last = pending
+        self.__dict__["t_eff"] = int(t_last.item())
+        n = self.__dict__["t_eff"] + 1
+        for key, value in full.items():
+            self.__dict__[key] = value[:n]
+
+    def full(self, key: str) -> torch.Tensor:
+        """The (t_max, B, ...) tensor a fused rollout wrote, without waiting for t_eff; else the stored tensor."""
+        pending = self.__dict__.get("_pending")
+        return pending[0][key] if pending is not None else getattr(self, key)
+
     # The reference fills these two with zeros after every rollout (episode.py:226-227) and never reads them on the
     # training path; here they are materialised on first access.
     @property
     def q_estimates(self) -> torch.Tensor:
-        if self._q_estimates is None and self.policy is not None:
+        if self._q_estimates is None and (self.__dict__.get("policy") is not None or "_pending" in self.__dict__):
             self._q_estimates = torch.zeros_like(self.policy)
         return self._q_estimates
 
@@ -223,7 +252,7 @@ class Episodes:
 
     @property
     def v_estimates(self) -> torch.Tensor:
-        if self._v_estimates is None and self.rewards is not None:
+        if self._v_estimates is None and (self.__dict__.get("rewards") is not None or "_pending" in self.__dict__):
             self._v_estimates = torch.zeros_like(self.rewards)
         return self._v_estimates
 
@@ -282,7 +311,7 @@ class Episodes:
                 offsets.append(total)
                 n_bytes = t_max * b * math.prod(tail) * (8 if dtype == torch.int64 else 4)
                 total += (n_bytes + 255) // 256 * 256
-            arena = torch.empty(total, dtype=torch.uint8, device=dev)
+            arena = torch.empty(total + 256, dtype=torch.uint8, device=dev)
             out = {}
             for (key, dtype, tail), off in zip(fields, offsets):
                 n_bytes = t_max * b * math.prod(tail) * (8 if dtype == torch.int64 else 4)
@@ -293,16 +322,16 @@ class Episodes:
                 if uniforms.shape[0] < t_max or tuple(uniforms.shape[1:]) != (b, 2):
                     raise _b200.RnadError(f"uniforms must be ({t_max}+, {b}, 2), got {tuple(uniforms.shape)}")
                 uniforms = uniforms[:t_max].contiguous()
-            t_last, workspace = _rollout_scratch(dev, a, net.width, prec)
+            _, workspace = _rollout_scratch(dev, a, net.width, prec)
+            t_last = arena[total: total + 4].view(torch.int32)     # this batch's own t_eff word
             t_last.fill_(-1)
             L.rnad_rollout(_b200.ptr(packed.ev_tab), _b200.ptr(packed.tr_tab), a, packed.C, ctypes.byref(w), b, t_max,
                            self.states.seed, self.states.game_offset, _b200.ptr(uniforms), prec, ctypes.byref(traj),
                            _b200.ptr(t_last), _b200.ptr(workspace), _b200.stream())
-            self.t_eff = int(t_last.item())          # the rollout's only host synchronisation
         self.precision = precision
-        n = self.t_eff + 1
-        for key, value in out.items():
-            setattr(self, key, value[:n])
+        for key in Episodes._LAZY:
+            self.__dict__.pop(key, None)             # resolved on first access (see __getattr__)
+        self.__dict__["_pending"] = (out, t_last)
         self._q_estimates = None
         self._v_estimates = None
         self.states._idx_tensor, self.states._idx_fill = None, 0    # every game ended on the absorbing node
@@ -337,6 +366,7 @@ class Episodes:
     # -------------------------------------------------------------- containers
 
     def __repr__(self):
+        self._resolve()
         lines = []
         for key, value in self.__dict__.items():
             if torch.is_tensor(value) and torch.numel(value) > 20:
@@ -345,6 +375,7 @@ class Episodes:
         return "".join(lines)
 
     def _tensor_items(self):
+        self._resolve()
         return [(k, v) for k, v in self.__dict__.items() if torch.is_tensor(v)]
 
     def sample(self, batch_size):
@@ -363,6 +394,8 @@ class Episodes:
     @classmethod
     def collate(cls, lst: list):
         """Zero-pads every member along time to the longest and concatenates along batch (episode.py:258-290)."""
+        for e in lst:
+            e._resolve()
         t_eff = max(e.t_eff for e in lst)
         tree = lst[0].tree
         batch_size = sum(e.batch_size for e in lst)

@@ -306,8 +306,9 @@ class RNaD:
         if engine == "fused":
             if self._fused is None or self._fused.device != next(self.net.parameters()).device:
                 self._fused = fused.FusedLearner(self.net)
-            f = self._fused.forward(episodes.observations[: episodes.t_eff + 1], self.net, self.net_target,
-                                    self.net_reg, self.net_reg_)
+            # full-length tensors: no wait for t_eff; slots past the end of a game are invalid (index 0) and masked
+            observations = episodes.full("observations") if hasattr(episodes, "full") else episodes.observations
+            f = self._fused.forward(observations, self.net, self.net_target, self.net_reg, self.net_reg_)
             logit, log_pi, pi, v = f["logit"], f["log_pi"], f["pi"], f["v"]
             v_target, log_pi_reg, log_pi_reg_ = f["v_target"], f["log_pi_reg"], f["log_pi_reg_"]
         else:
@@ -330,7 +331,7 @@ class RNaD:
             global_counts=global_counts)
         self.last_losses = out.losses
         if engine == "fused":
-            flat = self._fused.backward(episodes.observations[: episodes.t_eff + 1], self.net, out.d_logit, out.d_v)
+            flat = self._fused.backward(observations, self.net, out.d_logit, out.d_v)
             dp.all_reduce_flat(flat)                      # the params' .grad are views of this buffer
         else:
             torch.autograd.backward([logit, v], [out.d_logit, out.d_v.unsqueeze(-1)])

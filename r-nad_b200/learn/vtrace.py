@@ -164,8 +164,10 @@ def get_loss_nerd(
 
 def count_played(episodes) -> torch.Tensor:
     """Device int32[2]: how many valid steps each player took in the batch (the losses' normalisers N_0, N_1)."""
-    indices = episodes.indices.detach().to(torch.int64).contiguous()
-    turns = episodes.turns.detach().to(torch.int64).contiguous()
+    # full-length tensors where a fused rollout left them (no wait for t_eff): slots past a game's end are invalid
+    get = episodes.full if hasattr(episodes, "full") else (lambda key: getattr(episodes, key))
+    indices = get("indices").detach().to(torch.int64).contiguous()
+    turns = get("turns").detach().to(torch.int64).contiguous()
     t, b = indices.shape
     with _b200.device_guard(indices):
         counts = torch.empty(2, dtype=torch.int32, device=indices.device)
@@ -197,8 +199,14 @@ def learner_targets(episodes, logit, pi, log_pi, v, v_target_net, log_pi_reg, lo
     replaces the local normalisers N_p (exact data-parallel losses on ragged trees).
     """
     L = _b200.lib()
-    t, b, a = episodes.policy.shape
-    dev = episodes.policy.device
+    def field(key):
+        # the trajectory tensor with as many half-moves as the learner's outputs: the full-length one a fused rollout
+        # wrote (available without waiting for t_eff) if `logit` was computed on it, else the stored (t_eff + 1) one
+        tensor = episodes.full(key) if hasattr(episodes, "full") else getattr(episodes, key)
+        return tensor if tensor.shape[0] == logit.shape[0] else getattr(episodes, key)
+
+    t, b, a = field("policy").shape
+    dev = logit.device
     res = LearnerTargets()
     with torch.cuda.device(dev):
         io = _b200.LearnerIO()
@@ -212,12 +220,12 @@ def learner_targets(episodes, logit, pi, log_pi, v, v_target_net, log_pi_reg, lo
             keep.append(tensor)
             setattr(io, name, _b200.ptr(tensor).value)
 
-        put("indices", episodes.indices, torch.int64)
-        put("turns", episodes.turns, torch.int64)
-        put("mu", episodes.policy)
-        put("actions_oh", episodes.actions)
-        put("rewards", episodes.rewards)
-        put("masks", episodes.masks)
+        put("indices", field("indices"), torch.int64)
+        put("turns", field("turns"), torch.int64)
+        put("mu", field("policy"))
+        put("actions_oh", field("actions"))
+        put("rewards", field("rewards"))
+        put("masks", field("masks"))
         put("logit", logit)
         put("pi", pi)
         put("log_pi", log_pi)
