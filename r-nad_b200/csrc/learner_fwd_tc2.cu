@@ -1,0 +1,412 @@
+// rnad_learner_forward, pipelined build: the four forward_batch calls of rnad.py:373-380 (five trunk evaluations per
+// trajectory row) with BOTH layers on tcgen05, as a persistent warp-specialised kernel - the structure of the
+// rollout engine (rollout_tc2.cu) without the game logic.
+//
+// A tile is 128 trajectory rows (row = TMEM lane).  Its ten *chunks* - 128 hidden units of, in turn, the learner's
+// value and policy trunks, the target net's value trunk and the two regularisation nets' policy trunks - stream
+// through a ring of three 128-column TMEM slots:
+//     MMA1  D[128 x 128]   = obs[128 x KP] (TMEM) x W1_chunk^T (smem)                     kind::tf32
+//     MMA2  D2[128 x 16]  += relu(D)[128 x 128] (TMEM) x W2_chunk^T (smem)
+// with two 16-column accumulators per tile: D2a = (v, logit[0..A)) of the learner, D2b = (v_target, logit_reg[0..A),
+// logit_reg_[0..A)).  Observations and accumulators are double-buffered across tiles.
+//   warps 12..15  issue the MMAs (stream item i by warp i % 4; MMA2s only ever ADD into accumulators the output
+//                 warps cleared, so their order across warps is free)
+//   warps 4..11   relu epilogue in tensor memory (bias via the constant-1 input column, else one FADD)
+//   warps 0..3    one thread per row: observation -> tensor memory (tf32); one tile later the heads: masked softmax /
+//                 log-softmax (net.py:76-80) of the three logit sets, the two values, written time-major.
+// Reference: nn/net.py:64-85.  Serves 2 <= A <= 3 (A = 4 keeps learner_fwd_kernel: its weights do not fit here).
+#include "tc_common.cuh"
+#include "tc_pipe.cuh"
+
+namespace rnad {
+namespace fwd2 {
+
+using namespace rnad::tc;
+using namespace rnad::tcp;
+
+constexpr int kRowWarps = 4, kEpiWarps = 8, kMmaWarps = 4;
+constexpr int kMmaWarp = kRowWarps + kEpiWarps;
+constexpr int kThreads = (kMmaWarp + kMmaWarps) * 32;
+constexpr int kChunk = 128, kSlots = 3, kTrunks = 5;
+constexpr int kItemsPerTile = kTrunks * (kHidden / kChunk);          // 10
+constexpr int kObsCol = kSlots * kChunk;                              // 2 x 32 columns of observations
+constexpr int kD2Col = kObsCol + 64;                                  // 2 x (16 + 16) columns of accumulators
+
+template <int A>
+struct Plan {
+    static constexpr int KIN = 2 * A * A;
+    static constexpr bool kBiasInK = (KIN % 8) != 0;
+    static constexpr int KP = round_up(KIN + (kBiasInK ? 1 : 0), 8);
+    static constexpr int kSbo1 = (KP / 4) * 128;
+    static constexpr int kTrunkBytes = kHidden * KP * 4;
+    static constexpr int kW2ChunkBytes = 8 * kChunk * 4;              // rows 0..7 of a [16 x 128] operand (rows 8..15 alias)
+    static constexpr int kW1 = 0;                                     // 5 trunks [256 x KP] tf32
+    static constexpr int kW2 = kW1 + kTrunks * kTrunkBytes;           // 10 chunks
+    static constexpr int kB1 = kW2 + kItemsPerTile * kW2ChunkBytes;   // first-layer biases, 5 x 256 f32
+    static constexpr int kB2 = kB1 + kTrunks * kHidden * 4;           // second-layer biases: 5 x 4 f32
+    static constexpr int kImageBytes = kB2 + kTrunks * 16;
+    static constexpr int kBar = round_up(kImageBytes, 8);
+    static constexpr int kNumBars = 1 + 2 + 2 + 2 + 4 * kSlots;       // image, obs[2], d2 done[2], d2 free[2], d1[6], relu[6]
+    static constexpr int kTmem = kBar + 8 * kNumBars;
+    static constexpr int kBytes = kTmem + 16;
+    static_assert(1 + 2 * A <= 8, "target value + two logit sets must fit 8 accumulator columns");
+    static_assert(kBytes <= 227 * 1024, "shared memory plan does not fit");
+    static_assert(KP <= 32, "observation columns do not fit");
+};
+
+struct Nets {
+    rnad_mlp_weights net, target, reg, reg_;
+};
+struct Out {
+    float *logit, *pi, *log_pi, *v, *v_target, *log_pi_reg, *log_pi_reg_;
+};
+
+template <int A>
+__global__ void pack_image_kernel(Nets w, uint8_t* __restrict__ image) {
+    using P = Plan<A>;
+    const int thread = blockIdx.x * blockDim.x + threadIdx.x, n_threads = gridDim.x * blockDim.x;
+    const float* w1[kTrunks] = {w.net.value_fc0_w, w.net.policy_fc0_w, w.target.value_fc0_w, w.reg.policy_fc0_w,
+                                w.reg_.policy_fc0_w};
+    const float* b1[kTrunks] = {w.net.value_fc0_b, w.net.policy_fc0_b, w.target.value_fc0_b, w.reg.policy_fc0_b,
+                                w.reg_.policy_fc0_b};
+    const float* w2[kTrunks] = {w.net.value_fc1_w, w.net.policy_fc1_w, w.target.value_fc1_w, w.reg.policy_fc1_w,
+                                w.reg_.policy_fc1_w};
+    const float* b2[kTrunks] = {w.net.value_fc1_b, w.net.policy_fc1_b, w.target.value_fc1_b, w.reg.policy_fc1_b,
+                                w.reg_.policy_fc1_b};
+    // accumulator row of output o of trunk t: D2a = (v, logit), D2b = (v_target, logit_reg, logit_reg_)
+    const int row0[kTrunks] = {0, 1, 0, 1, 1 + A};
+    const int n_out[kTrunks] = {1, A, 1, A, A};
+#pragma unroll
+    for (int t = 0; t < kTrunks; ++t) {
+        pack_trunk_operand<P::KIN, P::KP, P::kBiasInK>(w1[t], b1[t], image + P::kW1 + t * P::kTrunkBytes, thread, n_threads);
+        for (int j = thread; j < kHidden; j += n_threads) reinterpret_cast<float*>(image + P::kB1)[t * kHidden + j] = b1[t][j];
+        // second layer: per 128-unit half an [8 x 128] K-major operand, rows = accumulator columns
+        for (int e = thread; e < 2 * 8 * kChunk; e += n_threads) {
+            const int half = e / (8 * kChunk), r = (e / kChunk) % 8, k = e % kChunk;
+            const int o = r - row0[t];
+            const float v = (o >= 0 && o < n_out[t]) ? w2[t][o * kHidden + half * kChunk + k] : 0.f;
+            *reinterpret_cast<float*>(image + P::kW2 + (t * 2 + half) * P::kW2ChunkBytes + operand_offset<kChunk>(r, k)) = to_tf32(v);
+        }
+        if (thread < 4) reinterpret_cast<float*>(image + P::kB2)[t * 4 + thread] = thread < n_out[t] ? b2[t][thread] : 0.f;
+    }
+}
+
+// net.py:76-80: masked softmax / log-softmax of one row
+template <int A>
+__device__ __forceinline__ void heads(const float (&logit)[A], uint32_t mask_bits, float (&pi)[A], float (&log_pi)[A]) {
+    float e[A];
+    float sum = 0.f;
+#pragma unroll
+    for (int a = 0; a < A; ++a) {
+        e[a] = (mask_bits >> a) & 1u ? expf(logit[a]) : 0.f;
+        sum += e[a];
+    }
+    const float denom = fmaxf(sum, 1e-12f);
+    const float log_sum = logf(sum);
+#pragma unroll
+    for (int a = 0; a < A; ++a) {
+        pi[a] = e[a] / denom;
+        log_pi[a] = (mask_bits >> a) & 1u ? logit[a] - log_sum : 0.f;
+    }
+}
+
+template <int A>
+__global__ void __launch_bounds__(kThreads, 1) learner_fwd_tc2_kernel(const float* __restrict__ obs, int64_t N,
+                                                                       const uint8_t* __restrict__ image, Out out) {
+    using P = Plan<A>;
+    constexpr int KIN = P::KIN, KP = P::KP;
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t bar0 = smem_u32(smem + P::kBar);
+    const uint32_t bar_img = bar0;
+    auto bar_obs = [&](int b) { return bar0 + 8 + 8 * b; };                  // observations of a tile in tensor memory
+    auto bar_d2 = [&](int b) { return bar0 + 24 + 8 * b; };                  // all ten MMA2 groups of a tile complete
+    auto bar_free = [&](int b) { return bar0 + 40 + 8 * b; };                // accumulators read and cleared
+    auto bar_d1 = [&](int k) { return bar0 + 56 + 8 * k; };                  // per stream item i: barrier i % 6
+    auto bar_relu = [&](int k) { return bar0 + 56 + 8 * (2 * kSlots + k); };
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + P::kTmem);
+
+    if (warp == kMmaWarp) tmem_alloc<512>(tmem_slot);
+    if (tid == 0) {
+        mbar_init(bar_img, 1);
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(bar_obs(b), kRowWarps);
+            mbar_init(bar_d2(b), kItemsPerTile);
+            mbar_init(bar_free(b), kRowWarps);
+        }
+        for (int k = 0; k < 2 * kSlots; ++k) {
+            mbar_init(bar_d1(k), 1);
+            mbar_init(bar_relu(k), kEpiWarps);
+        }
+        mbar_fence_init();
+        tma_bulk_load(smem, image, P::kImageBytes, bar_img);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const int64_t num_tiles = (N + kTileM - 1) / kTileM;
+    int64_t my_tiles = 0;
+    if ((int64_t)blockIdx.x < num_tiles) my_tiles = (num_tiles - 1 - blockIdx.x) / gridDim.x + 1;
+    const uint32_t n_items = (uint32_t)(my_tiles * kItemsPerTile);
+
+    if (warp >= kMmaWarp) {
+        // ------------------------------------------------------------ MMA issuers
+        const int w = warp - kMmaWarp;
+        mbar_wait_c(bar_img, 0);
+        const uint64_t w1_desc = desc_sbo(smem_u32(smem + P::kW1), P::kSbo1);
+        const uint64_t w2_desc = desc_sbo(smem_u32(smem + P::kW2), (kChunk / 4) * 128);
+        constexpr uint32_t kIdesc1 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kChunk >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
+        constexpr uint32_t kIdesc2 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(16 >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
+        int seen_obs = -1, seen_free = -1;       // tiles whose observations / cleared accumulators this warp has seen
+        // first layers of chunk c of local tile k into `slot`; barrier index of the item
+        auto mma1 = [&](int k, int c, int slot, int bar_index) {
+#pragma unroll
+            for (int s = 0; s < KP / 8; ++s)
+                mma_ts(tmem_base + slot * kChunk, tmem_base + kObsCol + (k & 1) * 32 + s * 8,
+                       w1_desc + (uint64_t)(((c >> 1) * P::kTrunkBytes + (c & 1) * (kChunk / 8) * P::kSbo1 + s * 256) >> 4),
+                       kIdesc1, s > 0);
+            mma_commit(bar_d1(bar_index));
+        };
+        auto need_obs = [&](int k) {             // (each MMA warp checks for itself: the warps do not order each other)
+            if (k != seen_obs) {
+                mbar_wait_c(bar_obs(k & 1), (uint32_t)(k >> 1) & 1u);
+                tc_fence_after();
+                seen_obs = k;
+            }
+        };
+        if (w == 0 && n_items > 0) {             // fill the ring: chunks 0..2 of the first tile
+            need_obs(0);
+            if (elect_one())
+                for (int j = 0; j < kSlots; ++j) mma1(0, j, j, j);
+            __syncwarp();
+        }
+        // item i = w, w + 4, ...; (tile k, chunk c) of item i and of item j = i + 3, all incremental
+        int slot = w % kSlots, rb = w % (2 * kSlots);
+        uint32_t par = 0;
+        int k_i = 0, c_i = w, k_j = 0, c_j = w + kSlots;
+#pragma unroll 1
+        for (uint32_t i = w; i < n_items; i += kMmaWarps) {
+            const bool has_j = i + kSlots < n_items;
+            if (has_j) need_obs(k_j);
+            if (k_i != seen_free) {              // the accumulators of this tile's buffer were read and cleared (tile k_i - 2)
+                mbar_wait_c(bar_free(k_i & 1), ((uint32_t)(k_i >> 1) & 1u) ^ 1u);
+                tc_fence_after();
+                seen_free = k_i;
+            }
+            mbar_wait_c(bar_relu(rb), par);
+            tc_fence_after();
+            if (elect_one()) {
+                const uint32_t d2 = tmem_base + kD2Col + (k_i & 1) * 32 + (c_i >= 4 ? 16 : 0);   // D2a: trunks 0, 1; D2b: 2..4
+#pragma unroll
+                for (int s = 0; s < kChunk / 8; ++s)
+                    mma_ts(d2, tmem_base + slot * kChunk + s * 8,
+                           w2_desc + (uint64_t)((c_i * P::kW2ChunkBytes + s * 256) >> 4), kIdesc2, true);
+                mma_commit(bar_d2(k_i & 1));
+                if (has_j) mma1(k_j, c_j, slot, rb >= kSlots ? rb - kSlots : rb + kSlots);
+            }
+            __syncwarp();
+            slot = slot + 1 == kSlots ? 0 : slot + 1;
+            rb += kMmaWarps;
+            if (rb >= 2 * kSlots) {
+                rb -= 2 * kSlots;
+                par ^= 1u;
+            }
+            c_i += kMmaWarps;
+            if (c_i >= kItemsPerTile) {
+                c_i -= kItemsPerTile;
+                ++k_i;
+            }
+            c_j += kMmaWarps;
+            if (c_j >= kItemsPerTile) {
+                c_j -= kItemsPerTile;
+                ++k_j;
+            }
+        }
+    } else if (warp >= kRowWarps) {
+        // ------------------------------------------------------------ relu epilogue
+        const int e = warp - kRowWarps;
+        const int quad = e & 3, half = e >> 2;
+        constexpr int kCols = kChunk / 2;
+        const uint32_t tmem_mine = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(half * kCols);
+        const float* b1 = reinterpret_cast<const float*>(smem + P::kB1) + half * kCols;
+        if (!P::kBiasInK) mbar_wait_c(bar_img, 0);
+        int slot = 0, rb = 0, c = 0;
+        uint32_t par = 0;
+#pragma unroll 1
+        for (uint32_t i = 0; i < n_items; ++i) {
+            mbar_wait_c(bar_d1(rb), par);
+            tc_fence_after();
+            const uint32_t taddr = tmem_mine + slot * kChunk;
+            uint32_t r[kCols];
+#pragma unroll
+            for (int q = 0; q < kCols / 32; ++q) tmem_ld32p(taddr + q * 32, r + q * 32);
+            tmem_ld_wait();
+            if (!P::kBiasInK) {
+                const float4* bias = reinterpret_cast<const float4*>(b1 + c * kChunk);   // chunk c = trunk c/2, half c%2
+#pragma unroll
+                for (int k = 0; k < kCols / 4; ++k) {
+                    const float4 bb = bias[k];
+                    r[4 * k + 0] = __float_as_uint(__uint_as_float(r[4 * k + 0]) + bb.x);
+                    r[4 * k + 1] = __float_as_uint(__uint_as_float(r[4 * k + 1]) + bb.y);
+                    r[4 * k + 2] = __float_as_uint(__uint_as_float(r[4 * k + 2]) + bb.z);
+                    r[4 * k + 3] = __float_as_uint(__uint_as_float(r[4 * k + 3]) + bb.w);
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < kCols; ++k) r[k] = __float_as_uint(fmaxf(__uint_as_float(r[k]), 0.f));
+#pragma unroll
+            for (int q = 0; q < kCols / 32; ++q) tmem_st32(taddr + q * 32, r + q * 32);
+            tmem_st_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_relu(rb));
+            slot = slot + 1 == kSlots ? 0 : slot + 1;
+            if (++rb == 2 * kSlots) {
+                rb = 0;
+                par ^= 1u;
+            }
+            if (++c == kItemsPerTile) c = 0;
+        }
+    } else {
+        // ------------------------------------------------------------ rows: observations in, heads out
+        const uint32_t tmem_lane = tmem_base + ((uint32_t)(warp * 32) << 16);
+        mbar_wait_c(bar_img, 0);
+        const float* b2 = reinterpret_cast<const float*>(smem + P::kB2);
+        {   // both accumulator buffers start from zero
+            const uint32_t zero[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+#pragma unroll
+            for (int q = 0; q < 8; ++q) tmem_st8(tmem_lane + kD2Col + q * 8, zero);
+            tmem_st_wait();
+        }
+        uint32_t mask_prev = 0;
+        int64_t row_prev = -1;
+#pragma unroll 1
+        for (int64_t k = 0; k <= my_tiles; ++k) {
+            uint32_t mask_now = 0;
+            int64_t row_now = -1;
+            if (k < my_tiles) {
+                // ---- this tile's observation row -> tensor memory (its buffer is free: the heads of tile k - 2 are out)
+                const int64_t tile = (int64_t)blockIdx.x + k * gridDim.x;
+                const int64_t row = tile * kTileM + tid;
+                const bool active = row < N;
+                float x[KIN];
+                const float2* src = reinterpret_cast<const float2*>(obs + row * KIN);
+#pragma unroll
+                for (int q = 0; q < KIN / 2; ++q) {
+                    const float2 v = active ? __ldg(src + q) : make_float2(0.f, 0.f);
+                    x[2 * q] = v.x;
+                    x[2 * q + 1] = v.y;
+                }
+#pragma unroll
+                for (int a = 0; a < A; ++a) mask_now |= (x[A * A + a * A] != 0.f ? 1u : 0u) << a;   // obs[:, 1, :, 0]
+                row_now = active ? row : -1;
+#pragma unroll
+                for (int q = 0; q < KP / 8; ++q) {
+                    uint32_t v[8];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        const int kk = 8 * q + u;
+                        v[u] = __float_as_uint(kk < KIN ? to_tf32(x[kk < KIN ? kk : 0]) : ((P::kBiasInK && kk == KIN) ? 1.f : 0.f));
+                    }
+                    tmem_st8(tmem_lane + kObsCol + (k & 1) * 32 + 8 * q, v);
+                }
+                tmem_st_wait();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_obs(k & 1));
+            }
+            if (k > 0) {
+                // ---- heads of the previous tile
+                const int kp = (int)(k - 1);
+                mbar_wait_c(bar_d2(kp & 1), (uint32_t)(kp >> 1) & 1u);
+                tc_fence_after();
+                uint32_t da[8], db[8];
+                tmem_ld8(tmem_lane + kD2Col + (kp & 1) * 32, da);
+                tmem_ld8(tmem_lane + kD2Col + (kp & 1) * 32 + 16, db);
+                tmem_ld_wait();
+                {
+                    const uint32_t zero[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+                    tmem_st8(tmem_lane + kD2Col + (kp & 1) * 32, zero);
+                    tmem_st8(tmem_lane + kD2Col + (kp & 1) * 32 + 16, zero);
+                    tmem_st_wait();
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_free(kp & 1));
+                if (row_prev >= 0) {
+                    const int64_t row = row_prev;
+                    out.v[row] = __uint_as_float(da[0]) + b2[0];
+                    out.v_target[row] = __uint_as_float(db[0]) + b2[2 * 4];
+                    float lg[A], pi[A], lp[A];
+#pragma unroll
+                    for (int a = 0; a < A; ++a) lg[a] = __uint_as_float(da[1 + a]) + b2[1 * 4 + a];
+                    heads<A>(lg, mask_prev, pi, lp);
+#pragma unroll
+                    for (int a = 0; a < A; ++a) {
+                        out.logit[row * A + a] = lg[a];
+                        out.pi[row * A + a] = pi[a];
+                        out.log_pi[row * A + a] = lp[a];
+                    }
+#pragma unroll
+                    for (int a = 0; a < A; ++a) lg[a] = __uint_as_float(db[1 + a]) + b2[3 * 4 + a];
+                    heads<A>(lg, mask_prev, pi, lp);
+#pragma unroll
+                    for (int a = 0; a < A; ++a) out.log_pi_reg[row * A + a] = lp[a];
+#pragma unroll
+                    for (int a = 0; a < A; ++a) lg[a] = __uint_as_float(db[1 + A + a]) + b2[4 * 4 + a];
+                    heads<A>(lg, mask_prev, pi, lp);
+#pragma unroll
+                    for (int a = 0; a < A; ++a) out.log_pi_reg_[row * A + a] = lp[a];
+                }
+            }
+            mask_prev = mask_now;
+            row_prev = row_now;
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == kMmaWarp) tmem_dealloc<512>(tmem_base);
+}
+
+template <int A>
+int launch(const float* obs, int64_t N, const Nets& nets, const Out& out, uint8_t* workspace, cudaStream_t st) {
+    using P = Plan<A>;
+    pack_image_kernel<A><<<64, 256, 0, st>>>(nets, workspace);
+    RNAD_CHECK_LAUNCH("learner fwd2 pack_image_kernel");
+    const size_t smem = P::kBytes > 116 * 1024 ? P::kBytes : 116 * 1024;   // one CTA per SM (all 512 TMEM columns)
+    int rc = check_cuda(cudaFuncSetAttribute(learner_fwd_tc2_kernel<A>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
+                        "cudaFuncSetAttribute(learner_fwd_tc2)");
+    if (rc) return rc;
+    int64_t blocks = (N + kTileM - 1) / kTileM;
+    if (blocks > sm_count()) blocks = sm_count();
+    learner_fwd_tc2_kernel<A><<<(int)blocks, kThreads, smem, st>>>(obs, N, workspace, out);
+    RNAD_CHECK_LAUNCH("learner_fwd_tc2_kernel");
+    return RNAD_OK;
+}
+
+}  // namespace fwd2
+
+bool learner_forward_tc2_supported(int A, int width) { return width == tc::kHidden && (A == 2 || A == 3); }
+
+int64_t learner_forward_tc2_image_bytes(int A) {
+    switch (A) {
+        case 2: return fwd2::Plan<2>::kImageBytes;
+        case 3: return fwd2::Plan<3>::kImageBytes;
+    }
+    return 0;
+}
+
+int learner_forward_tc2(const float* obs, int64_t N, int A, const rnad_mlp_weights* net, const rnad_mlp_weights* target,
+                        const rnad_mlp_weights* reg, const rnad_mlp_weights* reg_, const rnad_learner_fwd_out* out,
+                        void* workspace, cudaStream_t st) {
+    fwd2::Nets nets{*net, *target, *reg, *reg_};
+    fwd2::Out o{out->logit, out->pi, out->log_pi, out->v, out->v_target, out->log_pi_reg, out->log_pi_reg_};
+    switch (A) {
+        case 2: return fwd2::launch<2>(obs, N, nets, o, (uint8_t*)workspace, st);
+        case 3: return fwd2::launch<3>(obs, N, nets, o, (uint8_t*)workspace, st);
+    }
+    return RNAD_EUNSUPPORTED;
+}
+
+}  // namespace rnad

@@ -23,6 +23,14 @@
 #include "tc_common.cuh"
 
 namespace rnad {
+
+// pipelined forward with both layers on the tensor core (learner_fwd_tc2.cu)
+bool learner_forward_tc2_supported(int A, int width);
+int64_t learner_forward_tc2_image_bytes(int A);
+int learner_forward_tc2(const float* obs, int64_t N, int A, const rnad_mlp_weights* net, const rnad_mlp_weights* target,
+                        const rnad_mlp_weights* reg, const rnad_mlp_weights* reg_, const rnad_learner_fwd_out* out,
+                        void* workspace, cudaStream_t st);
+
 namespace tc {
 
 constexpr int kLearnThreads = 256;   // two threads per trajectory row
@@ -857,10 +865,16 @@ __global__ void reduce_partials_kernel(const float* __restrict__ partials, int n
 
 constexpr int kMaxBwdCtas = 160;
 
+// the forward kernels' weight image sits at the start of the workspace: room for the larger of the two builds
+template <int A>
+int64_t fwd_image_reserve() {
+    const int64_t v1 = FwdPlan<A>::kImageBytes, v2 = learner_forward_tc2_image_bytes(A);
+    return round_up((int)(v1 > v2 ? v1 : v2), 256);
+}
+
 template <int A>
 int64_t workspace_bytes() {
-    return round_up(FwdPlan<A>::kImageBytes, 256) + round_up(BwdPlan<A>::kImageBytes, 256) +
-           (int64_t)kMaxBwdCtas * Shape<A>::kParams * 4;
+    return fwd_image_reserve<A>() + round_up(BwdPlan<A>::kImageBytes, 256) + (int64_t)kMaxBwdCtas * Shape<A>::kParams * 4;
 }
 
 template <int A, typename Kernel>
@@ -893,7 +907,7 @@ int launch_backward(const float* obs, int64_t N, const rnad_mlp_weights& w, cons
     using P = BwdPlan<A>;
     using PT = BwdTcPlan<A>;
     static_assert(PT::kImageBytes == P::kImageBytes && PT::kB1 == P::kB1, "both backward kernels read the same weight image");
-    uint8_t* image = workspace + round_up(FwdPlan<A>::kImageBytes, 256);
+    uint8_t* image = workspace + fwd_image_reserve<A>();
     float* partials = reinterpret_cast<float*>(image + round_up(P::kImageBytes, 256));
     pack_bwd_image_kernel<A><<<24, 256, 0, st>>>(w, image);
     RNAD_CHECK_LAUNCH("pack_bwd_image_kernel");
@@ -964,6 +978,9 @@ int rnad_learner_forward(const float* observations, int64_t N, int A, const rnad
     }
     RNAD_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "rnad_learner_forward: workspace must be 256-byte aligned");
     if (N == 0) return RNAD_OK;
+    static const bool v1 = getenv("RNAD_LEARNER_FWD_V1") != nullptr;   // the previous kernel, for A/B runs
+    if (!v1 && learner_forward_tc2_supported(A, net->width))
+        return learner_forward_tc2(observations, N, A, net, target, reg, reg_, out, workspace, (cudaStream_t)stream);
     tc::FwdNets nets{*net, *target, *reg, *reg_};
     tc::FwdOut o{out->logit, out->pi, out->log_pi, out->v, out->v_target, out->log_pi_reg, out->log_pi_reg_};
     cudaStream_t st = (cudaStream_t)stream;

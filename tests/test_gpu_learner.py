@@ -301,15 +301,27 @@ def test_fused_learner_forward_vs_oracle(a, T, B):
     assert bool((cpu(out["pi"])[mask == 0] == 0).all()) and bool((cpu(out["log_pi"])[mask == 0] == 0).all())
     close(cpu(out["pi"]).sum(-1), torch.ones(T, B), rtol=0, atol=1e-6)
     err = (cpu(out["logit"]) - ref_net[0]).abs().max().item()
-    # tight check against the engine's numerics restated on the CPU (tf32-rounded first-layer operands, fp64
-    # accumulation): what is left is the fp32 accumulation order of the MMA and of the second layer
+    # tight check against the engine's numerics restated on the CPU (oracle.mlp_forward_tc): tf32-rounded first-layer
+    # operands; for A <= 3 (pipelined kernel, both layers on the tensor core) also tf32 second layers with the
+    # activations truncated; fp64 accumulation.  What is left is fp32 accumulation order - and, rarely, an activation
+    # on the other side of a tf32 truncation boundary (see tests/test_gpu_env_rollout.py::TOL_TC).
     flat = obs.reshape(T * B, -1)
+    second = "tf32" if a <= 3 else "fp32"
+    tol_max, tol_mean = (5e-4, 5e-6) if second == "tf32" else (2e-5, 2e-6)
     for key_l, key_v, wts in (("logit", "v", weights[0]), (None, "v_target", weights[1])):
-        e_logit, _, e_v, _, _, _ = orc.mlp_forward_tc(wts, flat)
+        e_logit, _, e_v, _, _, _ = orc.mlp_forward_tc(wts, flat, second)
         if key_l:
-            close(cpu(out[key_l]).double().reshape(T * B, a), e_logit, rtol=0, atol=2e-5)
-        close(cpu(out[key_v]).double().reshape(T * B, 1), e_v, rtol=0, atol=2e-5)
-    err_tc = (cpu(out["logit"]).double().reshape(T * B, a) - orc.mlp_forward_tc(weights[0], flat)[0]).abs().max().item()
+            err_l = (cpu(out[key_l]).double().reshape(T * B, a) - e_logit).abs()
+            assert float(err_l.max()) < tol_max and float(err_l.mean()) < tol_mean, (float(err_l.max()), float(err_l.mean()))
+        err_v = (cpu(out[key_v]).double().reshape(T * B, 1) - e_v).abs()
+        assert float(err_v.max()) < tol_max and float(err_v.mean()) < tol_mean, (float(err_v.max()), float(err_v.mean()))
+    for key, wts in (("log_pi_reg", weights[2]), ("log_pi_reg_", weights[3])):
+        e_logit, _, _, e_exp, _, _ = orc.mlp_forward_tc(wts, flat, second)
+        m = flat[:, a * a: 2 * a * a: a] != 0
+        e_logp = torch.where(m, e_logit - torch.log(e_exp.sum(-1, keepdim=True)), torch.zeros_like(e_logit))
+        err_p = (cpu(out[key]).double().reshape(T * B, a) - e_logp).abs()
+        assert float(err_p.max()) < 2 * tol_max and float(err_p.mean()) < 2 * tol_mean, (key, float(err_p.max()), float(err_p.mean()))
+    err_tc = (cpu(out["logit"]).double().reshape(T * B, a) - orc.mlp_forward_tc(weights[0], flat, second)[0]).abs().max().item()
     print(f"fused forward A={a}: max |logit error| = {err:.2e} vs fp32 net, {err_tc:.2e} vs tf32-aware oracle")
 
 
