@@ -24,7 +24,10 @@ namespace fwd2 {
 using namespace rnad::tc;
 using namespace rnad::tcp;
 
-constexpr int kRowWarps = 4, kEpiWarps = 8, kMmaWarps = 4;
+#ifndef RNAD_FWD2_EPI_WARPS
+#define RNAD_FWD2_EPI_WARPS 8
+#endif
+constexpr int kRowWarps = 4, kEpiWarps = RNAD_FWD2_EPI_WARPS, kMmaWarps = 4;   // 8 or 16 epilogue warps (64 or 32 columns each)
 constexpr int kMmaWarp = kRowWarps + kEpiWarps;
 constexpr int kThreads = (kMmaWarp + kMmaWarps) * 32;
 constexpr int kChunk = 128, kSlots = 3, kTrunks = 5;
@@ -226,8 +229,8 @@ __global__ void __launch_bounds__(kThreads, 1) learner_fwd_tc2_kernel(const floa
     } else if (warp >= kRowWarps) {
         // ------------------------------------------------------------ relu epilogue
         const int e = warp - kRowWarps;
-        const int quad = e & 3, half = e >> 2;
-        constexpr int kCols = kChunk / 2;
+        const int quad = e & 3, half = e >> 2;                 // lane quadrant, column part
+        constexpr int kCols = kChunk / (kEpiWarps / 4);
         const uint32_t tmem_mine = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(half * kCols);
         const float* b1 = reinterpret_cast<const float*>(smem + P::kB1) + half * kCols;
         if (!P::kBiasInK) mbar_wait_c(bar_img, 0);

@@ -27,10 +27,10 @@ for role, name in enumerate(["head side 0", "head side 1"]):
         row = buf[role, t]
         print(f"  t={t}", " ".join(f"{(x - t0) if x else -1:6d}" for x in row[:5]))
 
-# stream items 16..55.  MMA warp (= chunk index c): loop top, observations of item+3 available, relu(item) seen,
-# MMA2(item) + MMA1(item+3) issued.  Epilogue warp 0: first layers of the item complete, relu written back.
+# stream items 16..55.  MMA warp (= chunk index c): relu(item) seen, MMA2(item) + MMA1(item+3) issued.
+# Epilogue warp 0: first layers of the item complete, relu written back.
 mma = buf[2].reshape(-1)[:320].reshape(-1, 8)
-print("item side c | MMA warp: top  obs ok  relu seen  issued | epilogue warp 0: d1 seen  relu done   (absolute cycles)")
+print("item side c | MMA warp: relu seen  issued | epilogue warp 0: d1 seen  relu done   (absolute cycles)")
 for j in range(40):
     i = j + 16
-    print(f"{i:4d} {(i//4)%2:4d} {i%4} | {mma[j,5]-t0:8d} {mma[j,6]-t0:8d} {mma[j,0]-t0:8d} {mma[j,2]-t0:8d} | {mma[j,3]-t0:8d} {mma[j,4]-t0:8d}")
+    print(f"{i:4d} {(i//4)%2:4d} {i%4} | {mma[j,0]-t0:8d} {mma[j,2]-t0:8d} | {mma[j,3]-t0:8d} {mma[j,4]-t0:8d}")
