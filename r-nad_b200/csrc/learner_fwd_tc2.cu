@@ -310,7 +310,7 @@ __global__ void __launch_bounds__(kThreads, 1) learner_fwd_tc2_kernel(const floa
 #pragma unroll
                     for (int u = 0; u < 8; ++u) {
                         const int kk = 8 * q + u;
-                        v[u] = __float_as_uint(kk < KIN ? to_tf32(x[kk < KIN ? kk : 0]) : ((P::kBiasInK && kk == KIN) ? 1.f : 0.f));
+                        v[u] = __float_as_uint(kk < KIN ? to_tf32_fast(x[kk < KIN ? kk : 0]) : ((P::kBiasInK && kk == KIN) ? 1.f : 0.f));
                     }
                     tmem_st8(tmem_lane + kObsCol + (k & 1) * 32 + 8 * q, v);
                 }

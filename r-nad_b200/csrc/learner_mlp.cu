@@ -146,7 +146,7 @@ __device__ __forceinline__ void store_operand_row(uint8_t* tile, int lane, const
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
             const int k = 4 * q + u;
-            v[u] = k < KIN ? to_tf32(x[k < KIN ? k : 0]) : ((kBiasInK && k == KIN) ? 1.f : 0.f);
+            v[u] = k < KIN ? to_tf32_fast(x[k < KIN ? k : 0]) : ((kBiasInK && k == KIN) ? 1.f : 0.f);
         }
         *reinterpret_cast<float4*>(tile + operand_offset<KP>(lane, 4 * q)) = make_float4(v[0], v[1], v[2], v[3]);
     }
@@ -712,7 +712,7 @@ __global__ void __launch_bounds__(kBwdTcThreads, 1) learner_bwd_tc_kernel(const 
             load_row<KIN>(obs, row, active, x);
             store_operand_row<KIN, KP, P::kBiasInK>(smem + P::kX, n, x);
 #pragma unroll
-            for (int k = 0; k < KIN; ++k) *reinterpret_cast<float*>(smem + P::kBX + off_t(k, n)) = to_tf32(x[k]);
+            for (int k = 0; k < KIN; ++k) *reinterpret_cast<float*>(smem + P::kBX + off_t(k, n)) = to_tf32_fast(x[k]);
             *reinterpret_cast<float*>(smem + P::kBX + off_t(KIN, n)) = 1.f;
             float g[1 + A];
             g[0] = active ? d_v[row] : 0.f;
@@ -720,7 +720,7 @@ __global__ void __launch_bounds__(kBwdTcThreads, 1) learner_bwd_tc_kernel(const 
             for (int a = 0; a < A; ++a) g[1 + a] = active ? d_logit[row * A + a] : 0.f;
 #pragma unroll
             for (int a = 0; a <= A; ++a) {
-                *reinterpret_cast<float*>(smem + P::kBG + off_t(a, n)) = to_tf32(g[a]);
+                *reinterpret_cast<float*>(smem + P::kBG + off_t(a, n)) = to_tf32_fast(g[a]);
                 s_g[n * 8 + a] = g[a];
                 gsum[a] += g[a];
             }
@@ -776,8 +776,8 @@ __global__ void __launch_bounds__(kBwdTcThreads, 1) learner_bwd_tc_kernel(const 
                     if (A > 3) s = fmaf(s_g[n * 8 + 4], w2[A > 3 ? 3 : 0], s);
                 }
                 const bool on = h > 0.f;
-                hr[i] = __float_as_uint(on ? to_tf32(h) : 0.f);
-                dh[i] = __float_as_uint(on ? to_tf32(s) : 0.f);
+                hr[i] = __float_as_uint(on ? to_tf32_fast(h) : 0.f);
+                dh[i] = __float_as_uint(on ? to_tf32_fast(s) : 0.f);
             }
             tmem_st32r(tmem_lane + cpart * 32, hr);
             tmem_st32r(tmem_lane + 128 + cpart * 32, dh);

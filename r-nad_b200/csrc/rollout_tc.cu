@@ -178,8 +178,8 @@ __global__ void __launch_bounds__(kThreads, 2) rollout_tc_kernel(RolloutArgs g, 
                 for (int k = KIN; k < KP; ++k) x[k] = (P::kBiasInK && k == KIN) ? 1.f : 0.f;
 #pragma unroll
                 for (int q = 0; q < KP / 4; ++q) {
-                    const float4 v = make_float4(to_tf32(x[4 * q]), to_tf32(x[4 * q + 1]), to_tf32(x[4 * q + 2]),
-                                                 to_tf32(x[4 * q + 3]));
+                    const float4 v = make_float4(to_tf32_fast(x[4 * q]), to_tf32_fast(x[4 * q + 1]), to_tf32_fast(x[4 * q + 2]),
+                                                 to_tf32_fast(x[4 * q + 3]));
                     *reinterpret_cast<float4*>(smem + P::kA + operand_offset<KP>(lane_g, 4 * q)) = v;
                 }
                 fence_async_smem();   // generic-proxy writes -> visible to the tensor core (async proxy)

@@ -492,7 +492,7 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tc2_kernel(RolloutArgs g,
 #pragma unroll
                     for (int u = 0; u < 8; ++u) {
                         const int kk = 8 * q + u;
-                        v[u] = __float_as_uint(kk < KIN ? to_tf32(x[kk < KIN ? kk : 0])
+                        v[u] = __float_as_uint(kk < KIN ? to_tf32_fast(x[kk < KIN ? kk : 0])
                                                         : ((P::kBiasInK && kk == KIN) ? 1.f : 0.f));
                     }
                     tmem_st8(my_obs + 8 * q, v);

@@ -17,6 +17,12 @@ __device__ __forceinline__ float to_tf32(float x) {
     return __uint_as_float(r);
 }
 
+// The same rounding (nearest, ties away from zero) for finite inputs with two integer instructions: ptxas expands
+// cvt.rna.tf32.f32 into a branchy sequence with Inf / NaN handling, which matters where it runs per matrix element.
+__device__ __forceinline__ float to_tf32_fast(float x) {
+    return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
+}
+
 // canonical K-major, no-swizzle operand layout: 8-row x 16-byte core matrices,
 // K chunks of a row group adjacent (LBO = 128 B), row groups SBO bytes apart
 template <int KP>

@@ -14,4 +14,8 @@ timeout 600 ncu --set full --clock-control none --import-source on -k regex:roll
     -o gpurun_out/prof_rollout_${TAG} -f python bench.py --steps 2 --warmup 3 --cpu-budget 0.5 > gpurun_out/ncu_full_${TAG}.log 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:learner_targets -s 1 -c 1 \
     -o gpurun_out/prof_learner_${TAG} -f python bench.py --steps 2 --warmup 3 --cpu-budget 0.5 >> gpurun_out/ncu_full_${TAG}.log 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:learner_fwd_tc2 -s 1 -c 1 \
+    -o gpurun_out/prof_fwd_${TAG} -f python bench.py --steps 2 --warmup 3 --cpu-budget 0.5 >> gpurun_out/ncu_full_${TAG}.log 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:learner_bwd_tc -s 1 -c 1 \
+    -o gpurun_out/prof_bwd_${TAG} -f python bench.py --steps 2 --warmup 3 --cpu-budget 0.5 >> gpurun_out/ncu_full_${TAG}.log 2>&1
 ls -la gpurun_out | tail -8
