@@ -567,11 +567,13 @@ struct BwdTcPlan : Shape<A> {
     static constexpr int kSboT = (kTileM / 4) * kLbo;                  // 8-row groups of BX / BG
     static constexpr int kB = 0;                                       // image: both trunks' first layers [256 x KP] tf32, K-major
     static constexpr int kB1 = kB + 2 * S::kTrunkBytes;                //        their biases, 2 x 256 f32
-    static constexpr int kImageBytes = kB1 + 2 * kHidden * 4;          // (same image as pack_bwd_image_kernel writes)
+    static constexpr int kW2T = kB1 + 2 * kHidden * 4;                 //        second layers transposed, [512 x 8] tf32 K-major:
+                                                                       //        row trunk*256 + j = (w2v[j],0..) or (0,w2p[0][j],..)
+    static constexpr int kImageBytes = kW2T + 2 * kHidden * 8 * 4;
     static constexpr int kX = kImageBytes;                             // observation tile [128 x KP] tf32, K-major
     static constexpr int kBX = kX + kTileM * S::KP * 4;
     static constexpr int kBG = kBX + (kNX / 8) * kSboT;
-    static constexpr int kG = kBG + (kNG / 8) * kSboT;                 // g[n][8] fp32: d_v, d_logit[0..A)
+    static constexpr int kG = kBG + (kNG / 8) * kSboT;                 // g tile [128 x 8] tf32, K-major: d_v, d_logit[0..A)
     static constexpr int kRed = kG + kTileM * 32;                      // [4 warps][8] partial sums of g (output-bias gradients)
     static constexpr int kBar = kRed + 4 * 32;
     static constexpr int kTmem = kBar + 32;
@@ -639,6 +641,26 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
 __device__ __forceinline__ void tmem_st_wait_all() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 template <int A>
+__global__ void pack_bwd_tc_image_kernel(rnad_mlp_weights w, uint8_t* __restrict__ image) {
+    using P = BwdTcPlan<A>;
+    const int thread = blockIdx.x * blockDim.x + threadIdx.x, n_threads = gridDim.x * blockDim.x;
+    pack_trunk_operand<P::KIN, P::KP, P::kBiasInK>(w.value_fc0_w, w.value_fc0_b, image + P::kB, thread, n_threads);
+    pack_trunk_operand<P::KIN, P::KP, P::kBiasInK>(w.policy_fc0_w, w.policy_fc0_b, image + P::kB + P::kTrunkBytes,
+                                                   thread, n_threads);
+    for (int j = thread; j < kHidden; j += n_threads) {
+        reinterpret_cast<float*>(image + P::kB1)[j] = w.value_fc0_b[j];
+        reinterpret_cast<float*>(image + P::kB1)[kHidden + j] = w.policy_fc0_b[j];
+    }
+    for (int e = thread; e < 2 * kHidden * 8; e += n_threads) {
+        const int row = e / 8, k = e % 8, trunk = row / kHidden, j = row % kHidden;
+        float v = 0.f;
+        if (trunk == 0 && k == 0) v = w.value_fc1_w[j];
+        if (trunk == 1 && k >= 1 && k <= A) v = w.policy_fc1_w[(k - 1) * kHidden + j];
+        *reinterpret_cast<float*>(image + P::kW2T + operand_offset<8>(row, k)) = to_tf32(v);
+    }
+}
+
+template <int A>
 __global__ void __launch_bounds__(kBwdTcThreads, 1) learner_bwd_tc_kernel(const float* __restrict__ obs, int64_t N,
                                                                            const uint8_t* __restrict__ image,
                                                                            rnad_mlp_weights w,
@@ -683,19 +705,15 @@ __global__ void __launch_bounds__(kBwdTcThreads, 1) learner_bwd_tc_kernel(const 
     tc_fence_after();
 
     const float* b1 = reinterpret_cast<const float*>(smem + P::kB1);
-    float* s_g = reinterpret_cast<float*>(smem + P::kG);
     auto off_t = [](int c, int n) { return (c >> 3) * P::kSboT + (n >> 2) * P::kLbo + (c & 7) * 16 + (n & 3) * 4; };
     float gsum[1 + A];
 #pragma unroll
     for (int a = 0; a <= A; ++a) gsum[a] = 0.f;
-    // this lane's hidden units (one per 128-unit half): second-layer weights and first-layer bias, loaded once
-    float w2v_j[2], w2p_j[2][A], bias_v[2], bias_p[2];
+    // this lane's hidden units (one per 128-unit half): first-layer bias where it does not ride in K
+    float bias_v[2], bias_p[2];
 #pragma unroll
     for (int half = 0; half < 2; ++half) {
         const int j = half * 128 + j_local;
-        w2v_j[half] = __ldg(w.value_fc1_w + j);
-#pragma unroll
-        for (int a = 0; a < A; ++a) w2p_j[half][a] = __ldg(w.policy_fc1_w + a * kHidden + j);
         bias_v[half] = P::kBiasInK ? 0.f : b1[j];
         bias_p[half] = P::kBiasInK ? 0.f : b1[kHidden + j];
     }
@@ -718,18 +736,24 @@ __global__ void __launch_bounds__(kBwdTcThreads, 1) learner_bwd_tc_kernel(const 
             g[0] = active ? d_v[row] : 0.f;
 #pragma unroll
             for (int a = 0; a < A; ++a) g[1 + a] = active ? d_logit[row * A + a] : 0.f;
+            float g8[8];
+#pragma unroll
+            for (int a = 0; a < 8; ++a) g8[a] = a <= A ? to_tf32_fast(g[a < 1 + A ? a : 0]) : 0.f;
 #pragma unroll
             for (int a = 0; a <= A; ++a) {
-                *reinterpret_cast<float*>(smem + P::kBG + off_t(a, n)) = to_tf32_fast(g[a]);
-                s_g[n * 8 + a] = g[a];
+                *reinterpret_cast<float*>(smem + P::kBG + off_t(a, n)) = g8[a];
                 gsum[a] += g[a];
             }
+            // the same values row-major, as the B operand of S^T = W2^T . G^T
+            *reinterpret_cast<float4*>(smem + P::kG + operand_offset<8>(n, 0)) = make_float4(g8[0], g8[1], g8[2], g8[3]);
+            *reinterpret_cast<float4*>(smem + P::kG + operand_offset<8>(n, 4)) = make_float4(g8[4], g8[5], g8[6], g8[7]);
             fence_async_smem();
         }
         tc_fence_before();
         __syncthreads();
 
-        // H^T = W1[trunk, half] . X^T   (M = hidden units, N = rows, K = inputs), into columns [0, 128)
+        // H^T = W1[trunk, half] . X^T   (M = hidden units, N = rows, K = inputs)      into columns [0, 128)
+        // S^T = W2^T[trunk, half] . G^T (K = the 1 + A outputs): (g W2)^T             into columns [128, 256)
         auto recompute = [&](int th) {
             const int trunk = th >> 1, half = th & 1;
             const uint32_t a_base = smem_u32(smem + P::kB) + trunk * P::kTrunkBytes + half * (128 / 8) * ((KP / 4) * 128);
@@ -737,6 +761,8 @@ __global__ void __launch_bounds__(kBwdTcThreads, 1) learner_bwd_tc_kernel(const 
 #pragma unroll
             for (int ks = 0; ks < KP / 8; ++ks)
                 mma_ss_n(tmem_base, make_desc<KP>(a_base + ks * 256), make_desc<KP>(b_base + ks * 256), idesc_tf32(128), ks > 0);
+            mma_ss_n(tmem_base + 128, make_desc<8>(smem_u32(smem + P::kW2T) + (trunk * kHidden + half * 128) * 32),
+                     make_desc<8>(smem_u32(smem + P::kG)), idesc_tf32(128), false);
         };
         if (tid == 0) {
             tc_fence_after();
@@ -746,38 +772,22 @@ __global__ void __launch_bounds__(kBwdTcThreads, 1) learner_bwd_tc_kernel(const 
 #pragma unroll 1
         for (int th = 0; th < 4; ++th) {                      // (trunk, 128-unit half)
             const int trunk = th >> 1, half = th & 1;
-            float w2[A > 1 ? A : 1];
-            if (trunk == 0) {
-                w2[0] = half ? w2v_j[1] : w2v_j[0];
-            } else {
-#pragma unroll
-                for (int a = 0; a < A; ++a) w2[a] = half ? w2p_j[1][a] : w2p_j[0][a];
-            }
             const float bias_j = trunk == 0 ? (half ? bias_v[1] : bias_v[0]) : (half ? bias_p[1] : bias_p[0]);
-            mbar_wait(bar_mma, phase);                        // H^T of this stage (and the gradient MMAs of the previous one)
+            mbar_wait(bar_mma, phase);                        // H^T, S^T of this stage (and the gradient MMAs of the previous one)
             phase ^= 1u;
             tc_fence_after();
-            // ---- this thread's 32 rows of its hidden unit: relu^T in place, dh^T next to it
+            // ---- this thread's 32 rows of its hidden unit: relu^T over H^T, dh^T = S^T where h > 0, both in place
+            //      (the tensor core truncates these fp32 A operands to tf32)
             uint32_t hr[32], dh[32];
             tmem_ld32(tmem_lane + cpart * 32, hr);
+            tmem_ld32(tmem_lane + 128 + cpart * 32, dh);
             tmem_ld_wait();
 #pragma unroll
             for (int i = 0; i < 32; ++i) {
-                const int n = cpart * 32 + i;
                 const float h = __uint_as_float(hr[i]) + bias_j;
-                const float4 g0 = *reinterpret_cast<const float4*>(s_g + n * 8);
-                float s;
-                if (trunk == 0) {
-                    s = g0.x * w2[0];
-                } else {
-                    s = g0.y * w2[0];
-                    if (A > 1) s = fmaf(g0.z, w2[A > 1 ? 1 : 0], s);
-                    if (A > 2) s = fmaf(g0.w, w2[A > 2 ? 2 : 0], s);
-                    if (A > 3) s = fmaf(s_g[n * 8 + 4], w2[A > 3 ? 3 : 0], s);
-                }
                 const bool on = h > 0.f;
-                hr[i] = __float_as_uint(on ? to_tf32_fast(h) : 0.f);
-                dh[i] = __float_as_uint(on ? to_tf32_fast(s) : 0.f);
+                hr[i] = on ? __float_as_uint(h) : 0u;
+                dh[i] = on ? dh[i] : 0u;
             }
             tmem_st32r(tmem_lane + cpart * 32, hr);
             tmem_st32r(tmem_lane + 128 + cpart * 32, dh);
@@ -874,7 +884,7 @@ int64_t fwd_image_reserve() {
 
 template <int A>
 int64_t workspace_bytes() {
-    return fwd_image_reserve<A>() + round_up(BwdPlan<A>::kImageBytes, 256) + (int64_t)kMaxBwdCtas * Shape<A>::kParams * 4;
+    return fwd_image_reserve<A>() + round_up(BwdTcPlan<A>::kImageBytes, 256) + (int64_t)kMaxBwdCtas * Shape<A>::kParams * 4;
 }
 
 template <int A, typename Kernel>
@@ -906,21 +916,23 @@ int launch_backward(const float* obs, int64_t N, const rnad_mlp_weights& w, cons
                     float* flat_grad, uint8_t* workspace, cudaStream_t st) {
     using P = BwdPlan<A>;
     using PT = BwdTcPlan<A>;
-    static_assert(PT::kImageBytes == P::kImageBytes && PT::kB1 == P::kB1, "both backward kernels read the same weight image");
+    static_assert(PT::kImageBytes >= P::kImageBytes, "the workspace reserves the larger image");
     uint8_t* image = workspace + fwd_image_reserve<A>();
-    float* partials = reinterpret_cast<float*>(image + round_up(P::kImageBytes, 256));
-    pack_bwd_image_kernel<A><<<24, 256, 0, st>>>(w, image);
-    RNAD_CHECK_LAUNCH("pack_bwd_image_kernel");
+    float* partials = reinterpret_cast<float*>(image + round_up(PT::kImageBytes, 256));
     int64_t blocks = (N + kTileM - 1) / kTileM;
     const int cap = sm_count() < kMaxBwdCtas ? sm_count() : kMaxBwdCtas;
     if (blocks > cap) blocks = cap;
     static const bool cuda_core_reduction = getenv("RNAD_LEARNER_BWD_CUDA_CORES") != nullptr;   // the previous kernel, for A/B runs
     if (cuda_core_reduction) {
+        pack_bwd_image_kernel<A><<<24, 256, 0, st>>>(w, image);
+        RNAD_CHECK_LAUNCH("pack_bwd_image_kernel");
         int rc = prepare<A>(learner_bwd_kernel<A>, P::kBytes, "cudaFuncSetAttribute(learner_bwd)");
         if (rc) return rc;
         learner_bwd_kernel<A><<<(int)blocks, kLearnThreads, P::kBytes, st>>>(obs, N, image, w, d_logit, d_v, partials);
         RNAD_CHECK_LAUNCH("learner_bwd_kernel");
     } else {
+        pack_bwd_tc_image_kernel<A><<<32, 256, 0, st>>>(w, image);
+        RNAD_CHECK_LAUNCH("pack_bwd_tc_image_kernel");
         // one CTA per SM owns all 512 TMEM columns: request more than half of the shared memory
         const size_t smem = PT::kBytes > 116 * 1024 ? PT::kBytes : 116 * 1024;
         int rc = prepare<A>(learner_bwd_tc_kernel<A>, smem, "cudaFuncSetAttribute(learner_bwd_tc)");
