@@ -21,6 +21,7 @@
 #include <cstdlib>
 
 #include "tc_common.cuh"
+#include "tc_pipe.cuh"
 
 namespace rnad {
 
@@ -229,10 +230,13 @@ __global__ void __launch_bounds__(kLearnThreads, 1) learner_fwd_kernel(const flo
         }
         tc_fence_before();
         __syncthreads();
-        if (tid == 0) {
+        if (warp == 0) {           // converged warp, one elected lane issues (see learner_bwd_tc_kernel)
             tc_fence_after();
-            issue_trunk_mma<KP>(a_base, b_base + 0 * P::kTrunkBytes, tmem_base + 0, bar_stage[0]);
-            issue_trunk_mma<KP>(a_base, b_base + 1 * P::kTrunkBytes, tmem_base + 256, bar_stage[1]);
+            if (tcp::elect_one()) {
+                issue_trunk_mma<KP>(a_base, b_base + 0 * P::kTrunkBytes, tmem_base + 0, bar_stage[0]);
+                issue_trunk_mma<KP>(a_base, b_base + 1 * P::kTrunkBytes, tmem_base + 256, bar_stage[1]);
+            }
+            __syncwarp();
         }
 
         float4 part[kFwdTrunks];
@@ -274,10 +278,12 @@ __global__ void __launch_bounds__(kLearnThreads, 1) learner_fwd_kernel(const flo
             tc_fence_before();
             if (pass + 2 < kFwdTrunks) {
                 __syncthreads();   // every thread has drained this accumulator stage
-                if (tid == 0) {
+                if (warp == 0) {
                     tc_fence_after();
-                    issue_trunk_mma<KP>(a_base, b_base + (pass + 2) * P::kTrunkBytes, tmem_base + stage * 256,
-                                        bar_stage[stage]);
+                    if (tcp::elect_one())
+                        issue_trunk_mma<KP>(a_base, b_base + (pass + 2) * P::kTrunkBytes, tmem_base + stage * 256,
+                                            bar_stage[stage]);
+                    __syncwarp();
                 }
             }
         }
@@ -720,22 +726,32 @@ __global__ void __launch_bounds__(kBwdTcThreads, 1) learner_bwd_tc_kernel(const 
 
     uint32_t phase = 0;
     const int64_t num_tiles = (N + kTileM - 1) / kTileM;
+    // threads 0..127 own one row of every tile; its observation and output gradients, one tile ahead
+    float x_next[KIN], g_next[1 + A];
+    auto load_tile_row = [&](int64_t tile) {
+        const int64_t row = tile * kTileM + tid;
+        const bool active = tile < num_tiles && row < N;
+        load_row<KIN>(obs, active ? row : 0, active, x_next);
+        g_next[0] = active ? __ldg(d_v + row) : 0.f;
+#pragma unroll
+        for (int a = 0; a < A; ++a) g_next[1 + a] = active ? __ldg(d_logit + row * A + a) : 0.f;
+    };
+    if (tid < kTileM) load_tile_row(blockIdx.x);
     for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        // ---- the tile's operands: observation tile (B of the recompute), x^T | 1 and g^T (B of the gradient MMAs)
+        // ---- the tile's operands: observation tile (B of the recompute), x^T | 1 and g^T (B of the gradient MMAs);
+        //      the row's data was loaded one tile ahead, the next tile's loads are issued right after it is consumed
         if (tid < kTileM) {
             const int n = tid;
-            const int64_t row = tile * kTileM + n;
-            const bool active = row < N;
-            float x[KIN];
-            load_row<KIN>(obs, row, active, x);
+            float x[KIN], g[1 + A];
+#pragma unroll
+            for (int k = 0; k < KIN; ++k) x[k] = x_next[k];
+#pragma unroll
+            for (int a = 0; a <= A; ++a) g[a] = g_next[a];
+            load_tile_row(tile + gridDim.x);
             store_operand_row<KIN, KP, P::kBiasInK>(smem + P::kX, n, x);
 #pragma unroll
             for (int k = 0; k < KIN; ++k) *reinterpret_cast<float*>(smem + P::kBX + off_t(k, n)) = to_tf32_fast(x[k]);
             *reinterpret_cast<float*>(smem + P::kBX + off_t(KIN, n)) = 1.f;
-            float g[1 + A];
-            g[0] = active ? d_v[row] : 0.f;
-#pragma unroll
-            for (int a = 0; a < A; ++a) g[1 + a] = active ? d_logit[row * A + a] : 0.f;
             float g8[8];
 #pragma unroll
             for (int a = 0; a < 8; ++a) g8[a] = a <= A ? to_tf32_fast(g[a < 1 + A ? a : 0]) : 0.f;
@@ -764,10 +780,15 @@ __global__ void __launch_bounds__(kBwdTcThreads, 1) learner_bwd_tc_kernel(const 
             mma_ss_n(tmem_base + 128, make_desc<8>(smem_u32(smem + P::kW2T) + (trunk * kHidden + half * 128) * 32),
                      make_desc<8>(smem_u32(smem + P::kG)), idesc_tf32(128), false);
         };
-        if (tid == 0) {
+        // (the whole warp runs this converged and one ELECTED lane issues: behind an `if (tid == 0)` ptxas wraps every
+        //  UTCHMMA in a waterfall loop and the issue rate drops to one MMA per ~75 cycles)
+        if (warp == 0) {
             tc_fence_after();
-            recompute(0);
-            mma_commit(bar_mma);
+            if (tcp::elect_one()) {
+                recompute(0);
+                mma_commit(bar_mma);
+            }
+            __syncwarp();
         }
 #pragma unroll 1
         for (int th = 0; th < 4; ++th) {                      // (trunk, 128-unit half)
@@ -797,10 +818,11 @@ __global__ void __launch_bounds__(kBwdTcThreads, 1) learner_bwd_tc_kernel(const 
             // ---- D_w2 += relu^T BG^T, D_w1 += dh^T BX^T (K = the 128 rows of the tile), then the next stage's H^T:
             //      the tensor core executes one thread's MMAs in order, so the recompute may overwrite relu^T right
             //      behind the MMAs that read it, and one commit covers the three groups
-            if (tid == 0) {
+            if (warp == 0) {
                 tc_fence_after();
                 const uint64_t bx = desc_lbo_sbo(smem_u32(smem + P::kBX), P::kLbo, P::kSboT);
                 const uint64_t bg = desc_lbo_sbo(smem_u32(smem + P::kBG), P::kLbo, P::kSboT);
+                if (tcp::elect_one()) {
 #pragma unroll
                 for (int ks = 0; ks < kTileM / 8; ++ks)
                     mma_ts_n(tmem_base + P::kColW2 + th * P::kNG, tmem_base + ks * 8, bg + (uint64_t)((ks * 2 * P::kLbo) >> 4),
@@ -811,6 +833,8 @@ __global__ void __launch_bounds__(kBwdTcThreads, 1) learner_bwd_tc_kernel(const 
                              idesc_tf32(P::kNX), true);
                 if (th < 3) recompute(th + 1);
                 mma_commit(bar_mma);
+                }
+                __syncwarp();
             }
         }
         mbar_wait(bar_mma, phase);                            // the last gradient MMAs have read the tile's operands
