@@ -561,8 +561,10 @@ __global__ void __launch_bounds__(kLearnThreads, 1) learner_bwd_kernel(const flo
 // whose accumulators stay in tensor memory over all tiles of the CTA.  No activation ever leaves the SM and the
 // CUDA cores do ~9 instructions per (row, hidden unit) instead of ~40.  Deterministic (fixed order everywhere).
 
-constexpr int kBwdTcThreads = 512;   // four threads per hidden unit (TMEM lane), 32 rows (columns) each
+constexpr int kBwdTcThreads = 256;   // two threads per hidden unit (TMEM lane), 32 rows (columns) of a 64-row stage each
 
+// Two CTAs share an SM, one per trunk (256 TMEM columns each): while one waits for its MMAs the other runs its
+// elementwise stage.  A stage is (128-unit half of the trunk) x (64-row half of the tile).
 template <int A>
 struct BwdTcPlan : Shape<A> {
     using S = Shape<A>;
@@ -571,12 +573,16 @@ struct BwdTcPlan : Shape<A> {
     static constexpr int kLbo = 144;                                   // K-chunk stride of BX / BG: 128 + 16 bytes of padding make the
                                                                        // transposing stores (32 rows n of one operand row c) conflict-free
     static constexpr int kSboT = (kTileM / 4) * kLbo;                  // 8-row groups of BX / BG
-    static constexpr int kB = 0;                                       // image: both trunks' first layers [256 x KP] tf32, K-major
-    static constexpr int kB1 = kB + 2 * S::kTrunkBytes;                //        their biases, 2 x 256 f32
-    static constexpr int kW2T = kB1 + 2 * kHidden * 4;                 //        second layers transposed, [512 x 8] tf32 K-major:
-                                                                       //        row trunk*256 + j = (w2v[j],0..) or (0,w2p[0][j],..)
+    // global image (pack_bwd_tc_image_kernel): both trunks' first layers, their biases, the transposed second layers
+    static constexpr int kB = 0;                                       // [2][256 x KP] tf32, K-major
+    static constexpr int kB1 = kB + 2 * S::kTrunkBytes;                // [2][256] f32
+    static constexpr int kW2T = kB1 + 2 * kHidden * 4;                 // [2][256 x 8] tf32 K-major: row j = (w2v[j],0..) or (0,w2p[0][j],..)
     static constexpr int kImageBytes = kW2T + 2 * kHidden * 8 * 4;
-    static constexpr int kX = kImageBytes;                             // observation tile [128 x KP] tf32, K-major
+    // shared memory of a CTA: its trunk's slices of the image, then the tile's operands
+    static constexpr int kSW1 = 0;
+    static constexpr int kSB1 = kSW1 + S::kTrunkBytes;
+    static constexpr int kSW2T = kSB1 + kHidden * 4;
+    static constexpr int kX = kSW2T + kHidden * 8 * 4;                 // observation tile [128 x KP] tf32, K-major
     static constexpr int kBX = kX + kTileM * S::KP * 4;
     static constexpr int kBG = kBX + (kNX / 8) * kSboT;
     static constexpr int kG = kBG + (kNG / 8) * kSboT;                 // g tile [128 x 8] tf32, K-major: d_v, d_logit[0..A)
@@ -584,10 +590,10 @@ struct BwdTcPlan : Shape<A> {
     static constexpr int kBar = kRed + 4 * 32;
     static constexpr int kTmem = kBar + 32;
     static constexpr int kBytes = kTmem + 16;
-    // tensor memory: [0,128) H^T -> relu^T, [128,256) dh^T, then 4 x kNX columns of D_w1 and 4 x 16 of D_w2
-    static constexpr int kColW1 = 256, kColW2 = 256 + 4 * kNX;
-    static_assert(kColW2 + 4 * kNG <= 512, "accumulators do not fit tensor memory");
-    static_assert(kBytes <= 227 * 1024, "shared memory plan does not fit");
+    // tensor memory (256 columns): [0,64) H^T -> relu^T, [64,128) S^T -> dh^T, then 2 x kNX of D_w1 and 2 x 16 of D_w2
+    static constexpr int kColW1 = 128, kColW2 = 128 + 2 * kNX;
+    static_assert(kColW2 + 2 * kNG <= 256, "accumulators do not fit the CTA's share of tensor memory");
+    static_assert(2 * (kBytes + 1024) <= 228 * 1024, "two CTAs per SM do not fit shared memory");
     static_assert(kX % 16 == 0 && kBX % 16 == 0 && kBG % 16 == 0 && kG % 16 == 0 && kBar % 8 == 0, "alignment");
 };
 
@@ -614,27 +620,6 @@ __device__ __forceinline__ void mma_ss_n(uint32_t d_tmem, uint64_t a_desc, uint6
         "l"(a_desc), "l"(b_desc), "r"(idesc), "r"((uint32_t)acc)
         : "memory");
 }
-__device__ __forceinline__ void mma_ts_n(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, bool acc) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t"
-        "}\n" ::"r"(d_tmem),
-        "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"((uint32_t)acc)
-        : "memory");
-}
-__device__ __forceinline__ void tmem_st32r(uint32_t taddr, const uint32_t* r) {
-    asm volatile(
-        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
-        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
-        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
-        "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
-        "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]),
-        "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]),
-        "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
-        : "memory");
-}
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
@@ -644,7 +629,6 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
         : "r"(taddr)
         : "memory");
 }
-__device__ __forceinline__ void tmem_st_wait_all() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 template <int A>
 __global__ void pack_bwd_tc_image_kernel(rnad_mlp_weights w, uint8_t* __restrict__ image) {
@@ -662,33 +646,46 @@ __global__ void pack_bwd_tc_image_kernel(rnad_mlp_weights w, uint8_t* __restrict
         float v = 0.f;
         if (trunk == 0 && k == 0) v = w.value_fc1_w[j];
         if (trunk == 1 && k >= 1 && k <= A) v = w.policy_fc1_w[(k - 1) * kHidden + j];
-        *reinterpret_cast<float*>(image + P::kW2T + operand_offset<8>(row, k)) = to_tf32(v);
+        *reinterpret_cast<float*>(image + P::kW2T + trunk * kHidden * 32 + operand_offset<8>(j, k)) = to_tf32(v);
     }
 }
 
 template <int A>
-__global__ void __launch_bounds__(kBwdTcThreads, 1) learner_bwd_tc_kernel(const float* __restrict__ obs, int64_t N,
+__global__ void __launch_bounds__(kBwdTcThreads, 2) learner_bwd_tc_kernel(const float* __restrict__ obs, int64_t N,
                                                                            const uint8_t* __restrict__ image,
-                                                                           rnad_mlp_weights w,
                                                                            const float* __restrict__ d_logit,
                                                                            const float* __restrict__ d_v,
                                                                            float* __restrict__ partials) {
     using P = BwdTcPlan<A>;
     constexpr int KIN = P::KIN, KP = P::KP;
+    constexpr int kSbo1 = (KP / 4) * 128;
     static_assert(A <= 4, "g[n] is staged as 8 floats");
     extern __shared__ __align__(1024) uint8_t smem[];
     const int tid = threadIdx.x, warp = tid >> 5, lane32 = tid & 31;
-    const int quad = warp & 3, cpart = warp >> 2;             // TMEM lane quadrant (hidden units), 32-column (row) part
+    const int trunk = blockIdx.x & 1;                         // 0: value trunk, 1: policy trunk
+    const int cta = blockIdx.x >> 1, n_ctas = gridDim.x >> 1; // the two CTAs of a pair walk the same tiles
+    const int quad = warp & 3, cpart = warp >> 2;             // TMEM lane quadrant (hidden units), 32-column (row) part of a stage
     const int j_local = quad * 32 + lane32;                   // hidden unit of the current 128-unit half == TMEM lane
     const uint32_t bar_img = smem_u32(smem + P::kBar), bar_mma = bar_img + 8;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + P::kTmem);
 
-    if (warp == 0) tmem_alloc<512>(tmem_slot);
+    if (warp == 0) tmem_alloc<256>(tmem_slot);
     if (tid == 0) {
         mbar_init(bar_img, 1);
         mbar_init(bar_mma, 1);
         mbar_fence_init();
-        tma_bulk_load(smem, image, P::kImageBytes, bar_img);
+        // this trunk's slices of the weight image: three bulk copies counted on one barrier
+        constexpr uint32_t kBytesIn = P::kTrunkBytes + kHidden * 4 + kHidden * 32;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_img), "r"(kBytesIn) : "memory");
+        auto bulk = [&](int dst, const uint8_t* src, uint32_t bytes) {
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                             smem_u32(smem + dst)),
+                         "l"(src), "r"(bytes), "r"(bar_img)
+                         : "memory");
+        };
+        bulk(P::kSW1, image + P::kB + trunk * P::kTrunkBytes, P::kTrunkBytes);
+        bulk(P::kSB1, image + P::kB1 + trunk * kHidden * 4, kHidden * 4);
+        bulk(P::kSW2T, image + P::kW2T + trunk * kHidden * 32, kHidden * 32);
     }
     // operand rows that are never written stay zero
     for (int i = tid; i < ((P::kNX + P::kNG) / 8) * P::kSboT / 4; i += kBwdTcThreads) reinterpret_cast<uint32_t*>(smem + P::kBX)[i] = 0u;
@@ -698,31 +695,27 @@ __global__ void __launch_bounds__(kBwdTcThreads, 1) learner_bwd_tc_kernel(const 
     mbar_wait(bar_img, 0);
     const uint32_t tmem_base = *tmem_slot;
     const uint32_t tmem_lane = tmem_base + ((uint32_t)(quad * 32) << 16);
-    {   // clear the gradient accumulators: columns [256, 512), 64 per thread of a lane
+    {   // clear the gradient accumulators: columns [128, 256), 64 per thread of a lane
         uint32_t zero[32];
 #pragma unroll
         for (int i = 0; i < 32; ++i) zero[i] = 0u;
 #pragma unroll
-        for (int q = 0; q < 2; ++q) tmem_st32r(tmem_lane + 256 + cpart * 64 + q * 32, zero);
-        tmem_st_wait_all();
+        for (int q = 0; q < 2; ++q) tcp::tmem_st32(tmem_lane + 128 + cpart * 64 + q * 32, zero);
+        tcp::tmem_st_wait();
     }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
 
-    const float* b1 = reinterpret_cast<const float*>(smem + P::kB1);
+    const float* b1 = reinterpret_cast<const float*>(smem + P::kSB1);
     auto off_t = [](int c, int n) { return (c >> 3) * P::kSboT + (n >> 2) * P::kLbo + (c & 7) * 16 + (n & 3) * 4; };
     float gsum[1 + A];
 #pragma unroll
     for (int a = 0; a <= A; ++a) gsum[a] = 0.f;
     // this lane's hidden units (one per 128-unit half): first-layer bias where it does not ride in K
-    float bias_v[2], bias_p[2];
+    float bias_j[2];
 #pragma unroll
-    for (int half = 0; half < 2; ++half) {
-        const int j = half * 128 + j_local;
-        bias_v[half] = P::kBiasInK ? 0.f : b1[j];
-        bias_p[half] = P::kBiasInK ? 0.f : b1[kHidden + j];
-    }
+    for (int half = 0; half < 2; ++half) bias_j[half] = P::kBiasInK ? 0.f : b1[half * 128 + j_local];
 
     uint32_t phase = 0;
     const int64_t num_tiles = (N + kTileM - 1) / kTileM;
@@ -736,8 +729,8 @@ __global__ void __launch_bounds__(kBwdTcThreads, 1) learner_bwd_tc_kernel(const 
 #pragma unroll
         for (int a = 0; a < A; ++a) g_next[1 + a] = active ? __ldg(d_logit + row * A + a) : 0.f;
     };
-    if (tid < kTileM) load_tile_row(blockIdx.x);
-    for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    if (tid < kTileM) load_tile_row(cta);
+    for (int64_t tile = cta; tile < num_tiles; tile += n_ctas) {
         // ---- the tile's operands: observation tile (B of the recompute), x^T | 1 and g^T (B of the gradient MMAs);
         //      the row's data was loaded one tile ahead, the next tile's loads are issued right after it is consumed
         if (tid < kTileM) {
@@ -747,7 +740,7 @@ __global__ void __launch_bounds__(kBwdTcThreads, 1) learner_bwd_tc_kernel(const 
             for (int k = 0; k < KIN; ++k) x[k] = x_next[k];
 #pragma unroll
             for (int a = 0; a <= A; ++a) g[a] = g_next[a];
-            load_tile_row(tile + gridDim.x);
+            load_tile_row(tile + n_ctas);
             store_operand_row<KIN, KP, P::kBiasInK>(smem + P::kX, n, x);
 #pragma unroll
             for (int k = 0; k < KIN; ++k) *reinterpret_cast<float*>(smem + P::kBX + off_t(k, n)) = to_tf32_fast(x[k]);
@@ -768,17 +761,17 @@ __global__ void __launch_bounds__(kBwdTcThreads, 1) learner_bwd_tc_kernel(const 
         tc_fence_before();
         __syncthreads();
 
-        // H^T = W1[trunk, half] . X^T   (M = hidden units, N = rows, K = inputs)      into columns [0, 128)
-        // S^T = W2^T[trunk, half] . G^T (K = the 1 + A outputs): (g W2)^T             into columns [128, 256)
-        auto recompute = [&](int th) {
-            const int trunk = th >> 1, half = th & 1;
-            const uint32_t a_base = smem_u32(smem + P::kB) + trunk * P::kTrunkBytes + half * (128 / 8) * ((KP / 4) * 128);
-            const uint32_t b_base = smem_u32(smem + P::kX);
+        // stage st = (hidden half, row half).  H^T = W1[half] . X^T[rows]  (M = hidden units, N = 64 rows, K = inputs)
+        // into columns [0, 64);  S^T = W2^T[half] . G^T[rows] = (g W2)^T (K = the 1 + A outputs) into columns [64, 128)
+        auto recompute = [&](int st) {
+            const int half = st >> 1, rh = st & 1;
+            const uint32_t a_base = smem_u32(smem + P::kSW1) + half * (128 / 8) * kSbo1;
+            const uint32_t b_base = smem_u32(smem + P::kX) + rh * (64 / 8) * kSbo1;
 #pragma unroll
             for (int ks = 0; ks < KP / 8; ++ks)
-                mma_ss_n(tmem_base, make_desc<KP>(a_base + ks * 256), make_desc<KP>(b_base + ks * 256), idesc_tf32(128), ks > 0);
-            mma_ss_n(tmem_base + 128, make_desc<8>(smem_u32(smem + P::kW2T) + (trunk * kHidden + half * 128) * 32),
-                     make_desc<8>(smem_u32(smem + P::kG)), idesc_tf32(128), false);
+                mma_ss_n(tmem_base, make_desc<KP>(a_base + ks * 256), make_desc<KP>(b_base + ks * 256), idesc_tf32(64), ks > 0);
+            mma_ss_n(tmem_base + 64, make_desc<8>(smem_u32(smem + P::kSW2T) + half * 128 * 32),
+                     make_desc<8>(smem_u32(smem + P::kG) + rh * 64 * 32), idesc_tf32(64), false);
         };
         // (the whole warp runs this converged and one ELECTED lane issues: behind an `if (tid == 0)` ptxas wraps every
         //  UTCHMMA in a waterfall loop and the issue rate drops to one MMA per ~75 cycles)
@@ -791,9 +784,9 @@ __global__ void __launch_bounds__(kBwdTcThreads, 1) learner_bwd_tc_kernel(const 
             __syncwarp();
         }
 #pragma unroll 1
-        for (int th = 0; th < 4; ++th) {                      // (trunk, 128-unit half)
-            const int trunk = th >> 1, half = th & 1;
-            const float bias_j = trunk == 0 ? (half ? bias_v[1] : bias_v[0]) : (half ? bias_p[1] : bias_p[0]);
+        for (int st = 0; st < 4; ++st) {
+            const int half = st >> 1, rh = st & 1;
+            const float bias = half ? bias_j[1] : bias_j[0];
             mbar_wait(bar_mma, phase);                        // H^T, S^T of this stage (and the gradient MMAs of the previous one)
             phase ^= 1u;
             tc_fence_after();
@@ -801,38 +794,38 @@ __global__ void __launch_bounds__(kBwdTcThreads, 1) learner_bwd_tc_kernel(const 
             //      (the tensor core truncates these fp32 A operands to tf32)
             uint32_t hr[32], dh[32];
             tmem_ld32(tmem_lane + cpart * 32, hr);
-            tmem_ld32(tmem_lane + 128 + cpart * 32, dh);
+            tmem_ld32(tmem_lane + 64 + cpart * 32, dh);
             tmem_ld_wait();
 #pragma unroll
             for (int i = 0; i < 32; ++i) {
-                const float h = __uint_as_float(hr[i]) + bias_j;
+                const float h = __uint_as_float(hr[i]) + bias;
                 const bool on = h > 0.f;
                 hr[i] = on ? __float_as_uint(h) : 0u;
                 dh[i] = on ? dh[i] : 0u;
             }
-            tmem_st32r(tmem_lane + cpart * 32, hr);
-            tmem_st32r(tmem_lane + 128 + cpart * 32, dh);
-            tmem_st_wait_all();
+            tcp::tmem_st32(tmem_lane + cpart * 32, hr);
+            tcp::tmem_st32(tmem_lane + 64 + cpart * 32, dh);
+            tcp::tmem_st_wait();
             tc_fence_before();
             __syncthreads();
-            // ---- D_w2 += relu^T BG^T, D_w1 += dh^T BX^T (K = the 128 rows of the tile), then the next stage's H^T:
-            //      the tensor core executes one thread's MMAs in order, so the recompute may overwrite relu^T right
-            //      behind the MMAs that read it, and one commit covers the three groups
+            // ---- D_w2[half] += relu^T BG^T, D_w1[half] += dh^T BX^T (K = the stage's 64 rows), then the next stage's
+            //      H^T / S^T: the tensor core executes one thread's MMAs in order, so the recompute may overwrite the
+            //      columns right behind the MMAs that read them, and one commit covers the three groups
             if (warp == 0) {
                 tc_fence_after();
-                const uint64_t bx = desc_lbo_sbo(smem_u32(smem + P::kBX), P::kLbo, P::kSboT);
-                const uint64_t bg = desc_lbo_sbo(smem_u32(smem + P::kBG), P::kLbo, P::kSboT);
+                const uint64_t bx = desc_lbo_sbo(smem_u32(smem + P::kBX) + rh * 16 * P::kLbo, P::kLbo, P::kSboT);
+                const uint64_t bg = desc_lbo_sbo(smem_u32(smem + P::kBG) + rh * 16 * P::kLbo, P::kLbo, P::kSboT);
                 if (tcp::elect_one()) {
 #pragma unroll
-                for (int ks = 0; ks < kTileM / 8; ++ks)
-                    mma_ts_n(tmem_base + P::kColW2 + th * P::kNG, tmem_base + ks * 8, bg + (uint64_t)((ks * 2 * P::kLbo) >> 4),
-                             idesc_tf32(P::kNG), true);
+                    for (int ks = 0; ks < 8; ++ks)
+                        tcp::mma_ts(tmem_base + P::kColW2 + half * P::kNG, tmem_base + ks * 8, bg + (uint64_t)((ks * 2 * P::kLbo) >> 4),
+                                    idesc_tf32(P::kNG), true);
 #pragma unroll
-                for (int ks = 0; ks < kTileM / 8; ++ks)
-                    mma_ts_n(tmem_base + P::kColW1 + th * P::kNX, tmem_base + 128 + ks * 8, bx + (uint64_t)((ks * 2 * P::kLbo) >> 4),
-                             idesc_tf32(P::kNX), true);
-                if (th < 3) recompute(th + 1);
-                mma_commit(bar_mma);
+                    for (int ks = 0; ks < 8; ++ks)
+                        tcp::mma_ts(tmem_base + P::kColW1 + half * P::kNX, tmem_base + 64 + ks * 8,
+                                    bx + (uint64_t)((ks * 2 * P::kLbo) >> 4), idesc_tf32(P::kNX), true);
+                    if (st < 3) recompute(st + 1);
+                    mma_commit(bar_mma);
                 }
                 __syncwarp();
             }
@@ -843,22 +836,22 @@ __global__ void __launch_bounds__(kBwdTcThreads, 1) learner_bwd_tc_kernel(const 
         __syncthreads();
     }
 
-    // ---- this CTA's partial gradient, flat in state_dict order
-    float* dst = partials + (int64_t)blockIdx.x * P::kParams;
+    // ---- this CTA's share of the pair's partial gradient, flat in state_dict order
+    float* dst = partials + (int64_t)cta * P::kParams;
     if (cpart == 0) {
 #pragma unroll 1
-        for (int th = 0; th < 4; ++th) {
-            const int trunk = th >> 1, j = (th & 1) * 128 + j_local;
+        for (int half = 0; half < 2; ++half) {
+            const int j = half * 128 + j_local;
             uint32_t acc[P::kNX];
 #pragma unroll
-            for (int q = 0; q < P::kNX / 16; ++q) tmem_ld16(tmem_lane + P::kColW1 + th * P::kNX + q * 16, acc + q * 16);
+            for (int q = 0; q < P::kNX / 16; ++q) tmem_ld16(tmem_lane + P::kColW1 + half * P::kNX + q * 16, acc + q * 16);
             tmem_ld_wait();
             float* w1_dst = dst + (trunk == 0 ? P::kOffV0w : P::kOffP0w) + j * KIN;
 #pragma unroll
             for (int k = 0; k < KIN; ++k) w1_dst[k] = __uint_as_float(acc[k]);
             dst[(trunk == 0 ? P::kOffV0b : P::kOffP0b) + j] = __uint_as_float(acc[KIN]);
             uint32_t acc2[16];
-            tmem_ld16(tmem_lane + P::kColW2 + th * P::kNG, acc2);
+            tmem_ld16(tmem_lane + P::kColW2 + half * P::kNG, acc2);
             tmem_ld_wait();
             if (trunk == 0) {
                 dst[P::kOffV1w + j] = __uint_as_float(acc2[0]);
@@ -880,12 +873,12 @@ __global__ void __launch_bounds__(kBwdTcThreads, 1) learner_bwd_tc_kernel(const 
     __syncthreads();
     if (tid <= A) {
         const float v = (s_red[0 * 8 + tid] + s_red[1 * 8 + tid]) + (s_red[2 * 8 + tid] + s_red[3 * 8 + tid]);
-        if (tid == 0) dst[P::kOffV1b] = v;
-        else dst[P::kOffP1b + tid - 1] = v;
+        if (tid == 0 && trunk == 0) dst[P::kOffV1b] = v;
+        if (tid > 0 && trunk == 1) dst[P::kOffP1b + tid - 1] = v;
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 0) tmem_dealloc<512>(tmem_base);
+    if (warp == 0) tmem_dealloc<256>(tmem_base);
 }
 
 __global__ void reduce_partials_kernel(const float* __restrict__ partials, int n_parts, int n_params,
@@ -957,11 +950,14 @@ int launch_backward(const float* obs, int64_t N, const rnad_mlp_weights& w, cons
     } else {
         pack_bwd_tc_image_kernel<A><<<32, 256, 0, st>>>(w, image);
         RNAD_CHECK_LAUNCH("pack_bwd_tc_image_kernel");
-        // one CTA per SM owns all 512 TMEM columns: request more than half of the shared memory
-        const size_t smem = PT::kBytes > 116 * 1024 ? PT::kBytes : 116 * 1024;
+        // two CTAs per SM (one per trunk, 256 TMEM columns each): pad the shared-memory request so that a third can
+        // never become resident and spin inside tcgen05.alloc
+        size_t smem = PT::kBytes;
+        const size_t floor_two_per_sm = 227 * 1024 / 3 + 1024;
+        if (smem < floor_two_per_sm) smem = floor_two_per_sm;
         int rc = prepare<A>(learner_bwd_tc_kernel<A>, smem, "cudaFuncSetAttribute(learner_bwd_tc)");
         if (rc) return rc;
-        learner_bwd_tc_kernel<A><<<(int)blocks, kBwdTcThreads, smem, st>>>(obs, N, image, w, d_logit, d_v, partials);
+        learner_bwd_tc_kernel<A><<<2 * (int)blocks, kBwdTcThreads, smem, st>>>(obs, N, image, d_logit, d_v, partials);
         RNAD_CHECK_LAUNCH("learner_bwd_tc_kernel");
     }
     reduce_partials_kernel<<<(P::kParams + 255) / 256, 256, 0, st>>>(partials, (int)blocks, P::kParams, flat_grad);
