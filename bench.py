@@ -335,13 +335,15 @@ def run_native(args):
             offset += p.numel()
     returns_host = torch.empty(batch, dtype=torch.float32).pin_memory()
     h2d_bytes = flat_host.numel() * 4
-    d2h_bytes = batch * 4 + 4                   # per-game returns + t_eff
+    d2h_bytes = batch * 4                       # per-game returns
 
     def e2e_step():
         flat_dev.copy_(flat_host, non_blocking=True)
         ep = Episodes(tree, batch)
         ep.generate(net, precision=precision)
-        returns_host.copy_(ep.rewards.sum(0), non_blocking=True)
+        # per-game returns from the full-length reward tensor (slots past a game's end hold zeros): one device -> host
+        # read per step; the trajectory length itself resolves lazily (Episodes.t_eff) and is not needed here
+        returns_host.copy_(ep.full("rewards").sum(0), non_blocking=True)
         torch.cuda.current_stream().synchronize()
 
     e2e_ms, _ = timed_steps(e2e_step, args.steps, args.warmup, flush, barrier)
@@ -413,7 +415,7 @@ def run_native(args):
                     "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
                     "ms_per_step": e2e_ms / args.steps,
                     "what": "net weights copied from pinned host memory, Episodes.generate(net), per-game returns "
-                            "and t_eff read back to the host"},
+                            "read back to the host"},
             "gpu_launches": args.steps * runner.launches_per_step,
             "roofline": {"bound": "hbm", "achieved": achieved_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                          "frac": achieved_gbs / peaks["hbm_gbs"],

@@ -108,7 +108,7 @@ RNAD_API int rnad_sample_categorical(const float* p, int64_t B, int N, const flo
  * Outputs, all (T,B,...) contiguous, reference dtypes (episode.py:218-225):
  *   indices i64, turns i64, observations f32 (T,B,2,A,A), policy f32 (T,B,A),
  *   actions f32 one-hot (T,B,A), rewards f32, values f32, masks f32 (T,B,A).
- * t_last (device int32, caller sets to -1): max over games of the last
+ * t_last (device int32; the call resets it to -1 in stream order): max over games of the last
  * half-move at which the game was not yet on the absorbing node (= t_eff).
  * workspace: 16-byte aligned device scratch of rnad_rollout_workspace_bytes()
  * (the tensor-core engine lays the weights out in MMA operand order there once per

@@ -36,6 +36,9 @@ extern "C" int rnad_rollout(const uint32_t* ev_tab, const uint32_t* tr_tab, int 
                      out->actions, out->rewards, out->values, out->masks};
     g.t_last = t_last;
     cudaStream_t st = (cudaStream_t)stream;
+    // the kernels atomicMax into *t_last: start it at -1 here, in stream order
+    int rc = check_cuda(cudaMemsetAsync(t_last, 0xFF, sizeof(int32_t), st), "cudaMemsetAsync(t_last)");
+    if (rc) return rc;
     switch (precision) {
         case RNAD_PREC_FP32: return rollout_fp32(g, st);
         case RNAD_PREC_TF32: return rollout_tc(g, workspace, st);

@@ -182,6 +182,45 @@ def _rollout_scratch(dev, a, width, prec):
     return hit
 
 
+_LAYOUTS = {}
+
+
+class _TrajectoryArena:
+    """
+    One device allocation holding the eight (t_max, B, ...) trajectory tensors of a fused rollout in the order of
+    `rnad_trajectory` (256-byte aligned each) plus the batch's t_eff word; tensor views are created on first use.
+    """
+
+    KEYS = ("indices", "turns", "observations", "policy", "actions", "rewards", "values", "masks")
+
+    def __init__(self, t_max, b, a, dev):
+        layout = _LAYOUTS.get((t_max, b, a))
+        if layout is None:
+            fields = ((torch.int64, ()), (torch.int64, ()), (torch.float32, (2, a, a)), (torch.float32, (a,)),
+                      (torch.float32, (a,)), (torch.float32, ()), (torch.float32, ()), (torch.float32, (a,)))
+            offsets, total = [], 0
+            for dtype, tail in fields:
+                n_bytes = t_max * b * math.prod(tail) * (8 if dtype == torch.int64 else 4)
+                offsets.append((total, n_bytes, dtype, (t_max, b) + tail))
+                total += (n_bytes + 255) // 256 * 256
+            layout = _LAYOUTS[(t_max, b, a)] = (dict(zip(self.KEYS, offsets)), total)
+        self.fields, self.total = layout
+        self.arena = torch.empty(self.total + 256, dtype=torch.uint8, device=dev)
+        self.t_last = self.arena[self.total: self.total + 4].view(torch.int32)
+        self.views = {}
+
+    def pointers(self):
+        base = self.arena.data_ptr()
+        return [base + self.fields[k][0] for k in self.KEYS]
+
+    def __getitem__(self, key):
+        view = self.views.get(key)
+        if view is None:
+            off, n_bytes, dtype, shape = self.fields[key]
+            view = self.views[key] = self.arena[off: off + n_bytes].view(dtype).view(shape)
+        return view
+
+
 class Episodes:
     """A batch of rollout trajectories from the root; tensors are time-major (T, B, ...)."""
 
@@ -230,8 +269,8 @@ class Episodes:
         full, t_last = pending
         self.__dict__["t_eff"] = int(t_last.item())
         n = self.__dict__["t_eff"] + 1
-        for key, value in full.items():
-            self.__dict__[key] = value[:n]
+        for key in _TrajectoryArena.KEYS:
+            self.__dict__[key] = full[key][:n]
 
     def full(self, key: str) -> torch.Tensor:
         """The (t_max, B, ...) tensor a fused rollout wrote, without waiting for t_eff; else the stored tensor."""
@@ -302,32 +341,19 @@ class Episodes:
         prec = _b200.PRECISIONS[precision]
 
         with torch.cuda.device(dev):
-            # one allocation for the whole trajectory: the eight (T, B, ...) tensors are views of it
-            fields = (("indices", torch.int64, ()), ("turns", torch.int64, ()), ("observations", torch.float32, (2, a, a)),
-                      ("policy", torch.float32, (a,)), ("actions", torch.float32, (a,)), ("rewards", torch.float32, ()),
-                      ("values", torch.float32, ()), ("masks", torch.float32, (a,)))
-            offsets, total = [], 0
-            for _, dtype, tail in fields:
-                offsets.append(total)
-                n_bytes = t_max * b * math.prod(tail) * (8 if dtype == torch.int64 else 4)
-                total += (n_bytes + 255) // 256 * 256
-            arena = torch.empty(total + 256, dtype=torch.uint8, device=dev)
-            out = {}
-            for (key, dtype, tail), off in zip(fields, offsets):
-                n_bytes = t_max * b * math.prod(tail) * (8 if dtype == torch.int64 else 4)
-                out[key] = arena[off: off + n_bytes].view(dtype).view((t_max, b) + tail)
-            traj = _b200.Trajectory(**{k: v.data_ptr() for k, v in out.items()})
+            # one allocation for the whole trajectory: the eight (T, B, ...) tensors are views of it, made on demand
+            out = _TrajectoryArena(t_max, b, a, dev)
+            traj = _b200.Trajectory(*out.pointers())
             if uniforms is not None:
                 uniforms = uniforms.to(device=dev, dtype=torch.float32).contiguous()
                 if uniforms.shape[0] < t_max or tuple(uniforms.shape[1:]) != (b, 2):
                     raise _b200.RnadError(f"uniforms must be ({t_max}+, {b}, 2), got {tuple(uniforms.shape)}")
                 uniforms = uniforms[:t_max].contiguous()
             _, workspace = _rollout_scratch(dev, a, net.width, prec)
-            t_last = arena[total: total + 4].view(torch.int32)     # this batch's own t_eff word
-            t_last.fill_(-1)
+            t_last = out.t_last                                    # this batch's own t_eff word (the call resets it)
             L.rnad_rollout(_b200.ptr(packed.ev_tab), _b200.ptr(packed.tr_tab), a, packed.C, ctypes.byref(w), b, t_max,
                            self.states.seed, self.states.game_offset, _b200.ptr(uniforms), prec, ctypes.byref(traj),
-                           _b200.ptr(t_last), _b200.ptr(workspace), _b200.stream())
+                           t_last.data_ptr(), _b200.ptr(workspace), _b200.stream())
         self.precision = precision
         for key in Episodes._LAZY:
             self.__dict__.pop(key, None)             # resolved on first access (see __getattr__)
