@@ -27,9 +27,9 @@
 //                           memory - so that no global load sits between a column action and
 //                           the next observation.
 //
-// Everything is ordered by mbarriers; no CTA-wide barrier inside the rollout.  The
-// weights arrive as ONE TMA bulk copy of an image a pre-kernel lays out in operand
-// order.  Reference: environment/episode.py:175-230, nn/net.py:37-51.
+// Everything is ordered by mbarriers; no CTA-wide barrier inside the rollout.  Every
+// CTA lays the weights out in operand order in its own shared memory at start-up (the
+// whole launch is this one kernel).  Reference: environment/episode.py:175-230, nn/net.py:37-51.
 #include "game.cuh"
 #include "rollout.cuh"
 #include "tc_common.cuh"
@@ -124,36 +124,48 @@ __device__ long long g_trace[4][16][24];
 #define TRI(role, item, which) do { } while (0)
 #endif
 
+// The weight image in MMA-operand order, written straight into the CTA's shared memory by all of its threads
+// (43 KB of fp32 nn.Linear tensors from L2 -> 66 KB of tf32 operands): no pre-kernel, no workspace.
 template <int A>
-__global__ void pack_weights_kernel(rnad_mlp_weights w, uint8_t* __restrict__ image) {
+__device__ __forceinline__ void pack_weights(const rnad_mlp_weights& w, uint8_t* __restrict__ image, int thread) {
     using P = Plan<A>;
     constexpr int KIN = P::KIN, KP = P::KP;
-    const int thread = blockIdx.x * blockDim.x + threadIdx.x, stride = gridDim.x * blockDim.x;
-    for (int e = thread; e < 2 * kHidden * KP; e += stride) {
-        const int n = e / KP, k = e % KP;   // hidden unit n of [value trunk | policy trunk], input k
-        const int j = n & (kHidden - 1);
-        float v = 0.f;
-        if (k < KIN) v = (n < kHidden ? w.value_fc0_w : w.policy_fc0_w)[j * KIN + k];
-        else if (P::kBiasInK && k == KIN) v = (n < kHidden ? w.value_fc0_b : w.policy_fc0_b)[j];
-        *reinterpret_cast<float*>(image + P::kW1 + operand_offset<KP>(n, k)) = to_tf32(v);
-    }
-    // second layers as ONE [8 x 512] operand: row 0 = value_fc1 over the value trunk's hidden units,
-    // rows 1..A = policy_fc1 over the policy trunk's, zero elsewhere
-    for (int e = thread; e < 8 * kK2; e += stride) {
-        const int n = e / kK2, k = e % kK2;
-        float v = 0.f;
-        if (n == 0 && k < kHidden) v = w.value_fc1_w[k];
-        else if (n >= 1 && n <= A && k >= kHidden) v = w.policy_fc1_w[(n - 1) * kHidden + (k - kHidden)];
-        *reinterpret_cast<float*>(image + P::kW2 + operand_offset<kK2>(n, k)) = to_tf32(v);
-    }
-    for (int j = thread; j < kHidden; j += stride) {
-        reinterpret_cast<float*>(image + P::kB1)[j] = w.value_fc0_b[j];
-        reinterpret_cast<float*>(image + P::kB1)[kHidden + j] = w.policy_fc0_b[j];
+    static_assert(kThreads >= 2 * kHidden, "one thread per first-layer row");
+    if (thread < 2 * kHidden) {
+        // first layers: thread n owns hidden unit n of [value trunk | policy trunk]: one row of 2A^2 inputs (scalar loads,
+        // all in flight at once; the tensors are only guaranteed 4-byte aligned) -> KP / 4 sixteen-byte operand chunks
+        const int n = thread, j = n & (kHidden - 1);
+        const float* src = (n < kHidden ? w.value_fc0_w : w.policy_fc0_w) + j * KIN;
+        float x[KP];
+#pragma unroll
+        for (int k = 0; k < KIN; ++k) x[k] = __ldg(src + k);
+        const float bias = __ldg((n < kHidden ? w.value_fc0_b : w.policy_fc0_b) + j);
+#pragma unroll
+        for (int k = KIN; k < KP; ++k) x[k] = (P::kBiasInK && k == KIN) ? bias : 0.f;
+#pragma unroll
+        for (int q = 0; q < KP / 4; ++q)
+            *reinterpret_cast<float4*>(image + P::kW1 + operand_offset<KP>(n, 4 * q)) =
+                make_float4(to_tf32_fast(x[4 * q]), to_tf32_fast(x[4 * q + 1]), to_tf32_fast(x[4 * q + 2]), to_tf32_fast(x[4 * q + 3]));
+        reinterpret_cast<float*>(image + P::kB1)[n] = bias;
+        // second layers as ONE [8 x 512] operand: row 0 = value_fc1 over the value trunk's hidden units, rows 1..A =
+        // policy_fc1 over the policy trunk's, zero elsewhere; thread k owns column k (hidden unit k of the two trunks)
+        const int k = thread;
+        float col[8];
+#pragma unroll
+        for (int r = 0; r < 8; ++r) col[r] = 0.f;
+        if (k < kHidden) {
+            col[0] = __ldg(w.value_fc1_w + k);
+        } else {
+#pragma unroll
+            for (int a = 0; a < A; ++a) col[1 + a] = __ldg(w.policy_fc1_w + a * kHidden + (k - kHidden));
+        }
+#pragma unroll
+        for (int r = 0; r < 8; ++r) *reinterpret_cast<float*>(image + P::kW2 + operand_offset<kK2>(r, k)) = to_tf32_fast(col[r]);
     }
     if (thread < 8) {
         float v = 0.f;
-        if (thread == 0) v = w.value_fc1_b[0];
-        else if (thread <= A) v = w.policy_fc1_b[thread - 1];
+        if (thread == 0) v = __ldg(w.value_fc1_b);
+        else if (thread <= A) v = __ldg(w.policy_fc1_b + thread - 1);
         reinterpret_cast<float*>(image + P::kB2)[thread] = v;
     }
 }
@@ -247,7 +259,7 @@ __device__ __forceinline__ void gather_candidates(const uint32_t* __restrict__ t
 }
 
 template <int A, int C>
-__global__ void __launch_bounds__(kThreads, 1) rollout_tc2_kernel(RolloutArgs g, const uint8_t* __restrict__ image) {
+__global__ void __launch_bounds__(kThreads, 1) rollout_tc2_kernel(RolloutArgs g) {
     using P = Plan<A>;
     constexpr int KIN = P::KIN, KP = P::KP;
     static_assert(A <= 4, "value + logits must fit the 8 useful columns of the second-layer accumulator");
@@ -268,7 +280,6 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tc2_kernel(RolloutArgs g,
 
     if (warp == kMmaWarp) tmem_alloc<kTmemCols>(tmem_slot);
     if (tid == 0) {
-        mbar_init(bar_img, 1);
         for (int s = 0; s < kSides; ++s) {
             mbar_init(bar_a(s), 4);              // one arrival per head warp of the side
             mbar_init(bar_d2(s), kMmaWarps);     // each MMA warp commits its chunk
@@ -278,8 +289,9 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tc2_kernel(RolloutArgs g,
             mbar_init(bar_relu(s), kEpiPerItem);
         }
         mbar_fence_init();
-        tma_bulk_load(smem, image, P::kImageBytes, bar_img);
     }
+    pack_weights<A>(g.w, smem, tid);
+    fence_async_smem();          // generic-proxy writes -> visible to the tensor core's (async proxy) operand reads
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -293,7 +305,6 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tc2_kernel(RolloutArgs g,
         // ------------------------------------------------------------ MMA issuers (keep the launch allocation)
         // The whole warp runs the loop converged and one elected lane issues: the descriptors then live in
         // uniform registers (an `if (lane == 0)` branch makes ptxas wrap every UTCHMMA in a waterfall loop).
-        mbar_wait_c(bar_img, 0);
         const uint64_t w1_desc = desc_sbo(smem_u32(smem + P::kW1), P::kSbo1);
         const uint64_t w2_desc = desc_sbo(smem_u32(smem + P::kW2), 8 * kK2 * 4);
         constexpr uint32_t kIdesc1 = instr_desc(kChunk), kIdesc2 = instr_desc(kN2);
@@ -372,7 +383,6 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tc2_kernel(RolloutArgs g,
         constexpr int kCols = kChunk / 2;
         const uint32_t tmem_mine = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(half * kCols);
         const float* b1 = reinterpret_cast<const float*>(smem + P::kB1) + half * kCols;
-        if (!P::kBiasInK) mbar_wait_c(bar_img, 0);
         const uint32_t n_items = (uint32_t)(my_pairs * g.T * kSides * kChunks);
         int slot = parity, rb = parity, c = parity;      // i % 3, i % 6, i % 4 of item i = parity, parity + kEpiStride, ...
         uint32_t par = 0;                                // (i / 6) & 1
@@ -454,7 +464,6 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tc2_kernel(RolloutArgs g,
         const uint32_t my_d2 = tmem_lane + d2_col(side), my_obs = tmem_lane + obs_col(side);
         float* s_obs = reinterpret_cast<float*>(smem + P::kObs) + (side * kTileM + hw * 32) * KIN;   // this warp's 32 rows
         uint32_t* s_cand = reinterpret_cast<uint32_t*>(smem + P::kCand) + side * A * P::kCandWords * kTileM + lane_g;
-        mbar_wait_c(bar_img, 0);
         const float b2v = reinterpret_cast<const float*>(smem + P::kB2)[0];
         float b2p[A];
 #pragma unroll
@@ -626,10 +635,8 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tc2_kernel(RolloutArgs g,
 }
 
 template <int A, int C>
-static int launch(const RolloutArgs& g, uint8_t* workspace, cudaStream_t st) {
+static int launch(const RolloutArgs& g, cudaStream_t st) {
     using P = Plan<A>;
-    pack_weights_kernel<A><<<32, 256, 0, st>>>(g.w, workspace);
-    RNAD_CHECK_LAUNCH("pack_weights_kernel");
     // One CTA per SM owns all 512 TMEM columns: ask for more than half of the shared memory so that a second
     // CTA can never become resident and spin inside tcgen05.alloc.
     size_t smem = P::kBytes;
@@ -645,7 +652,7 @@ static int launch(const RolloutArgs& g, uint8_t* workspace, cudaStream_t st) {
     const int64_t tiles = (g.B + kTileM - 1) / kTileM;
     int64_t blocks = (tiles + kSides - 1) / kSides;
     if (blocks > sm_count()) blocks = sm_count();
-    rollout_tc2_kernel<A, C><<<(int)blocks, kThreads, smem, st>>>(g, workspace);
+    rollout_tc2_kernel<A, C><<<(int)blocks, kThreads, smem, st>>>(g);
     RNAD_CHECK_LAUNCH("rollout_tc2_kernel");
     return RNAD_OK;
 }
@@ -661,12 +668,8 @@ extern "C" __attribute__((visibility("default"))) int rnad_debug_trace(long long
 bool rollout_tc2_supported(int A, int width, int C) { return rollout_tc_supported(A, width) && C >= 1 && C <= 4; }
 
 int64_t rollout_tc2_workspace_bytes(int A) {
-    switch (A) {
-        case 2: return tc2::Plan<2>::kImageBytes;
-        case 3: return tc2::Plan<3>::kImageBytes;
-        case 4: return tc2::Plan<4>::kImageBytes;
-    }
-    return 0;
+    (void)A;
+    return 0;   // the weight image is built in shared memory by the kernel itself
 }
 
 int rollout_tc2(const RolloutArgs& g, void* workspace, cudaStream_t st) {
@@ -675,12 +678,9 @@ int rollout_tc2(const RolloutArgs& g, void* workspace, cudaStream_t st) {
                   "(got width %d, max_actions %d, max_transitions %d)", g.w.width, g.A, g.C);
         return RNAD_EUNSUPPORTED;
     }
-    if (workspace == nullptr || (reinterpret_cast<uintptr_t>(workspace) & 15) != 0) {
-        set_error("rnad_rollout(tf32x2): needs a 16-byte aligned workspace of rnad_rollout_workspace_bytes()");
-        return RNAD_EINVAL;
-    }
+    (void)workspace;
 #define RNAD_TC2_CASE(a, c) \
-    if (g.A == a && g.C == c) return tc2::launch<a, c>(g, (uint8_t*)workspace, st);
+    if (g.A == a && g.C == c) return tc2::launch<a, c>(g, st);
     RNAD_TC2_CASE(2, 1) RNAD_TC2_CASE(2, 2) RNAD_TC2_CASE(2, 3) RNAD_TC2_CASE(2, 4)
     RNAD_TC2_CASE(3, 1) RNAD_TC2_CASE(3, 2) RNAD_TC2_CASE(3, 3) RNAD_TC2_CASE(3, 4)
     RNAD_TC2_CASE(4, 1) RNAD_TC2_CASE(4, 2) RNAD_TC2_CASE(4, 3) RNAD_TC2_CASE(4, 4)

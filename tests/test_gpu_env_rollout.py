@@ -342,3 +342,27 @@ def test_buffer_and_collate(golden):
     assert one.sample(64) is eps[0]
     sub = eps[0].sample(10)
     assert sub.policy.shape == (eps[0].t_eff + 1, 10, tree.max_actions)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "tf32", "tf32x2"])
+def test_rollout_with_weights_that_are_views_of_a_flat_buffer(golden, precision):
+    """nn.Linear tensors are only 4-byte aligned when they view one flat parameter buffer (bench.py's e2e path)."""
+    from environment.episode import Episodes
+
+    name, g = golden
+    tree = tree_from_golden(g, DEV)
+    net, _ = wide_net(tree.max_actions, 13, DEV)
+    flat = torch.empty(sum(p.numel() for p in net.parameters()) + 1, device=DEV)
+    offset = 1                                               # odd word offset: nothing is 8- or 16-byte aligned
+    with torch.no_grad():
+        for p in net.parameters():
+            view = flat[offset: offset + p.numel()].view_as(p)
+            view.copy_(p)
+            p.data = view
+            offset += p.numel()
+    w = {k: v.detach().cpu().clone() for k, v in net.state_dict().items()}
+    net.device = torch.device(DEV)
+    torch.manual_seed(5)
+    ep = Episodes(tree, 700)
+    ep.generate(net, precision=precision)
+    check_rollout_against_oracle(ep, tables_of(g), w, seed=ep.states.seed, tol=TOL[precision], precision=precision)
