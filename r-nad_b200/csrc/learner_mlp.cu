@@ -881,13 +881,27 @@ __global__ void __launch_bounds__(kBwdTcThreads, 2) learner_bwd_tc_kernel(const 
     if (warp == 0) tmem_dealloc<256>(tmem_base);
 }
 
+// Sum of the per-CTA partial gradients in a FIXED order (deterministic): eight lanes per parameter take the partials
+// p = lane, lane + 8, ... (eight loads in flight per thread as well) and meet in a shuffle tree.
 __global__ void reduce_partials_kernel(const float* __restrict__ partials, int n_parts, int n_params,
                                        float* __restrict__ flat_grad) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_params) return;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = t >> 3, sub = t & 7;
     float acc = 0.f;
-    for (int p = 0; p < n_parts; ++p) acc += partials[(int64_t)p * n_params + i];
-    flat_grad[i] = acc;
+    if (i < n_params) {
+        float a0 = 0.f, a1 = 0.f;
+        int p = sub;
+        for (; p + 8 < n_parts; p += 16) {
+            a0 += partials[(int64_t)p * n_params + i];
+            a1 += partials[(int64_t)(p + 8) * n_params + i];
+        }
+        if (p < n_parts) a0 += partials[(int64_t)p * n_params + i];
+        acc = a0 + a1;
+    }
+    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+    if (i < n_params && sub == 0) flat_grad[i] = acc;
 }
 
 constexpr int kMaxBwdCtas = 160;
@@ -960,7 +974,7 @@ int launch_backward(const float* obs, int64_t N, const rnad_mlp_weights& w, cons
         learner_bwd_tc_kernel<A><<<2 * (int)blocks, kBwdTcThreads, smem, st>>>(obs, N, image, d_logit, d_v, partials);
         RNAD_CHECK_LAUNCH("learner_bwd_tc_kernel");
     }
-    reduce_partials_kernel<<<(P::kParams + 255) / 256, 256, 0, st>>>(partials, (int)blocks, P::kParams, flat_grad);
+    reduce_partials_kernel<<<(P::kParams * 8 + 255) / 256, 256, 0, st>>>(partials, (int)blocks, P::kParams, flat_grad);
     RNAD_CHECK_LAUNCH("reduce_partials_kernel");
     return RNAD_OK;
 }
