@@ -11,8 +11,10 @@
 //                           A chunk is 128 hidden units of [value trunk | policy trunk]:
 //                             MMA1  D[128 x 128]  = obs[128 x KP] (TMEM) x W1_c^T (smem)      kind::tf32, 3 slots
 //                             MMA2  D2[128 x 16] += relu(D)[128 x 128] (TMEM) x W2_c^T (smem)
-//                           both with the A operand in tensor memory; column 0 of D2 is the
-//                           value, columns 1..A the logits.
+//                           both with the A operand in tensor memory.  The policy trunk's chunks come
+//                           first and have their own accumulator (logits in columns 1..A): the heads
+//                           start on them while the value trunk (value in column 0 of its own
+//                           accumulator) is still in the ring.
 //   warps 8..15             epilogue of MMA1: tcgen05.ld, relu (the bias rides in K as a
 //                           constant-1 input column where K has padding, else one FADD),
 //                           tcgen05.st back in place, arrive on the slot's mbarrier.  One
@@ -69,9 +71,14 @@ constexpr int kTmemCols = 512;
 constexpr int kN2 = 16;                          // N of the second-layer MMA (smallest legal at M = 128)
 constexpr int kK2 = 2 * kHidden;                 // its K: value trunk | policy trunk
 
-// per side: 16 columns of second-layer accumulators (value, logits), then the observations
-__host__ __device__ constexpr int d2_col(int side) { return kSideCol + 64 * side; }
-__host__ __device__ constexpr int obs_col(int side) { return kSideCol + 64 * side + 16; }
+// per side: the policy trunk's second-layer accumulator (logits in columns 1..A), the value trunk's (value in column
+// 0), then the observations
+__host__ __device__ constexpr int d2p_col(int side) { return kSideCol + 64 * side; }
+__host__ __device__ constexpr int d2v_col(int side) { return kSideCol + 64 * side + 16; }
+__host__ __device__ constexpr int obs_col(int side) { return kSideCol + 64 * side + 32; }
+// Chunk order within a half-move: the POLICY trunk first (c = 0, 1), the value trunk after it (c = 2, 3).  The next
+// observation only needs the sampled action, so the heads work on it while the value chunks are still in the ring.
+__host__ __device__ constexpr int chunk_hidden(int c) { return c < 2 ? kHidden + c * kChunk : (c - 2) * kChunk; }
 
 template <int A>
 struct Plan {
@@ -88,7 +95,7 @@ struct Plan {
     static constexpr int kObs = kImageBytes;                         // fp32 observation staging, [side][128 x KIN]
     static constexpr int kCand = kObs + kSides * kTileM * KIN * 4;   // transition candidates, [side][A][kCandWords][128]
     static constexpr int kBar = kCand + kSides * A * kCandWords * kTileM * 4;
-    static constexpr int kNumBars = 1 + kSides + 4 * kSlots + kSides;   // image, obs-ready[2], d1[6], relu[6], d2[2]
+    static constexpr int kNumBars = 1 + kSides + 4 * kSlots + 3 * kSides;   // (unused), obs-ready[2], d1[6], relu[6], logits[2], value[2], value-free[2]
     static constexpr int kTmem = kBar + 8 * kNumBars;
     static constexpr int kBytes = kTmem + 16;
     // the second 8-row group of the W2 operand is read 16 KB behind the first: it must stay inside the allocation
@@ -275,14 +282,18 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tc2_kernel(RolloutArgs g)
     // completion of item i - 2 kSlots while item i - kSlots is still in flight.
     auto bar_d1 = [&](int k) { return bar0 + 8 + 8 * kSides + 8 * k; };
     auto bar_relu = [&](int k) { return bar0 + 8 + 8 * kSides + 8 * (2 * kSlots + k); };
-    auto bar_d2 = [&](int side) { return bar0 + 8 + 8 * kSides + 32 * kSlots + 8 * side; };  // value / logits complete
+    auto bar_d2p = [&](int side) { return bar0 + 8 + 8 * kSides + 32 * kSlots + 8 * side; };                // logits complete
+    auto bar_d2v = [&](int side) { return bar0 + 8 + 8 * kSides + 32 * kSlots + 8 * (kSides + side); };     // value complete
+    auto bar_vfree = [&](int side) { return bar0 + 8 + 8 * kSides + 32 * kSlots + 8 * (2 * kSides + side); };   // value read, cleared
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + P::kTmem);
 
     if (warp == kMmaWarp) tmem_alloc<kTmemCols>(tmem_slot);
     if (tid == 0) {
         for (int s = 0; s < kSides; ++s) {
             mbar_init(bar_a(s), 4);              // one arrival per head warp of the side
-            mbar_init(bar_d2(s), kMmaWarps);     // each MMA warp commits its chunk
+            mbar_init(bar_d2p(s), 2);            // the two MMA warps of the policy chunks commit
+            mbar_init(bar_d2v(s), 2);            // the two of the value chunks
+            mbar_init(bar_vfree(s), 4);          // one arrival per head warp of the side
         }
         for (int s = 0; s < 2 * kSlots; ++s) {
             mbar_init(bar_d1(s), 1);
@@ -331,7 +342,7 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tc2_kernel(RolloutArgs g)
 #pragma unroll
             for (int s = 0; s < KP / 8; ++s)
                 mma_ts(tmem_base + slot * kChunk, tmem_base + obs_col(side) + s * 8,
-                       w1_desc + (uint64_t)((c * (kChunk / 8) * P::kSbo1 + s * 256) >> 4), kIdesc1, s > 0);
+                       w1_desc + (uint64_t)(((chunk_hidden(c) / 8) * P::kSbo1 + s * 256) >> 4), kIdesc1, s > 0);
             mma_commit(bar_d1(bar_index));
         };
         if (w == 0 && n_items > 0) {             // fill the ring: items 0 .. kSlots-1 are chunks 0 .. 2 of (side 0, half-move 0)
@@ -343,22 +354,26 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tc2_kernel(RolloutArgs g)
         // item i = w, w + 4, ...: all index arithmetic incremental (no divisions in the loop)
         int slot = w % kSlots, rb = w % (2 * kSlots);   // i % 3, i % 6
         uint32_t par = 0;                                // (i / 6) & 1
-        int side = 0;                                    // (i / 4) & 1
+        int side = 0, hm = 0;                            // (i / 4) & 1, i / 8
         const int cj = (w + kSlots) & (kChunks - 1);     // chunk index of item j = i + 3
         int side_j = (w + kSlots) >> 2, hm_j = 0;        // its side ((j / 4) & 1) and half-move (j / 8), j = w + 3 < 8
 #pragma unroll 1
         for (uint32_t i = w; i < n_items; i += kMmaWarps) {
             const bool has_j = i + kSlots < n_items;
             if (has_j) need_obs(side_j, hm_j);
+            if (w >= 2) {                // value chunks: the heads have read and cleared the previous half-move's value
+                mbar_wait_c(bar_vfree(side), (uint32_t)hm & 1u);
+                tc_fence_after();
+            }
             mbar_wait_c(bar_relu(rb), par);
             tc_fence_after();
             TRI(2, i, 0);
             if (elect_one()) {
 #pragma unroll
                 for (int s = 0; s < kChunk / 8; ++s)   // second layers: A = relu(hidden) in tensor memory
-                    mma_ts(tmem_base + d2_col(side), tmem_base + slot * kChunk + s * 8,
-                           w2_desc + (uint64_t)(((w * (kChunk / 8) + s) * 256) >> 4), kIdesc2, true);
-                mma_commit(bar_d2(side));
+                    mma_ts(tmem_base + (w < 2 ? d2p_col(side) : d2v_col(side)), tmem_base + slot * kChunk + s * 8,
+                           w2_desc + (uint64_t)(((chunk_hidden(w) / 8 + s) * 256) >> 4), kIdesc2, true);
+                mma_commit(w < 2 ? bar_d2p(side) : bar_d2v(side));
                 if (has_j) mma1(cj, side_j, slot, rb >= kSlots ? rb - kSlots : rb + kSlots);   // item i + 3, into the slot just read
             }
             __syncwarp();
@@ -371,6 +386,7 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tc2_kernel(RolloutArgs g)
                 par ^= 1u;
             }
             side ^= 1;
+            if (side == 0) ++hm;
             side_j ^= 1;
             if (side_j == 0) ++hm_j;             // j / 8 advances whenever j / 4 becomes even
         }
@@ -402,7 +418,7 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tc2_kernel(RolloutArgs g)
                 for (int q = 0; q < kCols / 32; ++q) tmem_ld32p(taddr + q * 32, r + q * 32);
                 tmem_ld_wait();
                 if (!P::kBiasInK) {
-                    const float4* bias = reinterpret_cast<const float4*>(b1 + c * kChunk + hh * kCols);
+                    const float4* bias = reinterpret_cast<const float4*>(b1 + chunk_hidden(c) + hh * kCols);
 #pragma unroll
                     for (int k = 0; k < kCols / 4; ++k) {
                         const float4 bb = bias[k];
@@ -424,7 +440,7 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tc2_kernel(RolloutArgs g)
                     tmem_ld32p(taddr + q * 32, r);
                     tmem_ld_wait();
                     if (!P::kBiasInK) {
-                        const float4* bias = reinterpret_cast<const float4*>(b1 + c * kChunk + q * 32);
+                        const float4* bias = reinterpret_cast<const float4*>(b1 + chunk_hidden(c) + q * 32);
 #pragma unroll
                         for (int k = 0; k < 8; ++k) {
                             const float4 bb = bias[k];
@@ -444,6 +460,7 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tc2_kernel(RolloutArgs g)
             __syncwarp();
             if ((tid & 31) == 0) mbar_arrive(bar_relu(rb));
             if (e == 0) TRI(2, i, 4);
+            TRI(3, i, e);
             // i += kEpiStride
             slot = slot + kEpiStride >= kSlots ? slot + kEpiStride - kSlots : slot + kEpiStride;
             rb += kEpiStride;
@@ -461,14 +478,14 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tc2_kernel(RolloutArgs g)
         const int lane = tid & 31;
         const int hw = warp & 3;                              // head warp of the side == lane quadrant
         const uint32_t tmem_lane = tmem_base + ((uint32_t)(hw * 32) << 16);
-        const uint32_t my_d2 = tmem_lane + d2_col(side), my_obs = tmem_lane + obs_col(side);
+        const uint32_t my_d2p = tmem_lane + d2p_col(side), my_d2v = tmem_lane + d2v_col(side), my_obs = tmem_lane + obs_col(side);
         float* s_obs = reinterpret_cast<float*>(smem + P::kObs) + (side * kTileM + hw * 32) * KIN;   // this warp's 32 rows
         uint32_t* s_cand = reinterpret_cast<uint32_t*>(smem + P::kCand) + side * A * P::kCandWords * kTileM + lane_g;
         const float b2v = reinterpret_cast<const float*>(smem + P::kB2)[0];
         float b2p[A];
 #pragma unroll
         for (int a = 0; a < A; ++a) b2p[a] = reinterpret_cast<const float*>(smem + P::kB2)[1 + a];
-        const uint32_t my_bar_a = bar_a(side), my_bar_d2 = bar_d2(side);
+        const uint32_t my_bar_a = bar_a(side), my_bar_d2p = bar_d2p(side), my_bar_d2v = bar_d2v(side), my_bar_vfree = bar_vfree(side);
 
         uint32_t ph_d2 = 0;
         int last_valid = -1;
@@ -493,7 +510,7 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tc2_kernel(RolloutArgs g)
                 tmem_ld_wait();          // this thread's read of the accumulators is complete before they are cleared
                 {
                     const uint32_t zero[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
-                    tmem_st8(my_d2, zero);   // the second-layer MMAs of the next half-move only ever accumulate
+                    tmem_st8(my_d2p, zero);  // the second-layer MMAs of the next half-move only ever accumulate
                 }
 #pragma unroll
                 for (int q = 0; q < KP / 8; ++q) {
@@ -544,22 +561,6 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tc2_kernel(RolloutArgs g)
                 return u;
             };
 
-#ifdef RNAD_TC2_NOHEAD
-            // experiment: heads only hand the barriers around (the output is garbage)
-            for (int t = -1; t < g.T; ++t) {
-                if (t >= 0) {
-                    mbar_wait_c(my_bar_d2, ph_d2);
-                    ph_d2 ^= 1u;
-                    tc_fence_after();
-                }
-                if (t + 1 < g.T) {
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(my_bar_a);
-                }
-            }
-            continue;
-#endif
             Uniforms2 u;
             u.action = u.chance = 0.f;
             // half-move -1 is the set-up of the tile: it only publishes the root observation
@@ -567,25 +568,43 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tc2_kernel(RolloutArgs g)
             for (int t = -1; t < g.T; ++t) {
                 const int turn = t & 1;
                 const bool more = t + 1 < g.T;
+                // the value accumulator: read (t >= 0), cleared, handed back to the MMA warps of the value chunks
+                auto take_value = [&]() {
+                    float v = 0.f;
+                    if (t >= 0) {
+                        mbar_wait_c(my_bar_d2v, ph_d2);        // (same parity sequence as the logits barrier)
+                        tc_fence_after();
+                        uint32_t dv[8];
+                        tmem_ld8(my_d2v, dv);
+                        tmem_ld_wait();
+                        v = __uint_as_float(dv[0]) + b2v;
+                    }
+                    const uint32_t zero[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+                    tmem_st8(my_d2v, zero);
+                    tmem_st_wait();
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(my_bar_vfree);
+                    return v;
+                };
                 if (t < 0) {
                     if (active) load_node<A>(g.ev_tab, node, n);
                     build_obs<A>(n, 0, x);
                     publish_obs();
+                    if (k == 0) take_value();   // (later pairs: cleared and handed back after the previous pair's last half-move)
                 } else {
                     if (node != 0) last_valid = max(last_valid, t);
                     const int n_legal = turn == 0 ? n.rows : n.cols;
                     // a row half-move does not move the game: the column player's observation is known beforehand
                     if (turn == 0) build_obs<A>(n, 1, x);
                     if (lane_g == 0) TR(side, t, 0);
-                    mbar_wait_c(my_bar_d2, ph_d2);
-                    ph_d2 ^= 1u;
+                    mbar_wait_c(my_bar_d2p, ph_d2);                // the logits; the value trunk is still in the ring
                     tc_fence_after();
                     if (lane_g == 0) TR(side, t, 1);
                     uint32_t d2[8];
-                    tmem_ld8(my_d2, d2);
+                    tmem_ld8(my_d2p, d2);
                     if (turn == 0 && more) publish_obs();          // critical path of a row half-move ends here
                     tmem_ld_wait();
-                    const float value = __uint_as_float(d2[0]) + b2v;
                     float logit[A];
 #pragma unroll
                     for (int a = 0; a < A; ++a) logit[a] = __uint_as_float(d2[1 + a]) + b2p[a];
@@ -613,6 +632,8 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tc2_kernel(RolloutArgs g)
                     }
                     if (lane_g == 0) TR(side, t, 3);
                     // ---- from here on off the critical path: the tensor core and the epilogue warps are busy
+                    const float value = take_value();
+                    ph_d2 ^= 1u;
                     if (active)
                         write_record<A>(g.out, (int64_t)t * g.B + b, node_now, turn, n_legal, policy, action, value, reward);
                 }

@@ -34,3 +34,7 @@ print("item side c | MMA warp: relu seen  issued | epilogue warp 0: d1 seen  rel
 for j in range(40):
     i = j + 16
     print(f"{i:4d} {(i//4)%2:4d} {i%4} | {mma[j,0]-t0:8d} {mma[j,2]-t0:8d} | {mma[j,3]-t0:8d} {mma[j,4]-t0:8d}")
+epi = buf[3].reshape(-1)[:320].reshape(-1, 8)
+print("item | relu written back by epilogue warp 0..7 (absolute cycles) | relu seen by the MMA warp")
+for j in range(24):
+    print(f"{j+16:4d} | " + " ".join(f"{x-t0:7d}" for x in epi[j]) + f" | {mma[j,0]-t0:8d}")
