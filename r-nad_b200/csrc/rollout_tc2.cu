@@ -32,6 +32,7 @@
 // Everything is ordered by mbarriers; no CTA-wide barrier inside the rollout.  Every
 // CTA lays the weights out in operand order in its own shared memory at start-up (the
 // whole launch is this one kernel).  Reference: environment/episode.py:175-230, nn/net.py:37-51.
+#include <atomic>
 #include "game.cuh"
 #include "rollout.cuh"
 #include "tc_common.cuh"
@@ -97,7 +98,8 @@ struct Plan {
     static constexpr int kBar = kCand + kSides * A * kCandWords * kTileM * 4;
     static constexpr int kNumBars = 1 + kSides + 4 * kSlots + 3 * kSides;   // (unused), obs-ready[2], d1[6], relu[6], logits[2], value[2], value-free[2]
     static constexpr int kTmem = kBar + 8 * kNumBars;
-    static constexpr int kBytes = kTmem + 16;
+    static constexpr int kRoot = kTmem + 16;                         // the root's node record (every game starts there)
+    static constexpr int kBytes = kRoot + round_up(ev_stride_of(A) * 4, 16);
     // the second 8-row group of the W2 operand is read 16 KB behind the first: it must stay inside the allocation
     static_assert(kBytes >= kW2 + 2 * 8 * kK2 * 4, "W2 operand alias runs past the allocation");
     static_assert(kBytes <= 227 * 1024, "shared memory plan does not fit");
@@ -122,7 +124,7 @@ static_assert(kHeadWarps % 4 == 0 && kEpiWarps % 4 == 0, "roles must fill whole 
 
 #ifdef RNAD_TRACE
 // development aid: cycle stamps of CTA 0's first tile pair.  [role][half-move][event]
-__device__ long long g_trace[4][16][24];
+__device__ long long g_trace[5][16][24];
 #define TR(role, t, ev) do { if (blockIdx.x == 0 && first_pair && (t) < 16) g_trace[role][t][ev] = clock64(); } while (0)
 // stream items: flat [role 2 = MMA warp, role 3 = epilogue warp 0][2 * item + which]
 #define TRI(role, item, which) do { if (blockIdx.x == 0 && (item) >= 16 && (item) < 16 + 40) (&g_trace[role][0][0])[8 * ((item) - 16) + (which)] = clock64(); } while (0)
@@ -130,6 +132,12 @@ __device__ long long g_trace[4][16][24];
 #define TR(role, t, ev) do { } while (0)
 #define TRI(role, item, which) do { } while (0)
 #endif
+
+// relu in place of the first-layer accumulators, split over the two arithmetic pipes of a scheduler: even hidden units
+// max(x, 0) (FMNMX, alu pipe), odd hidden units x + |x| = 2 relu(x) (FADD, fma pipe) - exactly twice the value for every
+// finite x, and pack_weights halves the second-layer weights of the odd units (a power of two: bit-identical products)
+__device__ __forceinline__ float relu_split(float x, int k) { return (k & 1) ? x + fabsf(x) : fmaxf(x, 0.f); }
+__device__ __forceinline__ float relu_split_scale(int hidden) { return (hidden & 1) ? 0.5f : 1.f; }
 
 // The weight image in MMA-operand order, written straight into the CTA's shared memory by all of its threads
 // (43 KB of fp32 nn.Linear tensors from L2 -> 66 KB of tf32 operands): no pre-kernel, no workspace.
@@ -167,7 +175,8 @@ __device__ __forceinline__ void pack_weights(const rnad_mlp_weights& w, uint8_t*
             for (int a = 0; a < A; ++a) col[1 + a] = __ldg(w.policy_fc1_w + a * kHidden + (k - kHidden));
         }
 #pragma unroll
-        for (int r = 0; r < 8; ++r) *reinterpret_cast<float*>(image + P::kW2 + operand_offset<kK2>(r, k)) = to_tf32_fast(col[r]);
+        for (int r = 0; r < 8; ++r)      // (relu_split: the epilogue hands odd hidden units over doubled)
+            *reinterpret_cast<float*>(image + P::kW2 + operand_offset<kK2>(r, k)) = to_tf32_fast(col[r]) * relu_split_scale(k);
     }
     if (thread < 8) {
         float v = 0.f;
@@ -287,6 +296,9 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tc2_kernel(RolloutArgs g)
     auto bar_vfree = [&](int side) { return bar0 + 8 + 8 * kSides + 32 * kSlots + 8 * (2 * kSides + side); };   // value read, cleared
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + P::kTmem);
 
+#ifdef RNAD_TRACE
+    if (blockIdx.x == 0 && tid == 0) g_trace[0][15][0] = clock64();
+#endif
     if (warp == kMmaWarp) tmem_alloc<kTmemCols>(tmem_slot);
     if (tid == 0) {
         for (int s = 0; s < kSides; ++s) {
@@ -301,11 +313,18 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tc2_kernel(RolloutArgs g)
         }
         mbar_fence_init();
     }
+    // every game starts at the root (node 1): its record is fetched once, underneath the weight packing
+    uint32_t root_word = 0;
+    if (tid < ev_stride_of(A)) root_word = __ldg(g.ev_tab + ev_stride_of(A) + tid);
     pack_weights<A>(g.w, smem, tid);
+    if (tid < ev_stride_of(A)) reinterpret_cast<uint32_t*>(smem + P::kRoot)[tid] = root_word;
     fence_async_smem();          // generic-proxy writes -> visible to the tensor core's (async proxy) operand reads
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+#ifdef RNAD_TRACE
+    if (blockIdx.x == 0 && tid == 0) g_trace[0][15][1] = clock64();
+#endif
     const uint32_t tmem_base = *tmem_slot;
     const int64_t num_tiles = (g.B + kTileM - 1) / kTileM;
     const int64_t num_pairs = (num_tiles + kSides - 1) / kSides;
@@ -374,10 +393,17 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tc2_kernel(RolloutArgs g)
                     mma_ts(tmem_base + (w < 2 ? d2p_col(side) : d2v_col(side)), tmem_base + slot * kChunk + s * 8,
                            w2_desc + (uint64_t)(((chunk_hidden(w) / 8 + s) * 256) >> 4), kIdesc2, true);
                 mma_commit(w < 2 ? bar_d2p(side) : bar_d2v(side));
+                TRI(2, i, 1);
                 if (has_j) mma1(cj, side_j, slot, rb >= kSlots ? rb - kSlots : rb + kSlots);   // item i + 3, into the slot just read
             }
             __syncwarp();
             TRI(2, i, 2);
+#ifdef RNAD_TRACE
+            if (has_j && blockIdx.x == 0 && i >= 16 && i < 56) {   // when do the first layers just issued complete?
+                mbar_wait_c(bar_d1((i + kSlots) % (2 * kSlots)), ((i + kSlots) / (2 * kSlots)) & 1u);
+                TRI(2, i, 5);
+            }
+#endif
             // i += 4
             slot = slot + 1 == kSlots ? 0 : slot + 1;
             rb += kMmaWarps;
@@ -400,13 +426,13 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tc2_kernel(RolloutArgs g)
         const uint32_t tmem_mine = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(half * kCols);
         const float* b1 = reinterpret_cast<const float*>(smem + P::kB1) + half * kCols;
         const uint32_t n_items = (uint32_t)(my_pairs * g.T * kSides * kChunks);
-        int slot = parity, rb = parity, c = parity;      // i % 3, i % 6, i % 4 of item i = parity, parity + kEpiStride, ...
-        uint32_t par = 0;                                // (i / 6) & 1
-#pragma unroll 1
-        for (uint32_t i = parity; i < n_items; i += kEpiStride) {
+        // one stream item: wait for its first layers, relu this warp's 32 lanes x 64 columns in place, hand it to MMA2
+        auto epi_item = [&](uint32_t i, int slot, int rb, int c, uint32_t par) {
+            (void)i;
             mbar_wait_c(bar_d1(rb), par);
             tc_fence_after();
             if (e == 0) TRI(2, i, 3);
+            TRI(4, i, e);
             const uint32_t taddr = tmem_mine + slot * kChunk;
             if (kEpiWarps == 8) {
 #pragma unroll
@@ -417,6 +443,7 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tc2_kernel(RolloutArgs g)
 #pragma unroll
                 for (int q = 0; q < kCols / 32; ++q) tmem_ld32p(taddr + q * 32, r + q * 32);
                 tmem_ld_wait();
+                if (e == 0) TRI(2, i, 6);
                 if (!P::kBiasInK) {
                     const float4* bias = reinterpret_cast<const float4*>(b1 + chunk_hidden(c) + hh * kCols);
 #pragma unroll
@@ -429,7 +456,7 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tc2_kernel(RolloutArgs g)
                     }
                 }
 #pragma unroll
-                for (int k = 0; k < kCols; ++k) r[k] = __float_as_uint(fmaxf(__uint_as_float(r[k]), 0.f));
+                for (int k = 0; k < kCols; ++k) r[k] = __float_as_uint(relu_split(__uint_as_float(r[k]), k));
 #pragma unroll
                 for (int q = 0; q < kCols / 32; ++q) tmem_st32(taddr + q * 32, r + q * 32);
               }
@@ -451,24 +478,45 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tc2_kernel(RolloutArgs g)
                         }
                     }
 #pragma unroll
-                    for (int k = 0; k < 32; ++k) r[k] = __float_as_uint(fmaxf(__uint_as_float(r[k]), 0.f));
+                    for (int k = 0; k < 32; ++k) r[k] = __float_as_uint(relu_split(__uint_as_float(r[k]), k));
                     tmem_st32(taddr + q * 32, r);
                 }
             }
             tmem_st_wait();
+            if (e == 0) TRI(2, i, 7);
             tc_fence_before();
             __syncwarp();
             if ((tid & 31) == 0) mbar_arrive(bar_relu(rb));
             if (e == 0) TRI(2, i, 4);
             TRI(3, i, e);
-            // i += kEpiStride
-            slot = slot + kEpiStride >= kSlots ? slot + kEpiStride - kSlots : slot + kEpiStride;
-            rb += kEpiStride;
-            if (rb >= 2 * kSlots) {
-                rb -= 2 * kSlots;
-                par ^= 1u;
+        };
+        if constexpr (kEpiWarps == 8 && !kEpiWide) {
+            // every warp takes every item: unrolled over the period of the slot ring (3), the barrier ring (6) and the
+            // chunks of a half-move (4), so that tensor-memory addresses, barrier addresses and parities are immediates -
+            // what an epilogue warp does between two items is on the critical path of the stream
+            constexpr int kPeriod = 12;
+#pragma unroll 1
+            for (uint32_t i0 = 0; i0 < n_items; i0 += kPeriod) {
+#pragma unroll
+                for (int u = 0; u < kPeriod; ++u) {
+                    if (u > 0 && (u & 3) == 0 && i0 + u >= n_items) break;    // (n_items is a multiple of 8)
+                    epi_item(i0 + u, u % kSlots, u % (2 * kSlots), u % kChunks, (uint32_t)(u / (2 * kSlots)) & 1u);
+                }
             }
-            c = (c + kEpiStride) & (kChunks - 1);
+        } else {
+            int slot = parity, rb = parity, c = parity;      // i % 3, i % 6, i % 4 of item i = parity, parity + kEpiStride, ...
+            uint32_t par = 0;                                // (i / 6) & 1
+#pragma unroll 1
+            for (uint32_t i = parity; i < n_items; i += kEpiStride) {
+                epi_item(i, slot, rb, c, par);
+                slot = slot + kEpiStride >= kSlots ? slot + kEpiStride - kSlots : slot + kEpiStride;
+                rb += kEpiStride;
+                if (rb >= 2 * kSlots) {
+                    rb -= 2 * kSlots;
+                    par ^= 1u;
+                }
+                c = (c + kEpiStride) & (kChunks - 1);
+            }
         }
     } else {
         // ------------------------------------------------------------ heads: one thread per game
@@ -588,7 +636,13 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tc2_kernel(RolloutArgs g)
                     return v;
                 };
                 if (t < 0) {
-                    if (active) load_node<A>(g.ev_tab, node, n);
+                    if (active) {
+                        const uint32_t* rw = reinterpret_cast<const uint32_t*>(smem + P::kRoot);
+#pragma unroll
+                        for (int i = 0; i < A * A; ++i) n.ev[i] = __uint_as_float(rw[i]);
+                        n.rows = rw[A * A] & 0xff;
+                        n.cols = (rw[A * A] >> 8) & 0xff;
+                    }
                     build_obs<A>(n, 0, x);
                     publish_obs();
                     if (k == 0) take_value();   // (later pairs: cleared and handed back after the previous pair's last half-move)
@@ -652,6 +706,9 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tc2_kernel(RolloutArgs g)
 
     tc_fence_before();
     __syncthreads();
+#ifdef RNAD_TRACE
+    if (blockIdx.x == 0 && tid == 0) g_trace[0][15][2] = clock64();
+#endif
     if (warp == kMmaWarp) tmem_dealloc<kTmemCols>(tmem_base);
 }
 
@@ -663,13 +720,21 @@ static int launch(const RolloutArgs& g, cudaStream_t st) {
     size_t smem = P::kBytes;
     const size_t floor_one_per_sm = 116 * 1024;
     if (smem < floor_one_per_sm) smem = floor_one_per_sm;
-    int rc = check_cuda(cudaFuncSetAttribute(rollout_tc2_kernel<A, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
+    // function attributes are per device: set once per device and instantiation (a few microseconds of host time each)
+    static std::atomic<int> configured_device{-1};
+    int device = 0;
+    int rc = check_cuda(cudaGetDevice(&device), "cudaGetDevice");
+    if (rc) return rc;
+    if (configured_device.load(std::memory_order_acquire) != device) {
+        rc = check_cuda(cudaFuncSetAttribute(rollout_tc2_kernel<A, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
                         "cudaFuncSetAttribute(rollout_tc2, smem)");
-    if (rc) return rc;
-    rc = check_cuda(cudaFuncSetAttribute(rollout_tc2_kernel<A, C>, cudaFuncAttributePreferredSharedMemoryCarveout,
-                                         cudaSharedmemCarveoutMaxShared),
-                    "cudaFuncSetAttribute(rollout_tc2, carveout)");
-    if (rc) return rc;
+        if (rc) return rc;
+        rc = check_cuda(cudaFuncSetAttribute(rollout_tc2_kernel<A, C>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                             cudaSharedmemCarveoutMaxShared),
+                        "cudaFuncSetAttribute(rollout_tc2, carveout)");
+        if (rc) return rc;
+        configured_device.store(device, std::memory_order_release);
+    }
     const int64_t tiles = (g.B + kTileM - 1) / kTileM;
     int64_t blocks = (tiles + kSides - 1) / kSides;
     if (blocks > sm_count()) blocks = sm_count();
