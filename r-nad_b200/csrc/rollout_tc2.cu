@@ -553,9 +553,20 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tc2_kernel(RolloutArgs g)
             n.rows = n.cols = 1;
             float x[KIN];
 
-            // observation words of half-move t in tf32 (A operand of the first layers) -> tensor memory; critical path
-            auto publish_obs = [&]() {
+            // observation words of half-move t in tf32 (A operand of the first layers) -> tensor memory; critical path.
+            // `prev_t` >= 0: the heads run ahead of the value trunk of half-move prev_t (they only waited for its logits),
+            // whose first layers still READ the observation in place: wait for the first-layer commits of its two value
+            // chunks (stream items i2, i2 + 1) before overwriting.  Normally complete long before - those MMAs are
+            // issued ahead of the second layers of the policy chunks - but nothing else orders them.  (Parity: every
+            // earlier item on these barriers is complete once the logits are, and the next one needs this publication.)
+            auto publish_obs = [&](int prev_t) {
                 tmem_ld_wait();          // this thread's read of the accumulators is complete before they are cleared
+                if (prev_t >= 0) {
+                    const uint32_t i2 = (((uint32_t)(k * g.T + prev_t)) * kSides + side) * kChunks + 2;
+                    mbar_wait_c(bar_d1(i2 % (2 * kSlots)), (i2 / (2 * kSlots)) & 1u);
+                    mbar_wait_c(bar_d1((i2 + 1) % (2 * kSlots)), ((i2 + 1) / (2 * kSlots)) & 1u);
+                    tc_fence_after();
+                }
                 {
                     const uint32_t zero[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
                     tmem_st8(my_d2p, zero);  // the second-layer MMAs of the next half-move only ever accumulate
@@ -644,7 +655,7 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tc2_kernel(RolloutArgs g)
                         n.cols = (rw[A * A] >> 8) & 0xff;
                     }
                     build_obs<A>(n, 0, x);
-                    publish_obs();
+                    publish_obs(-1);
                     if (k == 0) take_value();   // (later pairs: cleared and handed back after the previous pair's last half-move)
                 } else {
                     if (node != 0) last_valid = max(last_valid, t);
@@ -657,7 +668,7 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tc2_kernel(RolloutArgs g)
                     if (lane_g == 0) TR(side, t, 1);
                     uint32_t d2[8];
                     tmem_ld8(my_d2p, d2);
-                    if (turn == 0 && more) publish_obs();          // critical path of a row half-move ends here
+                    if (turn == 0 && more) publish_obs(t);         // critical path of a row half-move ends here
                     tmem_ld_wait();
                     float logit[A];
 #pragma unroll
@@ -681,7 +692,7 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tc2_kernel(RolloutArgs g)
                         reward = __uint_as_float(cand[kTileM]);
                         if (more) {
                             build_obs<A>(n, 0, x);
-                            publish_obs();                         // critical path of a column half-move ends here
+                            publish_obs(t);                        // critical path of a column half-move ends here
                         }
                     }
                     if (lane_g == 0) TR(side, t, 3);

@@ -71,3 +71,32 @@ def episodes_from_golden(g, tree, device="cpu"):
     ep.q_estimates = torch.zeros_like(ep.policy)
     ep.v_estimates = torch.zeros_like(ep.rewards)
     return ep
+
+
+def gross_rollout_errors(ep, net, tol=2e-2):
+    """Recorded observations through a plain fp32 torch forward on the episodes' device: boolean (T, B) masks of the valid
+    slots whose recorded value / policy is off by more than `tol`.  The tensor-core engines differ from fp32 by < 1e-2;
+    a mis-ordered tensor-memory access (an ordering race in the fused kernel) by much more.  Returns the fp32 value too."""
+    import torch
+
+    T = ep.t_eff + 1
+    B = ep.indices.shape[1]
+    a = ep.policy.shape[-1]
+    obs = ep.observations[:T].reshape(T * B, -1)
+    allow = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        with torch.no_grad():
+            hv = torch.relu(obs @ net.value_fc0.weight.T + net.value_fc0.bias)
+            val = (hv @ net.value_fc1.weight.T + net.value_fc1.bias).reshape(T, B)
+            hp = torch.relu(obs @ net.policy_fc0.weight.T + net.policy_fc0.bias)
+            logit = (hp @ net.policy_fc1.weight.T + net.policy_fc1.bias).reshape(T, B, a)
+            mask = ep.masks[:T] > 0
+            e = torch.where(mask, torch.exp(logit - logit.max(-1, keepdim=True).values), torch.zeros_like(logit))
+            pol = e / e.sum(-1, keepdim=True).clamp_min(1e-12)
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = allow
+    valid = ep.indices[:T] != 0
+    bad_v = ((ep.values[:T] - val).abs() > tol) & valid
+    bad_p = ((ep.policy[:T] - pol).abs().max(-1).values > tol) & valid
+    return bad_v, bad_p, val

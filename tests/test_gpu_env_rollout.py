@@ -12,7 +12,7 @@ import pytest
 import torch
 
 from oracle import rnad_oracle as orc
-from helpers import close, episodes_of, mlp_from_golden, t, tables_of, tree_from_golden, weights_of
+from helpers import close, episodes_of, gross_rollout_errors, mlp_from_golden, t, tables_of, tree_from_golden, weights_of
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
@@ -250,6 +250,26 @@ def test_fused_rollout_width256_vs_oracle(golden, precision, batch):
     ep.generate(net, precision=precision)
     assert ep.precision == precision
     check_rollout_against_oracle(ep, tables_of(g), w, seed=ep.states.seed, tol=TOL[precision], precision=precision)
+
+
+@pytest.mark.parametrize("precision", ["tf32", "tf32x2"])
+def test_fused_rollout_repeated_launches_have_no_ordering_race(golden, precision):
+    """The warp roles of the fused kernel are ordered by mbarriers only; an ordering hole shows up as a rare, gross error
+    in whole lane quadrants (seen once: the heads overwrote the observation the value trunk's MMAs were still reading,
+    one launch in ten at A = 4).  Many launches, multi-pair batch with a ragged last tile, fp32 torch forward as checker."""
+    from environment.episode import Episodes
+
+    name, g = golden
+    tree = tree_from_golden(g, DEV)
+    net, _ = wide_net(tree.max_actions, 7, DEV)
+    net.device = torch.device(DEV)
+    for it in range(60):
+        torch.manual_seed(1000 + it)
+        ep = Episodes(tree, 40000)
+        ep.generate(net, precision=precision)
+        bad_v, bad_p, _ = gross_rollout_errors(ep, net)
+        assert int(bad_v.sum()) == 0 and int(bad_p.sum()) == 0, (
+            f"launch {it}: {int(bad_v.sum())} wrong values, {int(bad_p.sum())} wrong policies")
 
 
 def test_default_precision_is_tensor_core_when_supported(golden):
