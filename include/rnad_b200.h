@@ -40,9 +40,8 @@ extern "C" {
 #define RNAD_PREC_FP32 0 /* FFMA on the CUDA cores, fp32 throughout (validation build) */
 #define RNAD_PREC_TF32 1 /* first layer on tcgen05 tensor cores, kind::tf32, fp32 accumulate in TMEM */
 #define RNAD_PREC_TF32X2 2 /* both layers on tcgen05 (kind::tf32); the second reads relu(hidden) from tensor memory */
-/* Reproducibility for one seed: FP32 and TF32 give the same bits on every launch.  TF32X2 adds the second-layer partial
- * sums of two hidden-unit chunks into one accumulator in issue order: recorded values / policies agree across launches
- * to fp32 accumulation order (measured <= 1.4e-6 absolute), every sampling decision is a function of the recorded policy. */
+/* Reproducibility: for one seed, tables and weights every engine writes the same bits on every launch (no result depends
+ * on the order in which warps or CTAs were scheduled). */
 
 #define RNAD_MAX_ACTIONS 8
 #define RNAD_MAX_TRANSITIONS 8

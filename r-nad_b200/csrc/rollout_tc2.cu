@@ -89,8 +89,8 @@ struct Plan {
     static constexpr int kCandWords = A * A + 3;                     // child, reward, ev[A*A], rows|cols
     static constexpr int kSbo1 = (KP / 4) * 128;                     // bytes between 8-row groups of a [rows x KP] operand
     static constexpr int kW1 = 0;                                    // [512 x KP] tf32
-    static constexpr int kW2 = kW1 + 2 * kHidden * KP * 4;           // rows 0..7 of [16 x 512] tf32 (rows 8..15 alias what follows)
-    static constexpr int kB1 = kW2 + 8 * kK2 * 4;                    // first-layer biases, 512 f32 (used when !kBiasInK)
+    static constexpr int kW2 = kW1 + 2 * kHidden * KP * 4;           // [16 x 512] tf32: rows 0..7 serve the first chunk of a trunk, 8..15 the second
+    static constexpr int kB1 = kW2 + kN2 * kK2 * 4;                  // first-layer biases, 512 f32 (used when !kBiasInK)
     static constexpr int kB2 = kB1 + 2 * kHidden * 4;                // value bias, policy biases (8 f32)
     static constexpr int kImageBytes = kB2 + 32;
     static constexpr int kObs = kImageBytes;                         // fp32 observation staging, [side][128 x KIN]
@@ -100,8 +100,6 @@ struct Plan {
     static constexpr int kTmem = kBar + 8 * kNumBars;
     static constexpr int kRoot = kTmem + 16;                         // the root's node record (every game starts there)
     static constexpr int kBytes = kRoot + round_up(ev_stride_of(A) * 4, 16);
-    // the second 8-row group of the W2 operand is read 16 KB behind the first: it must stay inside the allocation
-    static_assert(kBytes >= kW2 + 2 * 8 * kK2 * 4, "W2 operand alias runs past the allocation");
     static_assert(kBytes <= 227 * 1024, "shared memory plan does not fit");
     static_assert(kImageBytes % 16 == 0 && kObs % 16 == 0 && kCand % 16 == 0 && kBar % 8 == 0 && (32 * KIN * 4) % 16 == 0,
                   "alignment");
@@ -162,20 +160,30 @@ __device__ __forceinline__ void pack_weights(const rnad_mlp_weights& w, uint8_t*
             *reinterpret_cast<float4*>(image + P::kW1 + operand_offset<KP>(n, 4 * q)) =
                 make_float4(to_tf32_fast(x[4 * q]), to_tf32_fast(x[4 * q + 1]), to_tf32_fast(x[4 * q + 2]), to_tf32_fast(x[4 * q + 3]));
         reinterpret_cast<float*>(image + P::kB1)[n] = bias;
-        // second layers as ONE [8 x 512] operand: row 0 = value_fc1 over the value trunk's hidden units, rows 1..A =
-        // policy_fc1 over the policy trunk's, zero elsewhere; thread k owns column k (hidden unit k of the two trunks)
+        // second layers as ONE [16 x 512] operand; thread k owns column k (hidden unit k of [value trunk | policy trunk]).
+        // Row 0 = value_fc1, rows 1..A = policy_fc1 for the hidden units of a trunk's FIRST 128-chunk, rows 8 and 9..8+A
+        // for those of its SECOND chunk, zero elsewhere: the two chunks of a trunk leave their partial sums in separate
+        // columns of the accumulator (the other chunk's MMAs add exact zeros there) and the head adds them in a fixed
+        // order - the result does not depend on the order in which the MMA warps got to issue.
         const int k = thread;
-        float col[8];
+        float col[kN2];
 #pragma unroll
-        for (int r = 0; r < 8; ++r) col[r] = 0.f;
+        for (int r = 0; r < kN2; ++r) col[r] = 0.f;
+        const int r0 = (k & kChunk) ? 8 : 0;
         if (k < kHidden) {
-            col[0] = __ldg(w.value_fc1_w + k);
+            const float wv = __ldg(w.value_fc1_w + k);
+            col[0] = r0 == 0 ? wv : 0.f;
+            col[8] = r0 == 8 ? wv : 0.f;
         } else {
 #pragma unroll
-            for (int a = 0; a < A; ++a) col[1 + a] = __ldg(w.policy_fc1_w + a * kHidden + (k - kHidden));
+            for (int a = 0; a < A; ++a) {
+                const float wp = __ldg(w.policy_fc1_w + a * kHidden + (k - kHidden));
+                col[1 + a] = r0 == 0 ? wp : 0.f;
+                col[9 + a] = r0 == 8 ? wp : 0.f;
+            }
         }
 #pragma unroll
-        for (int r = 0; r < 8; ++r)      // (relu_split: the epilogue hands odd hidden units over doubled)
+        for (int r = 0; r < kN2; ++r)    // (relu_split: the epilogue hands odd hidden units over doubled)
             *reinterpret_cast<float*>(image + P::kW2 + operand_offset<kK2>(r, k)) = to_tf32_fast(col[r]) * relu_split_scale(k);
     }
     if (thread < 8) {
@@ -342,8 +350,9 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tc2_kernel(RolloutArgs g)
         //     wait relu(i) -> MMA2(i) -> MMA1(i + kSlots) into the slot MMA2(i) has just read -> commit,
         // and MMA warp w takes the items with c == w: issuing blocks while the tensor core's queue is full and every
         // step has barrier latency around it, so several issuers keep the queue fed.  MMAs of one thread execute in
-        // issue order (that covers the slot reuse); MMA2s of different warps all ADD into the side's accumulator,
-        // which the head zeroes after reading it, so their order does not matter.
+        // issue order (that covers the slot reuse); MMA2s of different warps all ADD into the side's accumulator, each
+        // chunk's non-zero weights into its own 8 columns (pack_weights), which the head adds in a fixed order and zeroes
+        // after reading: their order does not matter, not even for the last bit.
         const int w = warp - kMmaWarp;           // == chunk index c of every item this warp issues
         const uint32_t n_items = (uint32_t)(my_pairs * g.T * kSides * kChunks);
         int seen_hm[kSides] = {-1, -1};
@@ -570,6 +579,7 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tc2_kernel(RolloutArgs g)
                 {
                     const uint32_t zero[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
                     tmem_st8(my_d2p, zero);  // the second-layer MMAs of the next half-move only ever accumulate
+                    tmem_st8(my_d2p + 8, zero);
                 }
 #pragma unroll
                 for (int q = 0; q < KP / 8; ++q) {
@@ -633,13 +643,15 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tc2_kernel(RolloutArgs g)
                     if (t >= 0) {
                         mbar_wait_c(my_bar_d2v, ph_d2);        // (same parity sequence as the logits barrier)
                         tc_fence_after();
-                        uint32_t dv[8];
+                        uint32_t dv[8], dw[8];                 // partial sums of the trunk's two chunks
                         tmem_ld8(my_d2v, dv);
+                        tmem_ld8(my_d2v + 8, dw);
                         tmem_ld_wait();
-                        v = __uint_as_float(dv[0]) + b2v;
+                        v = (__uint_as_float(dv[0]) + __uint_as_float(dw[0])) + b2v;
                     }
                     const uint32_t zero[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
                     tmem_st8(my_d2v, zero);
+                    tmem_st8(my_d2v + 8, zero);
                     tmem_st_wait();
                     tc_fence_before();
                     __syncwarp();
@@ -666,13 +678,14 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tc2_kernel(RolloutArgs g)
                     mbar_wait_c(my_bar_d2p, ph_d2);                // the logits; the value trunk is still in the ring
                     tc_fence_after();
                     if (lane_g == 0) TR(side, t, 1);
-                    uint32_t d2[8];
+                    uint32_t d2[8], d3[8];                         // partial sums of the policy trunk's two chunks
                     tmem_ld8(my_d2p, d2);
+                    tmem_ld8(my_d2p + 8, d3);
                     if (turn == 0 && more) publish_obs(t);         // critical path of a row half-move ends here
                     tmem_ld_wait();
                     float logit[A];
 #pragma unroll
-                    for (int a = 0; a < A; ++a) logit[a] = __uint_as_float(d2[1 + a]) + b2p[a];
+                    for (int a = 0; a < A; ++a) logit[a] = (__uint_as_float(d2[1 + a]) + __uint_as_float(d3[1 + a])) + b2p[a];
                     float policy[A];
                     masked_softmax_fast<A>(logit, n_legal, policy);
                     const int action = sample_icdf(policy, A, u.action);
