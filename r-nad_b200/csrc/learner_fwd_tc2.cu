@@ -10,7 +10,7 @@
 // with two 16-column accumulators per tile: D2a = (v, logit[0..A)) of the learner, D2b = (v_target, logit_reg[0..A),
 // logit_reg_[0..A)).  Observations and accumulators are double-buffered across tiles.
 //   warps 12..15  issue the MMAs (stream item i by warp i % 4; MMA2s only ever ADD into accumulators the output
-//                 warps cleared, so their order across warps is free)
+//                 warps cleared, each half of a trunk into its own columns, so their order across warps is free)
 //   warps 4..11   relu epilogue in tensor memory (bias via the constant-1 input column, else one FADD)
 //   warps 0..3    one thread per row: observation -> tensor memory (tf32); one tile later the heads: masked softmax /
 //                 log-softmax (net.py:76-80) of the three logit sets, the two values, written time-major.
@@ -42,7 +42,7 @@ struct Plan {
     static constexpr int KP = round_up(KIN + (kBiasInK ? 1 : 0), 8);
     static constexpr int kSbo1 = (KP / 4) * 128;
     static constexpr int kTrunkBytes = kHidden * KP * 4;
-    static constexpr int kW2ChunkBytes = 8 * kChunk * 4;              // rows 0..7 of a [16 x 128] operand (rows 8..15 alias)
+    static constexpr int kW2ChunkBytes = 16 * kChunk * 4;             // a [16 x 128] operand: rows 0..7 used by a trunk's first half, 8..15 by its second
     static constexpr int kW1 = 0;                                     // 5 trunks [256 x KP] tf32
     static constexpr int kW2 = kW1 + kTrunks * kTrunkBytes;           // 10 chunks
     static constexpr int kB1 = kW2 + kItemsPerTile * kW2ChunkBytes;   // first-layer biases, 5 x 256 f32
@@ -83,10 +83,13 @@ __global__ void pack_image_kernel(Nets w, uint8_t* __restrict__ image) {
     for (int t = 0; t < kTrunks; ++t) {
         pack_trunk_operand<P::KIN, P::KP, P::kBiasInK>(w1[t], b1[t], image + P::kW1 + t * P::kTrunkBytes, thread, n_threads);
         for (int j = thread; j < kHidden; j += n_threads) reinterpret_cast<float*>(image + P::kB1)[t * kHidden + j] = b1[t][j];
-        // second layer: per 128-unit half an [8 x 128] K-major operand, rows = accumulator columns
-        for (int e = thread; e < 2 * 8 * kChunk; e += n_threads) {
-            const int half = e / (8 * kChunk), r = (e / kChunk) % 8, k = e % kChunk;
-            const int o = r - row0[t];
+        // second layer: per 128-unit half a [16 x 128] K-major operand, rows = accumulator columns.  The first half of a
+        // trunk uses rows row0 + o, the second rows 8 + row0 + o (zero elsewhere): the two halves leave their partial
+        // sums in separate accumulator columns, added by the output warps in a fixed order, so the result does not
+        // depend on the order in which the MMA warps got to issue (bit-reproducible).
+        for (int e = thread; e < 2 * 16 * kChunk; e += n_threads) {
+            const int half = e / (16 * kChunk), r = (e / kChunk) % 16, k = e % kChunk;
+            const int o = r - (8 * half + row0[t]);
             const float v = (o >= 0 && o < n_out[t]) ? w2[t][o * kHidden + half * kChunk + k] : 0.f;
             *reinterpret_cast<float*>(image + P::kW2 + (t * 2 + half) * P::kW2ChunkBytes + operand_offset<kChunk>(r, k)) = to_tf32(v);
         }
@@ -325,13 +328,23 @@ __global__ void __launch_bounds__(kThreads, 1) learner_fwd_tc2_kernel(const floa
                 mbar_wait_c(bar_d2(kp & 1), (uint32_t)(kp >> 1) & 1u);
                 tc_fence_after();
                 uint32_t da[8], db[8];
-                tmem_ld8(tmem_lane + kD2Col + (kp & 1) * 32, da);
-                tmem_ld8(tmem_lane + kD2Col + (kp & 1) * 32 + 16, db);
-                tmem_ld_wait();
+                {
+                    uint32_t da_hi[8], db_hi[8];     // partial sums of the second half of every trunk
+                    tmem_ld8(tmem_lane + kD2Col + (kp & 1) * 32, da);
+                    tmem_ld8(tmem_lane + kD2Col + (kp & 1) * 32 + 8, da_hi);
+                    tmem_ld8(tmem_lane + kD2Col + (kp & 1) * 32 + 16, db);
+                    tmem_ld8(tmem_lane + kD2Col + (kp & 1) * 32 + 24, db_hi);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        da[q] = __float_as_uint(__uint_as_float(da[q]) + __uint_as_float(da_hi[q]));
+                        db[q] = __float_as_uint(__uint_as_float(db[q]) + __uint_as_float(db_hi[q]));
+                    }
+                }
                 {
                     const uint32_t zero[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
-                    tmem_st8(tmem_lane + kD2Col + (kp & 1) * 32, zero);
-                    tmem_st8(tmem_lane + kD2Col + (kp & 1) * 32 + 16, zero);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) tmem_st8(tmem_lane + kD2Col + (kp & 1) * 32 + 8 * q, zero);
                     tmem_st_wait();
                 }
                 tc_fence_before();
