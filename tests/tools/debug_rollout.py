@@ -1,6 +1,6 @@
 """Development aid: where does a tf32x2 rollout differ from the tf32-aware oracle?  usage: debug_rollout.py A C depth B"""
 import os, sys
-REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REPO = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path[:0] = [os.path.join(REPO, "r-nad_b200"), REPO]
 import numpy as np, torch
 import bench

@@ -1,6 +1,6 @@
 """Development aid: how does tcgen05 kind::tf32 treat an fp32 A operand read from tensor memory - truncate or round?"""
 import os, sys
-REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REPO = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path[:0] = [os.path.join(REPO, "r-nad_b200"), REPO, os.path.join(REPO, "tests")]
 import torch
 from oracle import rnad_oracle as orc
