@@ -36,9 +36,27 @@ import threading
 import time
 
 REPO = os.path.dirname(os.path.abspath(__file__))
-for _p in (os.path.join(REPO, "r-nad_b200"), REPO):
-    if _p not in sys.path:
-        sys.path.insert(0, _p)
+REF_ROOT = os.path.join(REPO, "baseline", "_ref")
+
+
+def _impl_from_argv():
+    for i, arg in enumerate(sys.argv):
+        if arg == "--impl" and i + 1 < len(sys.argv):
+            return sys.argv[i + 1]
+        if arg.startswith("--impl="):
+            return arg.split("=", 1)[1]
+    return "native"
+
+
+# The reference's packages are called environment / nn / learn / util - and so are this repository's API mirrors.
+# The reference arm therefore runs in a process that never puts r-nad_b200/ on sys.path (it imports baseline/_ref/ref
+# instead); everything else sees this repository's package.
+REFERENCE_ARM = (_impl_from_argv() == "reference" and os.path.isfile(os.path.join(REF_ROOT, "ref", "learn", "rnad.py"))
+                 and "--emit-tree" not in sys.argv)
+if not REFERENCE_ARM:
+    for _p in (os.path.join(REPO, "r-nad_b200"), REPO):
+        if _p not in sys.path:
+            sys.path.insert(0, _p)
 
 import numpy as np  # noqa: E402
 import torch  # noqa: E402
@@ -205,7 +223,7 @@ class RolloutRunner:
             setattr(self.w, layer + "_w", lin.weight.data_ptr())
             setattr(self.w, layer + "_b", lin.bias.data_ptr())
         self.w.width = net.width
-        self.t_last = torch.full((1,), -1, dtype=torch.int32, device=dev)
+        self.stats = torch.zeros(4, dtype=torch.int32, device=dev)
         ws = int(self.L.rnad_rollout_workspace_bytes(a, net.width, self.precision))
         self.workspace = torch.empty(max(ws, 16), dtype=torch.uint8, device=dev)
         self.launches_per_step = 2 if ws else 1      # weight-image pre-kernel + rollout kernel
@@ -216,7 +234,7 @@ class RolloutRunner:
         p = self.packed
         self.seed += 1
         self.L.rnad_rollout(b.ptr(p.ev_tab), b.ptr(p.tr_tab), p.A, p.C, c.byref(self.w), self.batch, self.T,
-                            self.seed, 0, None, self.precision, c.byref(self.traj), b.ptr(self.t_last),
+                            self.seed, None, 0, None, self.precision, c.byref(self.traj), b.ptr(self.stats),
                             b.ptr(self.workspace), b.stream())
 
 
@@ -319,7 +337,7 @@ def run_native(args):
 
     # ---- value: kernel throughput, everything resident
     kernel_ms, _ = timed_steps(runner.launch, args.steps, args.warmup, flush, barrier)
-    assert int(runner.t_last.item()) == T - 1
+    assert int(runner.stats[0].item()) == T
     # one env step = one VALID (t, b) slot: all of them on a regular tree, counted on the last rollout of a ragged one
     env_steps = int((runner.out["indices"] != 0).sum().item())
     assert env_steps == batch * T or args.config == "cfg4"
@@ -444,10 +462,124 @@ def run_native(args):
 
 # ------------------------------------------------------------------------ reference arm
 
+def workload_config(config, depth, a, c, n_nodes, batch, t_max):
+    """The `config` object of the JSON line - the same in both arms (the driver compares them)."""
+    shape = "thinned ragged" if config == "cfg4" else "regular"
+    return {"workload": f"{config}: depth={depth} max_actions={a} max_transitions={c} {shape} tree ({n_nodes} nodes), "
+                        f"batch={batch} games per GPU, T={t_max} half-moves, MLP width 256, self-play rollout fused "
+                        f"with the policy/value net forward + one R-NaD learner update per batch",
+            "l2": "256 MiB buffer written between timed steps"}
+
+
+def emit_tree(args):
+    """Writes the configuration's tree tables (built by this repository's generators, seed 0) to a file, for the
+    reference arm: both arms then play on the same tensors."""
+    depth, a, c, _ = CONFIGS[args.config]
+    if args.config in FAST_TREE_CONFIGS:
+        tree = fast_tree(args.config, depth, a, c, torch.device("cpu"))
+    else:
+        tree = make_tree(depth, a, c, seed=0)
+    keys = ("index_tensor", "value_tensor", "chance_tensor", "expected_value_tensor", "legal_tensor",
+            "root_value_tensor", "solution_tensor")
+    torch.save({k: getattr(tree, k).cpu() for k in keys} | {"hash": tree.hash}, args.emit_tree)
+
+
 def run_reference(args):
+    """
+    The UNMODIFIED reference (baseline/_ref/ref = a copy of /root/reference, see baseline/install_reference.py) on this
+    box's host cores: `Episodes.generate` (episode.py:175-230, timed by its own `generation_time`, :192-215) and the
+    learner loop body (rnad.py:495-526) through `RNaD.__resume`.  Harness-side only: the stand-in `pygambit` on
+    sys.path (the real one is absent), `b1_adam=0.0` (the reference's int default breaks Adam on torch 2.11), the tree
+    tensors handed over from a file so that both arms play the same tree.
+    """
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return None
+    if not REFERENCE_ARM:
+        return run_reference_port(args)
+    import tempfile
+
+    depth, a, c, batch = CONFIGS[args.config]
+    if args.batch:
+        batch = args.batch
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    with tempfile.TemporaryDirectory(prefix="rnad_ref_tree_") as tmp:
+        tree_file = os.path.join(tmp, "tree.pt")
+        subprocess.run([sys.executable, os.path.abspath(__file__), "--emit-tree", tree_file, "--config", args.config],
+                       check=True)
+        tables = torch.load(tree_file)
+    sys.path.insert(0, os.path.join(REF_ROOT, "_standin"))
+    sys.path.insert(0, os.path.join(REF_ROOT, "ref"))
+    import logging
+
+    from environment.episode import Episodes   # the reference's, from baseline/_ref/ref
+    from environment.tree import Tree
+    from learn.rnad import RNaD
+    from nn.net import MLP
+
+    assert os.path.realpath(sys.modules["learn.rnad"].__file__).startswith(os.path.realpath(REF_ROOT))
+    logging.disable(logging.INFO)
+    cpu_dev = torch.device("cpu")
+    tree = Tree(device=cpu_dev, max_actions=a, max_transitions=c, depth_bound=depth)
+    for key, value in tables.items():
+        setattr(tree, key, value)
+    n_nodes = int(tree.index_tensor.shape[0])
+    t_max = 2 * depth
+    sample_batch = min(batch, args.reference_batch)
+    torch.manual_seed(1234)
+    net = MLP(a, 256, device=cpu_dev)
+
+    # ---- env steps/s: Episodes.generate, the reference's own clock
+    for _ in range(min(args.warmup, 2)):
+        Episodes(tree, sample_batch).generate(net)
+    total, elapsed = 0, 0.0
+    for _ in range(args.steps):
+        ep = Episodes(tree, sample_batch)
+        ep.generate(net)
+        elapsed += ep.generation_time
+        total += int((ep.indices != 0).sum())
+    value = total / elapsed
+
+    # ---- updates/s: the rnad.py:495-526 loop body through the reference's own schedule loop
+    n_updates = max(2, min(args.steps // 4, 5))
+    trial = RNaD(tree=tree, device=cpu_dev, directory_name=f"bench_reference_{os.getpid()}", batch_size=sample_batch,
+                 eta=0.2, lr=1e-3, gamma_averaging=0.01, logit_clip=2, b1_adam=0.0, bounds=[1], delta_m=[1],
+                 net_params={"type": "MLP", "max_actions": a, "width": 256}, wandb=False)
+    trial._RNaD__initialize()
+    trial._RNaD__resume(checkpoint_mod=10 ** 9, expl_mod=10 ** 9, log_mod=10 ** 9)        # one warm-up update (m: 0 -> 1)
+    trial.bounds, trial.delta_m = [2], [n_updates]
+    t0 = time.perf_counter()
+    trial._RNaD__resume(checkpoint_mod=10 ** 9, expl_mod=10 ** 9, log_mod=10 ** 9)
+    learner_s = time.perf_counter() - t0
+    import shutil
+
+    shutil.rmtree(trial.directory, ignore_errors=True)
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    sample = (f"{args.steps} x Episodes.generate of {sample_batch} games x {t_max} half-moves and {n_updates} learner "
+              f"updates of {sample_batch} games, unmodified reference from baseline/_ref on {threads} torch threads")
+    result = {
+        "impl": "reference", "metric": "self_play_env_steps_per_sec", "value": value, "unit": "env_steps/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": elapsed * 1e3 / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
+        "config": workload_config(args.config, depth, a, c, n_nodes, batch, t_max),
+        "cpu_baseline": {"value": value, "unit": "env_steps/s", "cores": threads, "kind": "reference", "sample": sample},
+        "e2e": {"value": value, "unit": "env_steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "learner": {"updates_per_sec": n_updates / learner_s, "ms_per_update": learner_s * 1e3 / n_updates,
+                    "steps": n_updates, "batch": sample_batch,
+                    "env_steps_per_sec": n_updates * sample_batch * t_max / learner_s,
+                    "what": "reference RNaD.__resume loop body (rnad.py:495-526): Episodes.generate + Buffer.sample + "
+                            "__learn + Adam + target-net average, device cpu"},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(result), flush=True)
+    return result
+
+
+def run_reference_port(args):
+    """Fallback when baseline/_ref is absent (a checkout without /root/reference at build time): the CPU restatement
+    of the rollout (oracle/) - `cpu_baseline.kind = "port"`."""
     from oracle import rnad_oracle as orc
     from nn.net import MLP
 
@@ -455,8 +587,6 @@ def run_reference(args):
     if args.batch:
         batch = args.batch
     if args.config in FAST_TREE_CONFIGS:
-        from environment.tree import Tree
-
         tree = fast_tree(args.config, depth, a, c, torch.device("cpu"))   # on the host cores: minutes for the largest trees
     else:
         tree = make_tree(depth, a, c, seed=0)
@@ -482,12 +612,10 @@ def run_reference(args):
         "impl": "reference", "metric": "self_play_env_steps_per_sec", "value": value, "unit": "env_steps/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": elapsed * 1e3 / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
-        "config": {"workload": f"{args.config}: depth={depth} max_actions={a} max_transitions={c} regular tree, "
-                               f"MLP width 256; each step = one rollout of {sample_batch} games x {t_max} half-moves "
-                               f"(bounded sample of the {batch}-game batch)"},
+        "config": workload_config(args.config, depth, a, c, int(tree.index_tensor.shape[0]), batch, t_max),
         "cpu_baseline": {"value": value, "unit": "env_steps/s", "cores": threads, "kind": "port",
                          "sample": f"{args.steps} rollouts of {sample_batch} games, CPU restatement of the reference "
-                                   f"path (oracle/), torch-CPU ops on {threads} threads"},
+                                   f"path (oracle/), torch-CPU ops on {threads} threads (baseline/_ref not installed)"},
         "e2e": {"value": value, "unit": "env_steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -506,7 +634,10 @@ def main():
     ap.add_argument("--precision", default="tf32x2", choices=["tf32", "tf32x2", "fp32"])
     ap.add_argument("--cpu-budget", type=float, default=15.0, help="seconds of CPU work for cpu_baseline")
     ap.add_argument("--reference-batch", type=int, default=65536)
+    ap.add_argument("--emit-tree", default="", help="(internal) write the configuration's tree tables to this file")
     args = ap.parse_args()
+    if args.emit_tree:
+        return emit_tree(args)
     args.warmup = max(args.warmup, 3) if args.impl == "native" else args.warmup
     if args.impl == "reference":
         run_reference(args)

@@ -47,7 +47,7 @@ extern "C" {
 #define RNAD_MAX_TRANSITIONS 8
 
 RNAD_API const char* rnad_last_error(void);
-/* version of this ABI (major*100 + minor) */
+/* version of this ABI (major*100 + minor); 200: rnad_rollout takes seed_dev / stats, learner-step entry points */
 RNAD_API int rnad_version(void);
 /* number of SMs of the current device (host value), <0 on error */
 RNAD_API int rnad_device_sm_count(void);
@@ -110,11 +110,15 @@ RNAD_API int rnad_sample_categorical(const float* p, int64_t B, int N, const flo
  * Outputs, all (T,B,...) contiguous, reference dtypes (episode.py:218-225):
  *   indices i64, turns i64, observations f32 (T,B,2,A,A), policy f32 (T,B,A),
  *   actions f32 one-hot (T,B,A), rewards f32, values f32, masks f32 (T,B,A).
- * t_last (device int32; the call resets it to -1 in stream order): max over games of the last
- * half-move at which the game was not yet on the absorbing node (= t_eff).
- * workspace: 16-byte aligned device scratch of rnad_rollout_workspace_bytes()
- * (the tensor-core engine lays the weights out in MMA operand order there once per
- * call and every CTA fetches that image with one TMA bulk copy); may be NULL when 0.
+ * seed_dev: NULL, or a device uint64 the kernel reads the seed from instead of `seed` (a learner step
+ * captured in a CUDA graph varies the seed without re-recording the launch; see rnad_step_control).
+ * stats (device int32[4]; the call zeroes it in stream order - also for an empty batch):
+ *   [0] the longest game in half-moves = 1 + the last half-move at which some game was not yet on the
+ *       absorbing node (t_eff + 1);  [1], [2] the number of valid (t,b) slots of player 0 / player 1 - the
+ *       normalisers N_0, N_1 of both losses (vtrace.py:370-374, 387-389), so that nobody has to count them
+ *       again;  [3] reserved.
+ * workspace: 16-byte aligned device scratch of rnad_rollout_workspace_bytes() (RNAD_PREC_TF32 only: the
+ * weight image in MMA operand order; RNAD_PREC_TF32X2 and RNAD_PREC_FP32 need none); may be NULL when 0.
  * ------------------------------------------------------------------------ */
 typedef struct rnad_mlp_weights {
     const float* value_fc0_w; const float* value_fc0_b;
@@ -131,9 +135,10 @@ typedef struct rnad_trajectory {
 
 RNAD_API int rnad_rollout(const uint32_t* ev_tab, const uint32_t* tr_tab, int A, int C,
                  const rnad_mlp_weights* w /* host struct of device pointers */,
-                 int64_t B, int T, uint64_t seed, int64_t game_offset, const float* uniforms,
-                 int precision, const rnad_trajectory* out /* host struct of device pointers */,
-                 int32_t* t_last, void* workspace, void* stream);
+                 int64_t B, int T, uint64_t seed, const uint64_t* seed_dev, int64_t game_offset,
+                 const float* uniforms, int precision,
+                 const rnad_trajectory* out /* host struct of device pointers */,
+                 int32_t* stats, void* workspace, void* stream);
 
 RNAD_API int64_t rnad_rollout_workspace_bytes(int A, int width, int precision);
 
@@ -186,6 +191,12 @@ typedef struct rnad_learner_io {
     /* exact data-parallel normalisation (DP note i): if non-NULL, device int32[2]
      * GLOBAL counts to divide by instead of the local ones (already all-reduced by the caller) */
     const int32_t* global_counts;
+    /* unnormalised mode (the captured learner step, csrc/learner_step.cu): d_logit / d_v are written as if N_0 = N_1 = 1
+     * and the four loss numerators (critic p0, p1, NeuRD p0, p1) go to loss_sums (device float[4]); counts, losses and
+     * global_counts are not touched and nothing is counted - the division by the (global) step counts happens after
+     * the gradient exchange.  Rows of even t must belong to player 0 and of odd t to player 1 (rnad_rollout's). */
+    int unnormalised;
+    float* loss_sums;
 } rnad_learner_io;
 
 typedef struct rnad_learner_params {
@@ -193,6 +204,7 @@ typedef struct rnad_learner_params {
     float eps_threshold; int n_disc;
     float neurd_clip, beta;
     float value_weight, neurd_weight;
+    const float* alpha_dev;   /* if non-NULL: alpha is read from this device float (a captured step varies it) */
 } rnad_learner_params;
 
 RNAD_API int64_t rnad_learner_targets_workspace(int T, int64_t B);
@@ -235,6 +247,70 @@ RNAD_API int rnad_learner_forward(const float* observations, int64_t N, int A,
 RNAD_API int rnad_learner_backward(const float* observations, int64_t N, int A, const rnad_mlp_weights* net,
                           const float* d_logit, const float* d_v, float* flat_grad,
                           void* workspace, void* stream);
+/* The same for a (T,B,...) trajectory, one gradient per PLAYER: rows of even t are player 0's steps, rows of odd t
+ * player 1's (every row has exactly one owner and d_logit / d_v are zero elsewhere), and player_grads receives
+ * 2 x rnad_learner_param_count() floats - player 0's gradient, then player 1's.  With d_logit / d_v from
+ * rnad_learner_targets in unnormalised mode these are the numerators G_p of
+ *     d loss / d params = G_0 / N_0 + G_1 / N_1        (vtrace.py:370-374, 387-389; N_p = the players' step counts)
+ * which is what data-parallel ranks exchange: the division by the GLOBAL counts happens once, after the sum over
+ * ranks (rnad_learner_tail). */
+RNAD_API int rnad_learner_backward_split(const float* observations, int T, int64_t B, int A, const rnad_mlp_weights* net,
+                                const float* d_logit, const float* d_v, float* player_grads,
+                                void* workspace, void* stream);
+
+/* ------------------------------------------------------------------------
+ * One learner step as a replayable unit (rnad.py:495-526 loop body): the per-step scalars live in a device
+ * control block, the optimizer tail - and under data parallelism the one gradient exchange - is one kernel.
+ * ------------------------------------------------------------------------ */
+#define RNAD_MAX_PEERS 16
+#define RNAD_IPC_HANDLE_BYTES 64
+
+typedef struct rnad_step_ctrl {   /* DEVICE memory, 32 bytes, zero-initialised by the caller */
+    uint64_t seed;                /* rollout seed of this step      (pass &ctrl->seed  as rnad_rollout's seed_dev) */
+    float alpha;                  /* reward-transform mixing weight (pass &ctrl->alpha as rnad_learner_params.alpha_dev) */
+    uint32_t seq;                 /* completed rnad_learner_tail calls: slot parity and flag value of the exchange */
+    float adam_step;              /* Adam's step count (torch keeps it as a float) */
+    uint32_t error;               /* bit r set: gave up waiting for rank r's gradients */
+    uint32_t reserved[2];
+} rnad_step_ctrl;
+
+/* writes seed and alpha into *ctrl in stream order (a one-thread kernel; the arguments travel by value) */
+RNAD_API int rnad_step_control(rnad_step_ctrl* ctrl, uint64_t seed, float alpha, void* stream);
+
+/* rnad_learner_tail: [sum over ranks of (G_0 | G_1 | N_0, N_1 | loss numerators) over NVLink peer memory] ->
+ * g = G_0 / N_0 + G_1 / N_1 -> clip_grad_norm_(grad_clip) (rnad.py:456) -> Adam (torch.optim.Adam semantics without
+ * amsgrad / weight decay, rnad.py:514; exp_avg, exp_avg_sq and ctrl->adam_step are its state) ->
+ * target = gamma_averaging * params + (1 - gamma_averaging) * target (rnad.py:516-523).
+ * All flat arrays hold n_params floats in state_dict order (see rnad_learner_backward).
+ * flat_grad: the clipped gradient (what p.grad holds after RNaD.__learn).
+ * losses: device float[4] = {loss_v, loss_nerd, gradient norm before clipping, ctrl->error}; under data parallelism
+ * the losses are those of the GLOBAL batch, identical on every rank.
+ * world == 1: no exchange, xchg is ignored.  world > 1: xchg[r] is rank r's exchange buffer as mapped into THIS
+ * process (xchg[rank] the local one), each rnad_xchg_bytes(n_params, world) bytes, created zeroed by
+ * rnad_xchg_create on its owner and opened by the others through the 64-byte CUDA IPC handle; every rank calls
+ * rnad_learner_tail once per step, all with the same ctrl->seq. */
+typedef struct rnad_tail_args {
+    int n_params;
+    const float* player_grads;    /* [2][n_params], this rank's (rnad_learner_backward_split) */
+    const int32_t* stats;         /* rnad_rollout's stats words: [1], [2] = this rank's N_0, N_1 */
+    const float* loss_sums;       /* float[4], rnad_learner_targets in unnormalised mode */
+    float* params; float* target_params; float* exp_avg; float* exp_avg_sq;
+    float* flat_grad; float* losses;
+    rnad_step_ctrl* ctrl;
+    float lr, beta1, beta2, eps, grad_clip, gamma_averaging, one_minus_gamma_averaging;
+    int world, rank;
+    float* xchg[RNAD_MAX_PEERS];
+} rnad_tail_args;
+
+RNAD_API int rnad_learner_tail(const rnad_tail_args* args /* host struct */, void* stream);
+
+RNAD_API int64_t rnad_xchg_bytes(int n_params, int world);
+/* cudaMalloc + zero + cudaIpcGetMemHandle: *ptr = the local buffer, handle = RNAD_IPC_HANDLE_BYTES bytes to hand to the
+ * other ranks (host memory; e.g. through torch.distributed.all_gather_object) */
+RNAD_API int rnad_xchg_create(int64_t bytes, void** ptr, unsigned char* handle);
+RNAD_API int rnad_xchg_open(const unsigned char* handle, void** ptr);   /* a peer's buffer, mapped into this process */
+RNAD_API int rnad_xchg_close(void* ptr);                                 /* unmap a peer's buffer */
+RNAD_API int rnad_xchg_destroy(void* ptr);                               /* free the local buffer */
 
 #ifdef __cplusplus
 }

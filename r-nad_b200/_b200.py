@@ -28,8 +28,12 @@ EXPORTS = (
     "rnad_rollout_tc2_supported",
     "rnad_process_policy", "rnad_vtrace", "rnad_learner_targets_workspace", "rnad_count_played",
     "rnad_learner_targets", "rnad_learner_mlp_supported", "rnad_learner_mlp_workspace_bytes",
-    "rnad_learner_param_count", "rnad_learner_forward", "rnad_learner_backward",
+    "rnad_learner_param_count", "rnad_learner_forward", "rnad_learner_backward", "rnad_learner_backward_split",
+    "rnad_step_control", "rnad_learner_tail", "rnad_xchg_bytes", "rnad_xchg_create", "rnad_xchg_open", "rnad_xchg_close",
+    "rnad_xchg_destroy",
 )
+MAX_PEERS = 16
+IPC_HANDLE_BYTES = 64
 
 
 class RnadError(RuntimeError):
@@ -51,7 +55,8 @@ class LearnerIO(Structure):
         [(n, c_void_p) for n in ("indices", "turns", "mu", "actions_oh", "rewards", "masks", "logit", "pi", "log_pi",
                                  "v", "v_target_net", "log_pi_reg", "log_pi_reg_", "d_logit", "d_v", "pi_processed")]
         + [("v_target", c_void_p * 2), ("has_played", c_void_p * 2), ("learning_output", c_void_p * 2)]
-        + [("losses", c_void_p), ("counts", c_void_p), ("global_counts", c_void_p)]
+        + [("losses", c_void_p), ("counts", c_void_p), ("global_counts", c_void_p), ("unnormalised", c_int),
+           ("loss_sums", c_void_p)]
     )
 
 
@@ -62,7 +67,22 @@ class LearnerFwdOut(Structure):
 class LearnerParams(Structure):
     _fields_ = [("alpha", c_float), ("eta", c_float), ("lambda_", c_float), ("c", c_float), ("rho", c_float),
                 ("gamma", c_float), ("eps_threshold", c_float), ("n_disc", c_int), ("neurd_clip", c_float),
-                ("beta", c_float), ("value_weight", c_float), ("neurd_weight", c_float)]
+                ("beta", c_float), ("value_weight", c_float), ("neurd_weight", c_float), ("alpha_dev", c_void_p)]
+
+
+class StepCtrl(Structure):
+    """rnad_step_ctrl (device memory; mirrored here for offsets and for reading it back)."""
+    _fields_ = [("seed", c_uint64), ("alpha", c_float), ("seq", ctypes.c_uint32), ("adam_step", c_float),
+                ("error", ctypes.c_uint32), ("reserved", ctypes.c_uint32 * 2)]
+
+
+class TailArgs(Structure):
+    _fields_ = ([("n_params", c_int)]
+                + [(n, c_void_p) for n in ("player_grads", "stats", "loss_sums", "params", "target_params", "exp_avg",
+                                           "exp_avg_sq", "flat_grad", "losses", "ctrl")]
+                + [(n, c_float) for n in ("lr", "beta1", "beta2", "eps", "grad_clip", "gamma_averaging",
+                                          "one_minus_gamma_averaging")]
+                + [("world", c_int), ("rank", c_int), ("xchg", c_void_p * MAX_PEERS)])
 
 
 _lib = None
@@ -90,7 +110,7 @@ def lib():
     L.rnad_sample_categorical.argtypes = [c_void_p, c_int64, c_int, c_void_p, c_uint64, c_int, c_int64, c_void_p,
                                           c_void_p]
     L.rnad_rollout.argtypes = [c_void_p, c_void_p, c_int, c_int, POINTER(MlpWeights), c_int64, c_int, c_uint64,
-                               c_int64, c_void_p, c_int, POINTER(Trajectory), c_void_p, c_void_p, c_void_p]
+                               c_void_p, c_int64, c_void_p, c_int, POINTER(Trajectory), c_void_p, c_void_p, c_void_p]
     L.rnad_rollout_workspace_bytes.restype = c_int64
     L.rnad_rollout_workspace_bytes.argtypes = [c_int, c_int, c_int]
     L.rnad_rollout_tc_supported.argtypes = [c_int, c_int]
@@ -110,6 +130,16 @@ def lib():
         POINTER(LearnerFwdOut), c_void_p, c_void_p]
     L.rnad_learner_backward.argtypes = [c_void_p, c_int64, c_int, POINTER(MlpWeights), c_void_p, c_void_p, c_void_p,
                                         c_void_p, c_void_p]
+    L.rnad_learner_backward_split.argtypes = [c_void_p, c_int, c_int64, c_int, POINTER(MlpWeights), c_void_p, c_void_p,
+                                              c_void_p, c_void_p, c_void_p]
+    L.rnad_step_control.argtypes = [c_void_p, c_uint64, c_float, c_void_p]
+    L.rnad_learner_tail.argtypes = [POINTER(TailArgs), c_void_p]
+    L.rnad_xchg_bytes.restype = c_int64
+    L.rnad_xchg_bytes.argtypes = [c_int, c_int]
+    L.rnad_xchg_create.argtypes = [c_int64, POINTER(c_void_p), ctypes.c_char_p]
+    L.rnad_xchg_open.argtypes = [ctypes.c_char_p, POINTER(c_void_p)]
+    L.rnad_xchg_close.argtypes = [c_void_p]
+    L.rnad_xchg_destroy.argtypes = [c_void_p]
     no_errcheck = ("rnad_version", "rnad_device_sm_count", "rnad_rollout_tc_supported", "rnad_rollout_tc2_supported", "rnad_learner_mlp_supported",
                    "rnad_learner_param_count")
     for name in EXPORTS:

@@ -38,7 +38,7 @@ extern "C" {
 
 const char* rnad_last_error(void) { return rnad::g_error; }
 
-int rnad_version(void) { return 100; }
+int rnad_version(void) { return 200; }
 
 int rnad_device_sm_count(void) {
     int n = rnad::sm_count();

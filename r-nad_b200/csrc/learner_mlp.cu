@@ -652,6 +652,7 @@ __global__ void pack_bwd_tc_image_kernel(rnad_mlp_weights w, uint8_t* __restrict
 
 template <int A>
 __global__ void __launch_bounds__(kBwdTcThreads, 2) learner_bwd_tc_kernel(const float* __restrict__ obs, int64_t N,
+                                                                           int T_split, int64_t B_split,
                                                                            const uint8_t* __restrict__ image,
                                                                            const float* __restrict__ d_logit,
                                                                            const float* __restrict__ d_v,
@@ -718,19 +719,34 @@ __global__ void __launch_bounds__(kBwdTcThreads, 2) learner_bwd_tc_kernel(const 
     for (int half = 0; half < 2; ++half) bias_j[half] = P::kBiasInK ? 0.f : b1[half * 128 + j_local];
 
     uint32_t phase = 0;
-    const int64_t num_tiles = (N + kTileM - 1) / kTileM;
+    // Which tiles this CTA pair walks.  Flat mode (T_split == 0): tile u = rows [128 u, 128 u + 128) of the N rows, pair
+    // `cta` takes u = cta, cta + n_ctas, ...  Split mode (the rows are a (T_split, B_split) trajectory): tiles never
+    // straddle a half-move - half-move t has ceil(B / 128) tiles, the last one short - and pairs with an even index walk
+    // the tiles of even t (player 0's steps), pairs with an odd index those of odd t (player 1's): the per-pair partial
+    // sums then add up to one UNNORMALISED gradient per player (reduce_partials_kernel), which the caller divides by the
+    // global step counts after the exchange.
+    const bool split = T_split > 0;
+    const int player = split ? (cta & 1) : 0;
+    const int64_t tiles_per_t = split ? (B_split + kTileM - 1) / kTileM : 0;
+    const int64_t my_first = split ? (cta >> 1) : cta, my_stride = split ? (n_ctas >> 1) : n_ctas;
+    const int64_t num_tiles = split ? (int64_t)((T_split - player + 1) / 2) * tiles_per_t : (N + kTileM - 1) / kTileM;
     // threads 0..127 own one row of every tile; its observation and output gradients, one tile ahead
     float x_next[KIN], g_next[1 + A];
-    auto load_tile_row = [&](int64_t tile) {
-        const int64_t row = tile * kTileM + tid;
-        const bool active = tile < num_tiles && row < N;
+    auto load_tile_row = [&](int64_t u) {
+        int64_t row = u * kTileM + tid;
+        bool active = u < num_tiles && row < N;
+        if (split) {
+            const int64_t tt = 2 * (u / tiles_per_t) + player, j = (u % tiles_per_t) * kTileM + tid;
+            row = tt * B_split + j;
+            active = u < num_tiles && j < B_split;
+        }
         load_row<KIN>(obs, active ? row : 0, active, x_next);
         g_next[0] = active ? __ldg(d_v + row) : 0.f;
 #pragma unroll
         for (int a = 0; a < A; ++a) g_next[1 + a] = active ? __ldg(d_logit + row * A + a) : 0.f;
     };
-    if (tid < kTileM) load_tile_row(cta);
-    for (int64_t tile = cta; tile < num_tiles; tile += n_ctas) {
+    if (tid < kTileM) load_tile_row(my_first);
+    for (int64_t tile = my_first; tile < num_tiles; tile += my_stride) {
         // ---- the tile's operands: observation tile (B of the recompute), x^T | 1 and g^T (B of the gradient MMAs);
         //      the row's data was loaded one tile ahead, the next tile's loads are issued right after it is consumed
         if (tid < kTileM) {
@@ -740,7 +756,7 @@ __global__ void __launch_bounds__(kBwdTcThreads, 2) learner_bwd_tc_kernel(const 
             for (int k = 0; k < KIN; ++k) x[k] = x_next[k];
 #pragma unroll
             for (int a = 0; a <= A; ++a) g[a] = g_next[a];
-            load_tile_row(tile + n_ctas);
+            load_tile_row(tile + my_stride);
             store_operand_row<KIN, KP, P::kBiasInK>(smem + P::kX, n, x);
 #pragma unroll
             for (int k = 0; k < KIN; ++k) *reinterpret_cast<float*>(smem + P::kBX + off_t(k, n)) = to_tf32_fast(x[k]);
@@ -883,17 +899,20 @@ __global__ void __launch_bounds__(kBwdTcThreads, 2) learner_bwd_tc_kernel(const 
 
 // Sum of the per-CTA partial gradients in a FIXED order (deterministic): eight lanes per parameter take the partials
 // p = lane, lane + 8, ... (eight loads in flight per thread as well) and meet in a shuffle tree.
+// Split mode (gridDim.y == 2): blockIdx.y = player; player p's partials are the rows p, p + 2, ... (pairs with index
+// parity p) and its sum goes to flat_grad + p * n_params.
 __global__ void reduce_partials_kernel(const float* __restrict__ partials, int n_parts, int n_params,
                                        float* __restrict__ flat_grad) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     const int i = t >> 3, sub = t & 7;
+    const int step = gridDim.y, first = blockIdx.y;      // 1, 0 in flat mode
     float acc = 0.f;
     if (i < n_params) {
         float a0 = 0.f, a1 = 0.f;
-        int p = sub;
-        for (; p + 8 < n_parts; p += 16) {
+        int p = first + sub * step;
+        for (; p + 8 * step < n_parts; p += 16 * step) {
             a0 += partials[(int64_t)p * n_params + i];
-            a1 += partials[(int64_t)(p + 8) * n_params + i];
+            a1 += partials[(int64_t)(p + 8 * step) * n_params + i];
         }
         if (p < n_parts) a0 += partials[(int64_t)p * n_params + i];
         acc = a0 + a1;
@@ -901,7 +920,7 @@ __global__ void reduce_partials_kernel(const float* __restrict__ partials, int n
     acc += __shfl_xor_sync(0xffffffffu, acc, 1);
     acc += __shfl_xor_sync(0xffffffffu, acc, 2);
     acc += __shfl_xor_sync(0xffffffffu, acc, 4);
-    if (i < n_params && sub == 0) flat_grad[i] = acc;
+    if (i < n_params && sub == 0) flat_grad[(int64_t)blockIdx.y * n_params + i] = acc;
 }
 
 constexpr int kMaxBwdCtas = 160;
@@ -942,9 +961,11 @@ int launch_forward(const float* obs, int64_t N, const FwdNets& nets, const FwdOu
     return RNAD_OK;
 }
 
+// T_split > 0: the rows are a (T_split, B_split) trajectory and flat_grad receives TWO unnormalised gradients,
+// player 0's (rows of even t) then player 1's (see learner_bwd_tc_kernel).
 template <int A>
-int launch_backward(const float* obs, int64_t N, const rnad_mlp_weights& w, const float* d_logit, const float* d_v,
-                    float* flat_grad, uint8_t* workspace, cudaStream_t st) {
+int launch_backward(const float* obs, int64_t N, int T_split, int64_t B_split, const rnad_mlp_weights& w,
+                    const float* d_logit, const float* d_v, float* flat_grad, uint8_t* workspace, cudaStream_t st) {
     using P = BwdPlan<A>;
     using PT = BwdTcPlan<A>;
     static_assert(PT::kImageBytes >= P::kImageBytes, "the workspace reserves the larger image");
@@ -952,9 +973,15 @@ int launch_backward(const float* obs, int64_t N, const rnad_mlp_weights& w, cons
     float* partials = reinterpret_cast<float*>(image + round_up(PT::kImageBytes, 256));
     int64_t blocks = (N + kTileM - 1) / kTileM;
     const int cap = sm_count() < kMaxBwdCtas ? sm_count() : kMaxBwdCtas;
-    if (blocks > cap) blocks = cap;
+    if (T_split > 0) {
+        // an even number of CTA pairs, half of them per player; at least one pair each (a player without rows writes zeros)
+        const int64_t per_player = (int64_t)((T_split + 1) / 2) * ((B_split + kTileM - 1) / kTileM);
+        blocks = 2 * (per_player < cap / 2 ? per_player : cap / 2);
+    } else if (blocks > cap) {
+        blocks = cap;
+    }
     static const bool cuda_core_reduction = getenv("RNAD_LEARNER_BWD_CUDA_CORES") != nullptr;   // the previous kernel, for A/B runs
-    if (cuda_core_reduction) {
+    if (cuda_core_reduction && T_split == 0) {
         pack_bwd_image_kernel<A><<<24, 256, 0, st>>>(w, image);
         RNAD_CHECK_LAUNCH("pack_bwd_image_kernel");
         int rc = prepare<A>(learner_bwd_kernel<A>, P::kBytes, "cudaFuncSetAttribute(learner_bwd)");
@@ -971,10 +998,12 @@ int launch_backward(const float* obs, int64_t N, const rnad_mlp_weights& w, cons
         if (smem < floor_two_per_sm) smem = floor_two_per_sm;
         int rc = prepare<A>(learner_bwd_tc_kernel<A>, smem, "cudaFuncSetAttribute(learner_bwd_tc)");
         if (rc) return rc;
-        learner_bwd_tc_kernel<A><<<2 * (int)blocks, kBwdTcThreads, smem, st>>>(obs, N, image, d_logit, d_v, partials);
+        learner_bwd_tc_kernel<A><<<2 * (int)blocks, kBwdTcThreads, smem, st>>>(obs, N, T_split, B_split, image, d_logit,
+                                                                               d_v, partials);
         RNAD_CHECK_LAUNCH("learner_bwd_tc_kernel");
     }
-    reduce_partials_kernel<<<(P::kParams * 8 + 255) / 256, 256, 0, st>>>(partials, (int)blocks, P::kParams, flat_grad);
+    reduce_partials_kernel<<<dim3((P::kParams * 8 + 255) / 256, T_split > 0 ? 2 : 1), 256, 0, st>>>(
+        partials, (int)blocks, P::kParams, flat_grad);
     RNAD_CHECK_LAUNCH("reduce_partials_kernel");
     return RNAD_OK;
 }
@@ -1050,9 +1079,30 @@ int rnad_learner_backward(const float* observations, int64_t N, int A, const rna
     RNAD_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "rnad_learner_backward: workspace must be 256-byte aligned");
     cudaStream_t st = (cudaStream_t)stream;
     switch (A) {
-        case 2: return tc::launch_backward<2>(observations, N, *net, d_logit, d_v, flat_grad, (uint8_t*)workspace, st);
-        case 3: return tc::launch_backward<3>(observations, N, *net, d_logit, d_v, flat_grad, (uint8_t*)workspace, st);
-        case 4: return tc::launch_backward<4>(observations, N, *net, d_logit, d_v, flat_grad, (uint8_t*)workspace, st);
+        case 2: return tc::launch_backward<2>(observations, N, 0, 0, *net, d_logit, d_v, flat_grad, (uint8_t*)workspace, st);
+        case 3: return tc::launch_backward<3>(observations, N, 0, 0, *net, d_logit, d_v, flat_grad, (uint8_t*)workspace, st);
+        case 4: return tc::launch_backward<4>(observations, N, 0, 0, *net, d_logit, d_v, flat_grad, (uint8_t*)workspace, st);
+    }
+    return RNAD_EINVAL;
+}
+
+int rnad_learner_backward_split(const float* observations, int T, int64_t B, int A, const rnad_mlp_weights* net,
+                                const float* d_logit, const float* d_v, float* player_grads, void* workspace,
+                                void* stream) {
+    RNAD_REQUIRE(observations && d_logit && d_v && player_grads && workspace, "rnad_learner_backward_split: null pointer");
+    RNAD_REQUIRE(weights_ok(net), "rnad_learner_backward_split: null weight pointer");
+    RNAD_REQUIRE(T >= 1 && B >= 1, "rnad_learner_backward_split: empty trajectory");
+    if (!rnad_learner_mlp_supported(A, net->width)) {
+        set_error("rnad_learner_backward_split: needs width 256 and 2 <= max_actions <= 4");
+        return RNAD_EUNSUPPORTED;
+    }
+    RNAD_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "rnad_learner_backward_split: workspace must be 256-byte aligned");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t N = (int64_t)T * B;
+    switch (A) {
+        case 2: return tc::launch_backward<2>(observations, N, T, B, *net, d_logit, d_v, player_grads, (uint8_t*)workspace, st);
+        case 3: return tc::launch_backward<3>(observations, N, T, B, *net, d_logit, d_v, player_grads, (uint8_t*)workspace, st);
+        case 4: return tc::launch_backward<4>(observations, N, T, B, *net, d_logit, d_v, player_grads, (uint8_t*)workspace, st);
     }
     return RNAD_EINVAL;
 }

@@ -4,10 +4,10 @@
 using namespace rnad;
 
 extern "C" int rnad_rollout(const uint32_t* ev_tab, const uint32_t* tr_tab, int A, int C, const rnad_mlp_weights* w,
-                            int64_t B, int T, uint64_t seed, int64_t game_offset, const float* uniforms,
-                            int precision, const rnad_trajectory* out, int32_t* t_last, void* workspace,
-                            void* stream) {
-    RNAD_REQUIRE(ev_tab && tr_tab && w && out && t_last, "rnad_rollout: null pointer");
+                            int64_t B, int T, uint64_t seed, const uint64_t* seed_dev, int64_t game_offset,
+                            const float* uniforms, int precision, const rnad_trajectory* out, int32_t* stats,
+                            void* workspace, void* stream) {
+    RNAD_REQUIRE(ev_tab && tr_tab && w && out && stats, "rnad_rollout: null pointer");
     RNAD_REQUIRE(A >= 1 && A <= RNAD_MAX_ACTIONS, "rnad_rollout: max_actions %d outside [1,%d]", A, RNAD_MAX_ACTIONS);
     RNAD_REQUIRE(C >= 1 && C <= RNAD_MAX_TRANSITIONS, "rnad_rollout: max_transitions %d outside [1,%d]", C,
                  RNAD_MAX_TRANSITIONS);
@@ -19,6 +19,10 @@ extern "C" int rnad_rollout(const uint32_t* ev_tab, const uint32_t* tr_tab, int 
     RNAD_REQUIRE(out->indices && out->turns && out->observations && out->policy && out->actions && out->rewards &&
                      out->values && out->masks,
                  "rnad_rollout: null trajectory pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    // the kernels atomicMax / atomicAdd into stats: start from zero here, in stream order (also for an empty batch)
+    int rc = check_cuda(cudaMemsetAsync(stats, 0, 4 * sizeof(int32_t), st), "cudaMemsetAsync(stats)");
+    if (rc) return rc;
     if (B == 0 || T == 0) return RNAD_OK;
 
     RolloutArgs g;
@@ -30,15 +34,12 @@ extern "C" int rnad_rollout(const uint32_t* ev_tab, const uint32_t* tr_tab, int 
     g.B = B;
     g.T = T;
     g.seed = seed;
+    g.seed_dev = seed_dev;
     g.game_offset = game_offset;
     g.uniforms = uniforms;
     g.out = TrajPtrs{out->indices, out->turns, out->observations, out->policy,
                      out->actions, out->rewards, out->values, out->masks};
-    g.t_last = t_last;
-    cudaStream_t st = (cudaStream_t)stream;
-    // the kernels atomicMax into *t_last: start it at -1 here, in stream order
-    int rc = check_cuda(cudaMemsetAsync(t_last, 0xFF, sizeof(int32_t), st), "cudaMemsetAsync(t_last)");
-    if (rc) return rc;
+    g.stats = stats;
     switch (precision) {
         case RNAD_PREC_FP32: return rollout_fp32(g, st);
         case RNAD_PREC_TF32: return rollout_tc(g, workspace, st);
@@ -57,6 +58,6 @@ extern "C" int rnad_rollout_tc2_supported(int A, int width, int C) { return roll
 // bytes of device scratch rnad_rollout needs for this net shape and engine (0 = none)
 extern "C" int64_t rnad_rollout_workspace_bytes(int A, int width, int precision) {
     if (precision == RNAD_PREC_TF32 && rollout_tc_supported(A, width)) return rollout_tc_workspace_bytes(A);
-    if (precision == RNAD_PREC_TF32X2 && rollout_tc_supported(A, width)) return rollout_tc2_workspace_bytes(A);
+    if (precision == RNAD_PREC_TF32X2 && rollout_tc2_supported(A, width, 1)) return rollout_tc2_workspace_bytes(A);
     return 0;
 }

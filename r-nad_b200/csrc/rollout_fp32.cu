@@ -38,7 +38,8 @@ __global__ void __launch_bounds__(128) rollout_fp32_kernel(RolloutArgs g) {
     if (threadIdx.x < A) b2[1 + threadIdx.x] = g.w.policy_fc1_b[threadIdx.x];
     __syncthreads();
 
-    int last_valid = -1;
+    int last_valid = -1, n_valid0 = 0, n_valid1 = 0;
+    const uint64_t seed = g.seed_dev != nullptr ? __ldg(g.seed_dev) : g.seed;
     for (int64_t b = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; b < g.B; b += (int64_t)gridDim.x * blockDim.x) {
         int node = 1;   // every game starts at the root (episode.py:22)
         int row_action = 0;
@@ -46,7 +47,11 @@ __global__ void __launch_bounds__(128) rollout_fp32_kernel(RolloutArgs g) {
         for (int t = 0; t < g.T; ++t) {
             const int turn = t & 1;
             if (turn == 0) load_node<A>(g.ev_tab, node, n);
-            if (node != 0) last_valid = max(last_valid, t);
+            if (node != 0) {
+                last_valid = max(last_valid, t);
+                n_valid0 += turn == 0;
+                    n_valid1 += turn;
+            }
             float x[KIN];
             build_obs<A>(n, turn, x);
             const int n_legal = turn == 0 ? n.rows : n.cols;
@@ -89,7 +94,7 @@ __global__ void __launch_bounds__(128) rollout_fp32_kernel(RolloutArgs g) {
                 u.action = g.uniforms[slot * 2 + 0];
                 u.chance = g.uniforms[slot * 2 + 1];
             } else {
-                u = philox_uniforms(g.seed, (uint32_t)t, (uint64_t)(g.game_offset + b));
+                u = philox_uniforms(seed, (uint32_t)t, (uint64_t)(g.game_offset + b));
             }
             const int action = sample_icdf(policy, A, u.action);
             float reward = 0.f;
@@ -104,8 +109,7 @@ __global__ void __launch_bounds__(128) rollout_fp32_kernel(RolloutArgs g) {
             write_record<A>(g.out, slot, node_now, turn, n_legal, policy, action, value, reward);
         }
     }
-    last_valid = warp_max(last_valid);
-    if ((threadIdx.x & 31) == 0 && last_valid >= 0) atomicMax(g.t_last, last_valid);
+    publish_stats(g.stats, last_valid, n_valid0, n_valid1, threadIdx.x & 31);
 }
 
 template <int A>

@@ -142,7 +142,8 @@ __global__ void __launch_bounds__(kThreads, 2) rollout_tc_kernel(RolloutArgs g, 
     const uint32_t b_base = smem_u32(smem + P::kB);
 
     uint32_t phase = 0;
-    int last_valid = -1;
+    int last_valid = -1, n_valid0 = 0, n_valid1 = 0;
+    const uint64_t seed = g.seed_dev != nullptr ? __ldg(g.seed_dev) : g.seed;
     const int64_t num_tiles = (g.B + kTileM - 1) / kTileM;
     for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int64_t tile_base = tile * kTileM;
@@ -162,7 +163,11 @@ __global__ void __launch_bounds__(kThreads, 2) rollout_tc_kernel(RolloutArgs g, 
             int n_legal = 1;
             if (half == 0) {
                 if (turn == 0 && active) load_node<A>(g.ev_tab, node, n);
-                if (node != 0) last_valid = max(last_valid, t);
+                if (node != 0) {
+                    last_valid = max(last_valid, t);
+                    n_valid0 += turn == 0;
+                    n_valid1 += turn;
+                }
                 n_legal = turn == 0 ? n.rows : n.cols;
                 float x[KP];
                 {
@@ -271,7 +276,7 @@ __global__ void __launch_bounds__(kThreads, 2) rollout_tc_kernel(RolloutArgs g, 
                     u.action = active ? g.uniforms[slot * 2 + 0] : 0.f;
                     u.chance = active ? g.uniforms[slot * 2 + 1] : 0.f;
                 } else {
-                    u = philox_uniforms(g.seed, (uint32_t)t, (uint64_t)(g.game_offset + b));
+                    u = philox_uniforms(seed, (uint32_t)t, (uint64_t)(g.game_offset + b));
                 }
                 const int action = sample_icdf(policy, A, u.action);
                 float reward = 0.f;
@@ -288,8 +293,7 @@ __global__ void __launch_bounds__(kThreads, 2) rollout_tc_kernel(RolloutArgs g, 
         }
     }
 
-    last_valid = warp_max(last_valid);
-    if ((tid & 31) == 0 && last_valid >= 0) atomicMax(g.t_last, last_valid);
+    publish_stats(g.stats, last_valid, n_valid0, n_valid1, tid & 31);
     tc_fence_before();
     __syncthreads();
     if (warp == 0) {

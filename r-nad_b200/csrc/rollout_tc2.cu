@@ -545,7 +545,8 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tc2_kernel(RolloutArgs g)
         const uint32_t my_bar_a = bar_a(side), my_bar_d2p = bar_d2p(side), my_bar_d2v = bar_d2v(side), my_bar_vfree = bar_vfree(side);
 
         uint32_t ph_d2 = 0;
-        int last_valid = -1;
+        int last_valid = -1, n_valid0 = 0, n_valid1 = 0;
+        const uint64_t seed = g.seed_dev != nullptr ? __ldg(g.seed_dev) : g.seed;
         for (int64_t k = 0; k < my_pairs; ++k) {
 #ifdef RNAD_TRACE
             const bool first_pair = k == 0;
@@ -625,7 +626,7 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tc2_kernel(RolloutArgs g)
                     u.action = active ? __ldg(g.uniforms + slot_tb * 2 + 0) : 0.f;
                     u.chance = active ? __ldg(g.uniforms + slot_tb * 2 + 1) : 0.f;
                 } else {
-                    u = philox_uniforms(g.seed, (uint32_t)t, (uint64_t)(g.game_offset + b));
+                    u = philox_uniforms(seed, (uint32_t)t, (uint64_t)(g.game_offset + b));
                 }
                 return u;
             };
@@ -670,7 +671,11 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tc2_kernel(RolloutArgs g)
                     publish_obs(-1);
                     if (k == 0) take_value();   // (later pairs: cleared and handed back after the previous pair's last half-move)
                 } else {
-                    if (node != 0) last_valid = max(last_valid, t);
+                    if (node != 0) {
+                        last_valid = max(last_valid, t);
+                        n_valid0 += turn == 0;
+                    n_valid1 += turn;
+                    }
                     const int n_legal = turn == 0 ? n.rows : n.cols;
                     // a row half-move does not move the game: the column player's observation is known beforehand
                     if (turn == 0) build_obs<A>(n, 1, x);
@@ -724,8 +729,7 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tc2_kernel(RolloutArgs g)
                 if (t >= 0 && lane_g == 0) TR(side, t, 4);
             }
         }
-        last_valid = warp_max(last_valid);
-        if (lane == 0 && last_valid >= 0) atomicMax(g.t_last, last_valid);
+        publish_stats(g.stats, last_valid, n_valid0, n_valid1, lane);
     }
 
     tc_fence_before();

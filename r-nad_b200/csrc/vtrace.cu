@@ -6,6 +6,8 @@
 // in the reference's operation order (no FMA contraction), so that results
 // agree with the reference's fp32 torch-CPU ops bit for bit wherever the
 // reference's own summation order is reproducible (A <= 5; see sum_lanes).
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace rnad {
@@ -111,25 +113,18 @@ struct Scalars {
     float neg_eta, lambda_, c, rho, gamma;
 };
 
-// One step of _loop_v_trace (vtrace.py:262-333) for one player.  `own`/`opp`:
-// the slot is valid and belongs to this player / to the other one.
-template <int A>
-__device__ __forceinline__ void vtrace_step(Carry& k, const Scalars& s, bool own, bool opp, float v, float reward,
-                                            float cs, float inv_mu, float ent, const float (&elp)[A],
-                                            const float (&a_oh)[A], float& vt_out, float (&lo_out)[A]) {
+// One step of _loop_v_trace (vtrace.py:262-333) for one player, the part that touches the carry.  `own`/`opp`:
+// the slot is valid and belongs to this player / to the other one.  Returns the v-trace target `vt` and
+// `q_tail` = dR + gamma * IS * nvt - v, the carry-dependent factor of learning_output (vtrace.py:303-309).
+__device__ __forceinline__ void vtrace_scan_step(Carry& k, const Scalars& s, bool own, bool opp, float v, float reward,
+                                                 float cs, float ent, float& vt, float& q_tail) {
     const float Ru2 = add(add(reward, mul(s.gamma, k.Ru)), ent);
     const float dR = add(reward, mul(s.gamma, k.R));
     const float w = mul(cs, k.IS);
     const float t1 = mul(fminf(w, s.rho), sub(add(Ru2, mul(s.gamma, k.nv)), v));
     const float t2 = mul(mul(mul(s.lambda_, fminf(w, s.c)), s.gamma), sub(k.nvt, k.nv));
-    const float vt = add(add(v, t1), t2);
-    const float q_tail = sub(add(dR, mul(mul(s.gamma, k.IS), k.nvt)), v);
-#pragma unroll
-    for (int a = 0; a < A; ++a) {
-        const float lo = add(add(v, elp[a]), mul(mul(a_oh[a], inv_mu), q_tail));
-        lo_out[a] = own ? lo : 0.f;
-    }
-    vt_out = own ? vt : 0.f;
+    vt = add(add(v, t1), t2);
+    q_tail = sub(add(dR, mul(mul(s.gamma, k.IS), k.nvt)), v);
     if (own) {
         k.R = 0.f;
         k.Ru = 0.f;
@@ -145,6 +140,26 @@ __device__ __forceinline__ void vtrace_step(Carry& k, const Scalars& s, bool own
     } else {
         k.reset();
     }
+}
+
+// learning_output of an own step (vtrace.py:303-309): v + elp[a] + a_oh[a] / mu(a) * q_tail
+template <int A>
+__device__ __forceinline__ void learning_output_row(float v, const float (&elp)[A], const float (&a_oh)[A], float inv_mu,
+                                                    float q_tail, float (&lo)[A]) {
+#pragma unroll
+    for (int a = 0; a < A; ++a) lo[a] = add(add(v, elp[a]), mul(mul(a_oh[a], inv_mu), q_tail));
+}
+
+template <int A>
+__device__ __forceinline__ void vtrace_step(Carry& k, const Scalars& s, bool own, bool opp, float v, float reward,
+                                            float cs, float inv_mu, float ent, const float (&elp)[A],
+                                            const float (&a_oh)[A], float& vt_out, float (&lo_out)[A]) {
+    float vt, q_tail, lo[A];
+    vtrace_scan_step(k, s, own, opp, v, reward, cs, ent, vt, q_tail);
+    learning_output_row<A>(v, elp, a_oh, inv_mu, q_tail, lo);
+#pragma unroll
+    for (int a = 0; a < A; ++a) lo_out[a] = own ? lo[a] : 0.f;
+    vt_out = own ? vt : 0.f;
 }
 
 // vtrace.py:180-204: sum(a_oh * pi) * valid + (1 - valid)
@@ -224,7 +239,12 @@ template <int A>
 __global__ void __launch_bounds__(kLearnerBlock) learner_targets_kernel(rnad_learner_io io, rnad_learner_params p,
                                                                          int T, int64_t B, float* partials) {
     const int32_t* cnt = io.global_counts != nullptr ? io.global_counts : io.counts;
-    const float N[2] = {fmaxf((float)cnt[0], 1.f), fmaxf((float)cnt[1], 1.f)};
+    float N[2] = {1.f, 1.f};                       // unnormalised mode: the caller divides by the step counts later
+    if (!io.unnormalised) {
+        N[0] = fmaxf((float)cnt[0], 1.f);
+        N[1] = fmaxf((float)cnt[1], 1.f);
+    }
+    if (p.alpha_dev != nullptr) p.alpha = *p.alpha_dev;
     Scalars s;
     s.neg_eta = -p.eta;
     s.lambda_ = p.lambda_;
@@ -346,8 +366,183 @@ __global__ void __launch_bounds__(kLearnerBlock) learner_targets_kernel(rnad_lea
     }
 }
 
+// The same computation cut the way the north star words it: everything that is independent per (t, b) slot -
+// the reward-transform term, process_policy, the policy ratios, later the NeuRD force and both gradients - runs
+// with ONE THREAD PER SLOT (a block is 32 games x T half-moves; a warp is 32 games of one half-move, so every
+// (T, B, .) access stays coalesced), and only the 5-float carry of the two players' reverse scans is sequential: one
+// thread per (game, player) walks the T slots of its game through shared memory (5 words in, 2 words out per
+// slot).  Against one thread per game this puts T times as many loads in flight and fills the SMs at cfg2
+// (65,536 games were 0.58 waves of 128-thread blocks).  Same operations in the same order: bit-identical outputs.
+constexpr int kTbGames = 32;
+constexpr int kTbMaxT = 32;
+
+template <int A>
+__global__ void __launch_bounds__(kTbGames* kTbMaxT) learner_targets_tb_kernel(rnad_learner_io io, rnad_learner_params p,
+                                                                               int T, int64_t B, float* partials) {
+    __shared__ float s_v[kTbMaxT][kTbGames], s_reward[kTbMaxT][kTbGames], s_cs[kTbMaxT][kTbGames], s_ent[kTbMaxT][kTbGames];
+    __shared__ float s_vt[kTbMaxT][kTbGames], s_q[kTbMaxT][kTbGames];
+    __shared__ int s_flags[kTbMaxT][kTbGames];
+    __shared__ float red[4][kTbMaxT];
+    const int g = threadIdx.x, t = threadIdx.y;
+    const int32_t* cnt = io.global_counts != nullptr ? io.global_counts : io.counts;
+    float N[2] = {1.f, 1.f};
+    if (!io.unnormalised) {
+        N[0] = fmaxf((float)cnt[0], 1.f);
+        N[1] = fmaxf((float)cnt[1], 1.f);
+    }
+    if (p.alpha_dev != nullptr) p.alpha = *p.alpha_dev;
+    Scalars s;
+    s.neg_eta = -p.eta;
+    s.lambda_ = p.lambda_;
+    s.c = p.c;
+    s.rho = p.rho;
+    s.gamma = p.gamma;
+    const float one_minus_alpha = 1.f - p.alpha;
+    const float n_disc = (float)p.n_disc;
+    float lv[2] = {0.f, 0.f}, ln[2] = {0.f, 0.f};
+
+    const int64_t n_tiles = (B + kTbGames - 1) / kTbGames;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int64_t b = tile * kTbGames + g;
+        const bool active = b < B;
+        const int64_t i = (int64_t)t * B + (active ? b : 0);
+        // ---- per-slot part 1: everything the scans need
+        const bool is_valid = active && io.indices[i] != 0;
+        const float val = is_valid ? 1.f : 0.f;
+        const int turn = active ? (int)io.turns[i] : 0;
+        float a_oh[A], mu[A], pi[A], mask[A], L[A], ones[A], prod[A], pt[A], logit[A];
+#pragma unroll
+        for (int a = 0; a < A; ++a) {
+            a_oh[a] = io.actions_oh[i * A + a];
+            mu[a] = io.mu[i * A + a];
+            pi[a] = io.pi[i * A + a];
+            mask[a] = io.masks[i * A + a];
+            logit[a] = io.logit[i * A + a];
+            // rnad.py:382  log_pi - (alpha*log_pi_reg + (1-alpha)*log_pi_reg_)
+            L[a] = sub(io.log_pi[i * A + a],
+                       add(mul(p.alpha, io.log_pi_reg[i * A + a]), mul(one_minus_alpha, io.log_pi_reg_[i * A + a])));
+            ones[a] = 1.f;
+        }
+        const float v_net = io.v_target_net[i];
+        const float reward = io.rewards[i];
+        const float v_learner = io.v[i];
+        process_policy_row<A>(pi, mask, n_disc, p.eps_threshold, pt);
+#pragma unroll
+        for (int a = 0; a < A; ++a) prod[a] = mul(pt[a], L[a]);
+        const float mu_a = select_prob<A>(a_oh, mu, val);
+        const float cs = dvd(select_prob<A>(a_oh, pt, val), mu_a);
+        const float inv_mu = dvd(select_prob<A>(a_oh, ones, val), mu_a);
+        const float ent_base = mul(s.neg_eta, sum_lanes<A>(prod));
+        s_v[t][g] = v_net;
+        s_reward[t][g] = reward;
+        s_cs[t][g] = cs;
+        s_ent[t][g] = ent_base;
+        s_flags[t][g] = (is_valid ? 1 : 0) | (turn << 1);
+        __syncthreads();
+        // ---- the sequential part: one thread per (game, player) walks the game's slots backwards
+        for (int pl = t; pl < 2; pl += blockDim.y) {
+            Carry k;
+            k.reset();
+            for (int tt = T - 1; tt >= 0; --tt) {
+                const int f = s_flags[tt][g];
+                const bool own = (f & 1) && (f >> 1) == pl, opp = (f & 1) && (f >> 1) != pl;
+                const float po = own ? 1.f : (opp ? -1.f : 0.f);   // _player_others (vtrace.py:70-87)
+                const float r = s_reward[tt][g];
+                float vt, q_tail;
+                vtrace_scan_step(k, s, own, opp, s_v[tt][g], pl == 0 ? r : -r, s_cs[tt][g], mul(s_ent[tt][g], po), vt, q_tail);
+                if (own) {
+                    s_vt[tt][g] = vt;
+                    s_q[tt][g] = q_tail;
+                }
+            }
+        }
+        __syncthreads();
+        // ---- per-slot part 2: learning_output of the slot's owner, both losses and their gradients
+        float d_v = 0.f;
+        float d_logit[A];
+#pragma unroll
+        for (int a = 0; a < A; ++a) d_logit[a] = 0.f;
+#pragma unroll
+        for (int pl = 0; pl < 2; ++pl) {
+            const bool own = is_valid && turn == pl;
+            float vt = 0.f, lo[A];
+#pragma unroll
+            for (int a = 0; a < A; ++a) lo[a] = 0.f;
+            if (own) {
+                float elp[A];
+#pragma unroll
+                for (int a = 0; a < A; ++a) elp[a] = mul(mul(s.neg_eta, L[a]), 1.f);
+                vt = s_vt[t][g];
+                learning_output_row<A>(v_net, elp, a_oh, inv_mu, s_q[t][g], lo);
+                // critic (vtrace.py:377-393)
+                const float dv = sub(v_learner, vt);
+                lv[pl] = add(lv[pl], mul(dv, dv));
+                d_v = p.value_weight * 2.f * dv / N[pl];
+                // NeuRD (vtrace.py:355-367, 396-431) with importance_sampling_correction == 1
+                float pq[A], ll[A];
+#pragma unroll
+                for (int a = 0; a < A; ++a) {
+                    pq[a] = mul(pt[a], lo[a]);
+                    ll[a] = mul(logit[a], mask[a]);
+                }
+                const float baseline = sum_lanes<A>(pq);
+                const float mean_logit = dvd(sum_lanes<A>(ll), (float)A);
+                float gg[A], term[A];
+#pragma unroll
+                for (int a = 0; a < A; ++a) {
+                    float adv = sub(lo[a], baseline);
+                    adv = fminf(fmaxf(adv, -p.neurd_clip), p.neurd_clip);
+                    const float lc = sub(logit[a], mean_logit);
+                    const float force = add(lc > -p.beta ? fminf(adv, 0.f) : 0.f, lc < p.beta ? fmaxf(adv, 0.f) : 0.f);
+                    term[a] = mul(mask[a], mul(lc, force));
+                    gg[a] = -mask[a] * force / N[pl];
+                }
+                ln[pl] = add(ln[pl], sum_lanes<A>(term));
+                float gsum = 0.f;
+#pragma unroll
+                for (int a = 0; a < A; ++a) gsum += gg[a];
+#pragma unroll
+                for (int a = 0; a < A; ++a) d_logit[a] = p.neurd_weight * (gg[a] - mask[a] * gsum / (float)A);
+            }
+            if (active) {
+                if (io.v_target[pl]) io.v_target[pl][i] = vt;
+                if (io.has_played[pl]) io.has_played[pl][i] = own ? 1 : 0;
+                if (io.learning_output[pl]) {
+#pragma unroll
+                    for (int a = 0; a < A; ++a) io.learning_output[pl][i * A + a] = lo[a];
+                }
+            }
+        }
+        if (active) {
+            io.d_v[i] = d_v;
+#pragma unroll
+            for (int a = 0; a < A; ++a) {
+                io.d_logit[i * A + a] = d_logit[a];
+                if (io.pi_processed) io.pi_processed[i * A + a] = pt[a];
+            }
+        }
+        // (no third barrier: the next tile's part 1 writes the scan INPUTS, which nobody reads after the second barrier,
+        //  and its scan writes s_vt / s_q only after the next barrier, which every thread reaches after this part 2)
+    }
+
+    // per-block partial sums of the four loss numerators, fixed order -> deterministic totals
+    float vals[4] = {lv[0], lv[1], ln[0], ln[1]};
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const float w = warp_sum(vals[q]);
+        if (g == 0) red[q][t] = w;
+    }
+    __syncthreads();
+    if (t == 0 && g < 4) {
+        float acc = 0.f;
+        for (int w = 0; w < (int)blockDim.y; ++w) acc += red[g][w];
+        partials[blockIdx.x * 4 + g] = acc;
+    }
+}
+
 __global__ void reduce_losses_kernel(const float* __restrict__ partials, int n_blocks, const int32_t* counts,
-                                     const int32_t* global_counts, float* losses) {
+                                     const int32_t* global_counts, float* losses, float* loss_sums) {
     __shared__ float red[4][32];
     const int q = threadIdx.x >> 5, lane = threadIdx.x & 31;   // 4 warps, one per numerator
     float acc = 0.f;
@@ -360,6 +555,10 @@ __global__ void reduce_losses_kernel(const float* __restrict__ partials, int n_b
             float a = 0.f;
             for (int l = 0; l < 32; ++l) a += red[k][l];
             tot[k] = a;
+        }
+        if (loss_sums != nullptr) {       // unnormalised mode: the four numerators (critic p0, p1, NeuRD p0, p1)
+            for (int k = 0; k < 4; ++k) loss_sums[k] = tot[k];
+            return;
         }
         const int32_t* cnt = global_counts != nullptr ? global_counts : counts;
         const float n0 = fmaxf((float)cnt[0], 1.f), n1 = fmaxf((float)cnt[1], 1.f);
@@ -399,10 +598,31 @@ int launch_vtrace(const float* v, const float* valid, const int64_t* player_id, 
 template <int A>
 int launch_learner(const rnad_learner_io& io, const rnad_learner_params& p, int T, int64_t B, float* partials,
                    cudaStream_t st) {
-    const int blocks = blocks_for(B, kLearnerBlock, kMaxLearnerBlocks);
-    learner_targets_kernel<A><<<blocks, kLearnerBlock, 0, st>>>(io, p, T, B, partials);
-    RNAD_CHECK_LAUNCH("learner_targets_kernel");
-    reduce_losses_kernel<<<1, 128, 0, st>>>(partials, blocks, io.counts, io.global_counts, io.losses);
+    static const bool per_game = getenv("RNAD_TARGETS_PER_GAME") != nullptr;   // the previous kernel, for A/B runs
+    int blocks;
+    if (T <= kTbMaxT && !per_game) {
+        // one thread per (t, b) slot.  Every block gets the same number of 32-game tiles (no tail wave): with R blocks
+        // resident at once, n_tiles tiles take ceil(n_tiles / R) rounds, spread over ceil(n_tiles / rounds) blocks
+        const dim3 block(kTbGames, T);
+        int per_sm = 0;
+        int rc = check_cuda(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, learner_targets_tb_kernel<A>,
+                                                                          kTbGames * T, 0), "occupancy(learner_targets_tb)");
+        if (rc) return rc;
+        const int64_t resident = (int64_t)(per_sm > 0 ? per_sm : 1) * sm_count();
+        const int64_t n_tiles = (B + kTbGames - 1) / kTbGames;
+        const int64_t rounds = (n_tiles + resident - 1) / resident;
+        int64_t want = (n_tiles + rounds - 1) / rounds;
+        if (want > kMaxLearnerBlocks) want = kMaxLearnerBlocks;
+        blocks = (int)want;
+        learner_targets_tb_kernel<A><<<blocks, block, 0, st>>>(io, p, T, B, partials);
+        RNAD_CHECK_LAUNCH("learner_targets_tb_kernel");
+    } else {
+        blocks = blocks_for(B, kLearnerBlock, kMaxLearnerBlocks);
+        learner_targets_kernel<A><<<blocks, kLearnerBlock, 0, st>>>(io, p, T, B, partials);
+        RNAD_CHECK_LAUNCH("learner_targets_kernel");
+    }
+    reduce_losses_kernel<<<1, 128, 0, st>>>(partials, blocks, io.counts, io.global_counts, io.losses,
+                                            io.unnormalised ? io.loss_sums : nullptr);
     RNAD_CHECK_LAUNCH("reduce_losses_kernel");
     return RNAD_OK;
 }
@@ -485,13 +705,17 @@ int rnad_learner_targets(const rnad_learner_io* io, const rnad_learner_params* p
     RNAD_REQUIRE(io && p && workspace, "rnad_learner_targets: null pointer");
     RNAD_REQUIRE(io->indices && io->turns && io->mu && io->actions_oh && io->rewards && io->masks && io->logit &&
                      io->pi && io->log_pi && io->v && io->v_target_net && io->log_pi_reg && io->log_pi_reg_ &&
-                     io->d_logit && io->d_v && io->losses && io->counts,
+                     io->d_logit && io->d_v,
                  "rnad_learner_targets: null tensor pointer");
+    RNAD_REQUIRE(io->unnormalised ? io->loss_sums != nullptr : (io->losses && io->counts),
+                 "rnad_learner_targets: null loss / count pointer");
     RNAD_REQUIRE(A >= 1 && A <= RNAD_MAX_ACTIONS, "rnad_learner_targets: %d actions unsupported", A);
     RNAD_REQUIRE(T >= 1 && B >= 1, "rnad_learner_targets: empty trajectory");
     cudaStream_t st = (cudaStream_t)stream;
-    int rc = rnad_count_played(io->indices, io->turns, T, B, io->counts, stream);
-    if (rc) return rc;
+    if (!io->unnormalised) {
+        int rc = rnad_count_played(io->indices, io->turns, T, B, io->counts, stream);
+        if (rc) return rc;
+    }
     RNAD_DISPATCH_A(A, launch_learner<kA>(*io, *p, T, B, (float*)workspace, st));
     return RNAD_EINVAL;
 }

@@ -37,22 +37,13 @@ from environment.tree import Tree
 _game_offset_rank_stride = 1 << 40   # disjoint Philox game ids per data-parallel rank
 
 
-_seed_state = [None, 0]   # torch.initial_seed() the counter belongs to, batches drawn since
-
-
 def _fresh_seed() -> int:
     """
-    A new 62-bit rollout seed per batch, a pure function of torch's seed (so `torch.manual_seed` makes runs
-    reproducible) and of how many batches were drawn since - splitmix64, no tensor op and no device round trip.
+    A new 62-bit rollout seed per batch, drawn from torch's default CPU generator: `torch.manual_seed(s)` - also the
+    same `s` a second time - restarts the sequence, so a seeded run repeats its rollouts.  One scalar draw on the
+    host, no device round trip.
     """
-    base = torch.initial_seed()
-    if _seed_state[0] != base:
-        _seed_state[0], _seed_state[1] = base, 0
-    _seed_state[1] += 1
-    z = (base + _seed_state[1] * 0x9E3779B97F4A7C15) & 0xFFFFFFFFFFFFFFFF
-    z = ((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9) & 0xFFFFFFFFFFFFFFFF
-    z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & 0xFFFFFFFFFFFFFFFF
-    return (z ^ (z >> 31)) >> 2
+    return int(torch.empty((), dtype=torch.int64).random_(0, 1 << 62).item())
 
 
 def _rank() -> int:
@@ -76,7 +67,7 @@ class States:
         self._alive = None           # device int32 counter written by the last transition
         self._terminal = False
         self._t = 0
-        self.seed = _fresh_seed() if seed is None else int(seed)
+        self._seed = None if seed is None else int(seed)   # drawn on first use: containers (sample / collate) never roll out
         self.game_offset = _rank() * _game_offset_rank_stride
 
     @property
@@ -88,6 +79,16 @@ class States:
     @_idx.setter
     def _idx(self, value: torch.Tensor):
         self._idx_tensor = value
+
+    @property
+    def seed(self) -> int:
+        if self._seed is None:
+            self._seed = _fresh_seed()
+        return self._seed
+
+    @seed.setter
+    def seed(self, value):
+        self._seed = int(value)
 
     # -- reference attributes ------------------------------------------------
     @property
@@ -206,7 +207,8 @@ class _TrajectoryArena:
             layout = _LAYOUTS[(t_max, b, a)] = (dict(zip(self.KEYS, offsets)), total)
         self.fields, self.total = layout
         self.arena = torch.empty(self.total + 256, dtype=torch.uint8, device=dev)
-        self.t_last = self.arena[self.total: self.total + 4].view(torch.int32)
+        # rnad_rollout's stats words: [0] = t_eff + 1, [1], [2] = valid slots of player 0 / 1 (the losses' normalisers)
+        self.stats = self.arena[self.total: self.total + 16].view(torch.int32)
         self.views = {}
 
     def pointers(self):
@@ -266,9 +268,9 @@ class Episodes:
         pending = self.__dict__.pop("_pending", None)
         if pending is None:
             return
-        full, t_last = pending
-        self.__dict__["t_eff"] = int(t_last.item())
-        n = self.__dict__["t_eff"] + 1
+        full, stats = pending
+        n = int(stats[0].item())
+        self.__dict__["t_eff"] = n - 1
         for key in _TrajectoryArena.KEYS:
             self.__dict__[key] = full[key][:n]
 
@@ -350,14 +352,15 @@ class Episodes:
                     raise _b200.RnadError(f"uniforms must be ({t_max}+, {b}, 2), got {tuple(uniforms.shape)}")
                 uniforms = uniforms[:t_max].contiguous()
             _, workspace = _rollout_scratch(dev, a, net.width, prec)
-            t_last = out.t_last                                    # this batch's own t_eff word (the call resets it)
+            stats = out.stats                                      # this batch's own stats words (the call resets them)
             L.rnad_rollout(_b200.ptr(packed.ev_tab), _b200.ptr(packed.tr_tab), a, packed.C, ctypes.byref(w), b, t_max,
-                           self.states.seed, self.states.game_offset, _b200.ptr(uniforms), prec, ctypes.byref(traj),
-                           t_last.data_ptr(), _b200.ptr(workspace), _b200.stream())
+                           self.states.seed, None, self.states.game_offset, _b200.ptr(uniforms), prec,
+                           ctypes.byref(traj), stats.data_ptr(), _b200.ptr(workspace), _b200.stream())
         self.precision = precision
         for key in Episodes._LAZY:
             self.__dict__.pop(key, None)             # resolved on first access (see __getattr__)
-        self.__dict__["_pending"] = (out, t_last)
+        self.__dict__["_pending"] = (out, stats)
+        self.__dict__["_rollout_stats"] = stats      # device int32[4]; [1], [2] are what vtrace.count_played would count
         self._q_estimates = None
         self._v_estimates = None
         self.states._idx_tensor, self.states._idx_fill = None, 0    # every game ended on the absorbing node

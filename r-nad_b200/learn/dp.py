@@ -64,3 +64,28 @@ def broadcast_parameters(module: torch.nn.Module, src: int = 0) -> None:
         return
     for t in module.state_dict().values():
         d.broadcast(t, src=src)
+
+
+def barrier() -> None:
+    d = group()
+    if d is not None:
+        d.barrier()
+
+
+def broadcast_object(obj, src: int = 0):
+    """`obj` of rank `src` on every rank (picklable host object)."""
+    d = group()
+    if d is None:
+        return obj
+    box = [obj]
+    d.broadcast_object_list(box, src=src)
+    return box[0]
+
+
+def all_gather_object(obj):
+    d = group()
+    if d is None:
+        return [obj]
+    out = [None] * d.get_world_size()
+    d.all_gather_object(out, obj)
+    return out

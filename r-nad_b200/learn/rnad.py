@@ -197,10 +197,31 @@ class RNaD:
     # ------------------------------------------------------- init / checkpoints
 
     def __initialize(self):
-        """New run: four identical nets + Adam, checkpoint (0, 0).  Existing run: restore params and the latest checkpoint."""
+        """
+        New run: four identical nets + Adam, checkpoint (0, 0).  Existing run: restore params and the latest checkpoint.
+        Under data parallelism rank 0 alone looks at the run directory; the decision (and the checkpoint to resume
+        from) is broadcast, so that every rank takes the same branch and issues the same collectives, and the other
+        ranks read the files only after rank 0 has written them.
+        """
         logging.info("Initializing R-NaD run: {}".format(self.directory_name))
-        os.makedirs(self.directory, exist_ok=True)
-        saved_updates = [int(os.path.relpath(f.path, self.directory)) for f in os.scandir(self.directory) if f.is_dir()]
+        if dp.group() is not None:
+            hashes = dp.all_gather_object(self.tree.hash)
+            assert all(h == hashes[0] for h in hashes), f"the ranks hold different trees (hashes {hashes})"
+        saved_updates, resume_at = [], None
+        if self._is_writer():
+            os.makedirs(self.directory, exist_ok=True)
+            saved_updates = [int(os.path.relpath(f.path, self.directory)) for f in os.scandir(self.directory) if f.is_dir()]
+            if saved_updates:
+                m = max(saved_updates)
+                last_update = os.path.join(self.directory, str(m))
+                checkpoints = [int(os.path.relpath(f.path, last_update)) for f in os.scandir(last_update) if not f.is_dir()]
+                if checkpoints:
+                    resume_at = (m, max(checkpoints))
+                elif m == 0:
+                    saved_updates = []      # an interrupted first start left '0/' without a checkpoint: start over
+                else:
+                    raise FileNotFoundError(f"{last_update} holds no checkpoint")
+        saved_updates, resume_at = dp.broadcast_object((saved_updates, resume_at))
         if not saved_updates:
             self.tree_hash = self.tree.hash
             if self._is_writer():
@@ -224,6 +245,7 @@ class RNaD:
             self.m = 0
             self.n = 0
             self.__save_checkpoint()
+            dp.barrier()                        # checkpoint 0/0 exists before anybody may want it (use_same_init_net_as)
         else:
             params_dict = torch.load(os.path.join(self.directory, "params"), weights_only=False)
             for key, value in params_dict.items():
@@ -239,11 +261,10 @@ class RNaD:
                 self.__dict__[key] = value
             if self._is_writer():
                 torch.save(params_dict, os.path.join(self.directory, "params"))
-            self.m = max(saved_updates)
-            last_update = os.path.join(self.directory, str(self.m))
-            checkpoints = [int(os.path.relpath(f.path, last_update)) for f in os.scandir(last_update) if not f.is_dir()]
-            self.n = max(checkpoints)
+            self.m, self.n = resume_at
             self.__load_checkpoint(self.m, self.n)
+            for module in (self.net, self.net_target, self.net_reg, self.net_reg_):
+                dp.broadcast_parameters(module)   # same collectives on both branches; a no-op in content
 
         if self.wandb:
             import wandb
@@ -343,6 +364,9 @@ class RNaD:
                     _, _, pi_target, _ = self.net_target.forward_batch(episodes)
                 valid = (episodes.indices != 0).to(torch.float)
                 masks = episodes.masks
+                # the fused engine ran on the full-length (t_max) tensors; the log is over the stored t_eff + 1 half-moves
+                n_t = valid.shape[0]
+                logit, pi, pi_target = logit[:n_t], pi[:n_t], pi_target[:n_t]
                 total_norm = torch.sqrt(sum(p.grad.detach().pow(2).sum() for p in self.net.parameters())).item()
                 logit_mean = logit.mean().item()
                 uniform_policy = torch.nn.functional.normalize(masks, p=1, dim=-1)

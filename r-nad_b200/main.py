@@ -9,6 +9,10 @@ presets and one process per GPU when launched under torchrun:
     python main.py                               # reference defaults (3x3, depth <= 4, B=512)
     python main.py --preset cfg2 --etas 0.2      # depth 4, branching 3, chance 2, B=65536
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 main.py --preset cfg2
+
+Under torchrun every rank must hold the SAME tree and write into the SAME run directories: the tree seed (drawn by
+rank 0 when --seed is not given) and the timestamp of the directory names are broadcast from rank 0, and
+`RNaD.__initialize` asserts that the trees' hashes agree.
 """
 
 import argparse
@@ -71,21 +75,26 @@ def main():
 
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=device)
-    if args.seed is not None:
+    import learn.dp as dp
+
+    seed = args.seed
+    if world > 1 and seed is None:
+        seed = int.from_bytes(os.urandom(4), "little")    # rank 0's draw wins: the ranks must build the same tree
+    seed, timestamp = dp.broadcast_object((seed, str(int(time()))))
+    if seed is not None:
         import numpy as np
         import random as pyrandom
 
-        np.random.seed(args.seed)
-        pyrandom.seed(args.seed)
-        torch.manual_seed(args.seed)          # same tree on every rank
+        np.random.seed(seed)
+        pyrandom.seed(seed)
+        torch.manual_seed(seed)               # same tree on every rank
 
     tree = build_tree(args.preset, device, load=args.load_tree)
-    if args.seed is not None:
-        torch.manual_seed(args.seed * 1000 + int(os.environ.get("RANK", "0")))   # different games per rank
+    if seed is not None:
+        torch.manual_seed(seed * 1000 + int(os.environ.get("RANK", "0")))   # different games per rank
     if int(os.environ.get("RANK", "0")) == 0 and not args.load_tree:
         tree.save(args.save_tree)
 
-    timestamp = str(int(time()))
     for i, eta in enumerate(args.etas):
         same_init_net = None if i == 0 else f"{timestamp}-eta={args.etas[0]}"
         trial = RNaD(

@@ -137,19 +137,36 @@ TOL_TC_MEAN = 5e-6
 SECOND_LAYER = {"tf32": "fp32", "tf32x2": "tf32"}
 
 
-def check_rollout_against_oracle(ep, tables, w, seed=None, uniforms=None, game_offset=0, tol=None, precision=None):
+class _GameSubset:
+    """The trajectory of a subset of the batch's games (columns `games` of every (T, B, ...) tensor), on the CPU."""
+
+    def __init__(self, ep, games):
+        self.t_eff, self.batch_size, self.full_batch_size = ep.t_eff, len(games), ep.batch_size
+        sel = torch.as_tensor(games, dtype=torch.long, device=ep.indices.device)
+        for key in ("indices", "turns", "observations", "masks", "policy", "values", "actions", "rewards"):
+            setattr(self, key, getattr(ep, key).index_select(1, sel).cpu())
+
+
+def check_rollout_against_oracle(ep, tables, w, seed=None, uniforms=None, game_offset=0, tol=None, precision=None,
+                                 games=None):
     """
     Replays a GPU trajectory on the CPU oracle, half-move by half-move: every gather,
     mask and reward must be bit-exact, the net outputs within `tol`, and every sampled
     action / chance outcome must be exactly the inverse-CDF choice at the same uniform
-    (for actions: of the policy the kernel itself recorded).
+    (for actions: of the policy the kernel itself recorded).  `games`: replay only these
+    games of the batch (sorted indices) - the launch is the full batch, the CPU replay a sample.
     """
+    if games is not None:
+        games = np.asarray(games)
+        if uniforms is not None:
+            uniforms = uniforms[:, games]
+        ep = _GameSubset(ep, games)
     T = ep.t_eff + 1
     B = ep.batch_size
     A = tables["legal"].shape[-1]
     idx = torch.ones(B, dtype=torch.int64)
     row = None
-    games = np.arange(game_offset, game_offset + B)
+    games = (np.arange(B) if games is None else games) + game_offset
     assert ep.indices.dtype == torch.int64 and ep.turns.dtype == torch.int64
     assert tuple(ep.observations.shape) == (T, B, 2, A, A)
     for s in range(T):
@@ -185,7 +202,7 @@ def check_rollout_against_oracle(ep, tables, w, seed=None, uniforms=None, game_o
             idx, rew, _ = orc.step(tables["index"], tables["value"], tables["chance"], idx, row, act, uc)
             assert torch.equal(cpu(ep.rewards[s]), rew)
     assert bool((idx == 0).all()), "rollout stopped before every game was terminal"
-    if T > 0:
+    if T > 0 and B == getattr(ep, "full_batch_size", B):
         assert bool((cpu(ep.indices[T - 1]) != 0).any()), "t_eff overshoots the last live half-move"
 
 

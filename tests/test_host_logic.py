@@ -140,7 +140,7 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), name
     L = _b200.lib()
-    assert L.rnad_version() == 100
+    assert L.rnad_version() == 200
     evs, trs = ctypes.c_int(), ctypes.c_int()
     L.rnad_packed_strides(3, 2, ctypes.byref(evs), ctypes.byref(trs))
     assert (evs.value, trs.value) == (12, 8)
