@@ -104,7 +104,9 @@ def profiled_dram_traffic(kernel, config):
     The capture is of bench.py at cfg2 with a warm L2: most of the 69 MB trajectory is still in the 126 MB L2
     when the kernel ends, so this is a lower bound of the traffic that eventually reaches HBM.
     """
-    path = os.path.join(REPO, "profiles", f"r01_{kernel}.md")
+    path = os.path.join(REPO, "profiles", f"r02_{kernel}.md")
+    if not os.path.exists(path):
+        path = os.path.join(REPO, "profiles", f"r01_{kernel}.md")
     if config != "cfg2" or not os.path.exists(path):
         return None
     total = 0.0
@@ -278,10 +280,22 @@ def cpu_rollout_baseline(tree_tables, weights, a, batch, t_max, budget_s, thread
     return steps_done / elapsed, done, elapsed
 
 
+def learner_algorithmic(a, width=256):
+    """Algorithmic bytes and flops per trajectory row (one (t, b) slot) of the learner's kernels."""
+    kin = 2 * a * a
+    return {
+        # obs read; logit, pi, log_pi, log_pi_reg, log_pi_reg_ (A floats each), v, v_target written
+        "forward": {"bytes": 4 * kin + 5 * 4 * a + 8, "flops": 5 * 2 * kin * width + 2 * width * (2 + 3 * a)},
+        "targets": {"bytes": 44 + 32 * a, "flops": 80},
+        # obs, d_logit, d_v read; recompute of two trunks, dW1 | db1, dW2, (g W2)^T
+        "backward": {"bytes": 4 * kin + 4 * a + 4, "flops": 2 * 2 * kin * width + 2 * 2 * (kin + 1) * width + 2 * 2 * width * (1 + a)},
+    }
+
+
 def run_native(args):
     import torch.distributed as dist
 
-    from environment.episode import Episodes
+    from environment.episode import SelfPlay
     from learn.rnad import RNaD
     from nn.net import MLP
 
@@ -306,8 +320,6 @@ def run_native(args):
     if args.batch:
         batch = args.batch
     if args.config in FAST_TREE_CONFIGS:
-        from environment.tree import Tree
-
         tree = fast_tree(args.config, depth, a, c, dev)
         tables = None                            # copied to the host only if the CPU baseline runs
         n_nodes = int(tree.index_tensor.shape[0])
@@ -325,7 +337,6 @@ def run_native(args):
     precision = args.precision
     runner = RolloutRunner(tree, net, batch, precision)
     T = runner.T
-    env_steps = batch * T                       # regular tree: every (t, b) slot is a valid env step (ragged: counted below)
 
     flush_buf = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)
 
@@ -338,37 +349,59 @@ def run_native(args):
     # ---- value: kernel throughput, everything resident
     kernel_ms, _ = timed_steps(runner.launch, args.steps, args.warmup, flush, barrier)
     assert int(runner.stats[0].item()) == T
-    # one env step = one VALID (t, b) slot: all of them on a regular tree, counted on the last rollout of a ragged one
-    env_steps = int((runner.out["indices"] != 0).sum().item())
+    # one env step = one VALID (t, b) slot: all of them on a regular tree, counted by the kernel itself on a ragged one
+    env_steps = int(runner.stats[1].item()) + int(runner.stats[2].item())
+    assert env_steps == int((runner.out["indices"] != 0).sum().item())
     assert env_steps == batch * T or args.config == "cfg4"
 
-    # ---- e2e: public API with host buffers
-    # the actor's parameters become views of one flat device buffer, so that a fresh set of weights from the host
-    # (a learner elsewhere, a checkpoint) is ONE pinned host -> device copy
+    # ---- the same kernel, same precision as the reference's arithmetic: the fp32 validation engine
+    fp32 = None
+    if args.fp32_steps > 0 and runner.L.rnad_rollout_workspace_bytes(a, 256, 0) == 0:
+        runner32 = RolloutRunner(tree, net, batch, "fp32")
+        ms32, _ = timed_steps(runner32.launch, args.fp32_steps, 3, flush, barrier)
+        fp32 = {"ms_per_step": ms32 / args.fp32_steps, "steps": args.fp32_steps, "kernel": "rollout_fp32_kernel",
+                "what": "the same rollout with the net in fp32 on the CUDA cores (the reference's arithmetic; the "
+                        "validation engine that reproduces the reference's Episodes under equal uniforms)"}
+        del runner32
+
+    # ---- sustained: back-to-back rollouts for >= 1 s (no L2 flush in between: the 2 MB tables stay L2-resident as they
+    # do in training, the 69 MB trajectory is rewritten every launch), one event pair around the whole run
+    sustained = None
+    if args.sustained_s > 0:
+        n_sus = max(50, int(args.sustained_s * 1e3 / (kernel_ms / args.steps)))
+        sus_sampler = ClockSampler(local_rank)
+        torch.cuda.synchronize()
+        barrier()
+        sus_sampler.start()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n_sus):
+            runner.launch()
+        e1.record()
+        e1.synchronize()
+        sus_ms = e0.elapsed_time(e1)
+        sustained = {"launches": n_sus, "seconds": sus_ms / 1e3, "ms_per_step": sus_ms / n_sus, "clocks": sus_sampler.stop()}
+
+    # ---- e2e: the public API with host buffers: every step the actor's weights arrive from pinned HOST memory and the
+    # per-game returns go back to pinned host memory; environment.episode.SelfPlay replays copy -> rollout -> copy as
+    # one CUDA graph (timed region = control launch + replay + stream synchronize)
     flat_host = torch.cat([v.flatten() for v in weights_cpu.values()]).pin_memory()
-    flat_dev = torch.empty_like(flat_host, device=dev)
-    flat_dev.copy_(flat_host)
-    offset = 0
-    with torch.no_grad():
-        for p in net.parameters():               # registration order == state_dict order
-            p.data = flat_dev[offset: offset + p.numel()].view_as(p)
-            offset += p.numel()
     returns_host = torch.empty(batch, dtype=torch.float32).pin_memory()
     h2d_bytes = flat_host.numel() * 4
     d2h_bytes = batch * 4                       # per-game returns
+    actor = MLP(a, 256, device=dev)
+    actor.load_state_dict(net.state_dict())
+    play = SelfPlay(tree, batch, actor, precision=precision, weights_host=flat_host, returns_host=returns_host)
 
     def e2e_step():
-        flat_dev.copy_(flat_host, non_blocking=True)
-        ep = Episodes(tree, batch)
-        ep.generate(net, precision=precision)
-        # per-game returns from the full-length reward tensor (slots past a game's end hold zeros): one device -> host
-        # read per step; the trajectory length itself resolves lazily (Episodes.t_eff) and is not needed here
-        returns_host.copy_(ep.full("rewards").sum(0), non_blocking=True)
+        play.play()
         torch.cuda.current_stream().synchronize()
 
     e2e_ms, _ = timed_steps(e2e_step, args.steps, args.warmup, flush, barrier)
+    assert play.graph is not None
+    assert abs(float(returns_host.abs().sum()) - float((play.arena["rewards"].abs().sum()).item())) < 1e-3 * batch
 
-    # ---- learner: one full update through the public RNaD loop body
+    # ---- learner: full updates through the public RNaD loop body (learn/fused.py::LearnerStep: one CUDA graph)
     trial = RNaD(tree=tree, device=dev, directory_name=f"bench_rank{rank}", batch_size=batch, eta=0.2, lr=1e-3,
                  gamma_averaging=0.01, logit_clip=2, net_params={"type": "MLP", "max_actions": a, "width": 256})
     trial.net = net
@@ -385,20 +418,36 @@ def run_native(args):
         loss_host.copy_(trial.last_losses, non_blocking=True)
         torch.cuda.current_stream().synchronize()
 
-    learner_steps = max(3, args.steps // 2)
+    learner_steps = max(args.learner_steps, args.steps)
     learner_ms, _ = timed_steps(learner_step, learner_steps, max(3, args.warmup), flush, barrier)
+    step_engine = trial._step
+    # free-running: updates enqueued back to back, one synchronisation at the end (what RNaD.run does between logs)
+    torch.cuda.synchronize()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(learner_steps):
+        trial.learner_step(alpha=0.5)
+    e1.record()
+    e1.synchronize()
+    free_ms = e0.elapsed_time(e1)
+    if step_engine is not None:
+        step_engine.check()
+    per_kernel = step_engine.profile(reps=20, between=flush) if (step_engine is not None and world == 1) else None
     clocks = sampler.stop()
 
     # ---- max over ranks
-    times = torch.tensor([kernel_ms, e2e_ms, learner_ms], dtype=torch.float64, device=dev)
+    times = torch.tensor([kernel_ms, e2e_ms, learner_ms, free_ms], dtype=torch.float64, device=dev)
+    counts = torch.tensor([env_steps], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
-    kernel_ms, e2e_ms, learner_ms = (float(x) for x in times.tolist())
+        dist.all_reduce(counts)                  # ragged trees: the ranks' valid slots differ
+    kernel_ms, e2e_ms, learner_ms, free_ms = (float(x) for x in times.tolist())
+    total_env_steps = int(counts.item()) if world > 1 else env_steps
 
     result = None
     if rank == 0:
         peaks = measured_peaks()
-        total_env_steps = env_steps * world
         value = total_env_steps * args.steps / (kernel_ms / 1e3)
         per_launch_s = kernel_ms / 1e3 / args.steps
         bytes_per_launch = algorithmic_bytes_per_env_step(a, c) * env_steps
@@ -417,7 +466,36 @@ def run_native(args):
                                                                         args.cpu_budget, threads)
             cpu = {"value": cpu_value, "unit": "env_steps/s", "cores": threads, "kind": "port",
                    "sample": f"{cpu_rollouts} rollouts of {cpu_batch} games x {T} half-moves on the same tree and net "
-                             f"({cpu_elapsed:.1f} s, torch-CPU ops, {threads} threads)"}
+                             f"({cpu_elapsed:.1f} s, oracle/ restatement, torch-CPU ops, {threads} threads); the unmodified "
+                             f"reference itself is timed by `bench.py --impl reference` (kind \"reference\")"}
+        learner = {"updates_per_sec": learner_steps / (learner_ms / 1e3), "ms_per_update": learner_ms / learner_steps,
+                   "env_steps_per_sec": total_env_steps * learner_steps / (learner_ms / 1e3),
+                   "steps": learner_steps,
+                   "free_running": {"ms_per_update": free_ms / learner_steps, "updates_per_sec": learner_steps / (free_ms / 1e3),
+                                    "what": "the same updates enqueued back to back, one synchronisation at the end"},
+                   "engine": "LearnerStep (one CUDA graph per update)" if step_engine is not None and step_engine.graph is not None
+                             else "step-by-step path",
+                   "exchange": (f"inside rnad_learner_tail over CUDA-IPC peer memory, {world} ranks, "
+                                f"{2 * step_engine.n_params + 8} floats per rank and step, no NCCL call in the step")
+                               if (step_engine is not None and step_engine.exchange is not None) else "none (one rank)",
+                   "what": "RNaD.learner_step: rollout + 4x forward_batch + fused v-trace/NeuRD targets + backward"
+                           + (" + gradient exchange" if world > 1 else "") + " + clip + Adam + target average, "
+                           "losses read back to the host every step"}
+        if per_kernel is not None:
+            rows = batch * T
+            alg = learner_algorithmic(a)
+            kernels = {"rollout": {"ms": per_kernel["rollout"]},
+                       "pack": {"ms": per_kernel["pack"], "bound": "off the critical path (side stream, under the rollout)"},
+                       "tail": {"ms": per_kernel["tail"], "bound": "latency (one 8-CTA cluster, 43 KB of parameters)"}}
+            for name in ("forward", "targets", "backward"):
+                sec = per_kernel[name] / 1e3
+                gbs, tf = alg[name]["bytes"] * rows / sec / 1e9, alg[name]["flops"] * rows / sec / 1e12
+                kernels[name] = {"ms": per_kernel[name], "achieved_GBps": gbs, "frac_of_hbm": gbs / peaks["hbm_gbs"],
+                                 "achieved_TFLOPs": tf, "frac_of_bf16_peak": tf / peaks["bf16_tflops"],
+                                 "bound": "hbm" if name == "targets" else "tensor",
+                                 "algorithmic_bytes_per_row": alg[name]["bytes"], "algorithmic_flops_per_row": alg[name]["flops"]}
+            learner["roofline"] = {"kernels": kernels, "sum_of_kernels_ms": sum(v for k, v in per_kernel.items() if k != "pack"),
+                                   "how": "each C-ABI call of the step timed alone with CUDA events, 20 launches, L2 flushed"}
         result = {
             "metric": "self_play_env_steps_per_sec", "value": value, "unit": "env_steps/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -425,17 +503,16 @@ def run_native(args):
             "vs_baseline": None, "dtype": {"tf32": "tf32 (tcgen05, fp32 accumulate) + fp32", "tf32x2": "tf32 (tcgen05, fp32 accumulate)",
                                           "fp32": "fp32"}[precision],
             "data": "synthetic",
-            "config": {"workload": f"{args.config}: depth={depth} max_actions={a} max_transitions={c} regular tree "
-                                   f"({n_nodes} nodes), batch={batch} games per GPU, T={T} half-moves, MLP width 256, "
-                                   f"fused rollout+net kernel ({precision})",
-                       "env_steps_per_step": total_env_steps, "l2": "256 MiB buffer written between timed steps",
+            "config": workload_config(args.config, depth, a, c, n_nodes, batch, T),
+            "engine": {"rollout_kernel": kernel_name, "precision": precision, "env_steps_per_step": total_env_steps,
                        "partitioning": f"games sharded, {world} rank(s), no data-path collective in the rollout"},
             "clocks": clocks,
             "e2e": {"value": total_env_steps * args.steps / (e2e_ms / 1e3), "unit": "env_steps/s",
                     "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
                     "ms_per_step": e2e_ms / args.steps,
-                    "what": "net weights copied from pinned host memory, Episodes.generate(net), per-game returns "
-                            "read back to the host"},
+                    "what": "environment.episode.SelfPlay.play(): net weights copied from pinned host memory, rollout, "
+                            "per-game returns copied back to pinned host memory - one CUDA graph per batch - then a "
+                            "stream synchronize"},
             "gpu_launches": args.steps * runner.launches_per_step,
             "roofline": {"bound": "hbm", "achieved": achieved_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                          "frac": achieved_gbs / peaks["hbm_gbs"],
@@ -445,15 +522,22 @@ def run_native(args):
                          "peak_source": peaks["source"]},
             "roofline_tensor": {"achieved": tflops, "unit": "TFLOP/s (algorithmic MLP flops)",
                                 "peak_bf16": peaks["bf16_tflops"], "frac_of_bf16_peak": tflops / peaks["bf16_tflops"]},
-            "learner": {"updates_per_sec": learner_steps / (learner_ms / 1e3), "ms_per_update": learner_ms / learner_steps,
-                        "env_steps_per_sec": total_env_steps * learner_steps / (learner_ms / 1e3),
-                        "steps": learner_steps,
-                        "what": "RNaD.learner_step: rollout + 4x forward_batch + fused v-trace/NeuRD targets + "
-                                "backward" + (" + NCCL grad all-reduce" if world > 1 else "") + " + Adam + EMA, "
-                                "losses read back each step"},
+            "learner": learner,
             "cpu_baseline": cpu,
         }
+        if fp32 is not None:
+            fp32["value"] = total_env_steps / (fp32["ms_per_step"] / 1e3)
+            fp32["unit"] = "env_steps/s"
+            result["fp32"] = fp32
+        if sustained is not None:
+            sustained["value"] = total_env_steps / (sustained["ms_per_step"] / 1e3)
+            sustained["unit"] = "env_steps/s"
+            sustained["what"] = ("rollouts launched back to back for about a second (no L2 flush in between), one "
+                                 "CUDA event pair around the run, clocks sampled during it")
+            result["sustained"] = sustained
         print(json.dumps(result), flush=True)
+    if step_engine is not None:
+        step_engine.close()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -634,6 +718,9 @@ def main():
     ap.add_argument("--precision", default="tf32x2", choices=["tf32", "tf32x2", "fp32"])
     ap.add_argument("--cpu-budget", type=float, default=15.0, help="seconds of CPU work for cpu_baseline")
     ap.add_argument("--reference-batch", type=int, default=65536)
+    ap.add_argument("--learner-steps", type=int, default=200, help="timed learner updates (at least --steps)")
+    ap.add_argument("--fp32-steps", type=int, default=10, help="timed rollouts of the fp32 engine (0 = skip)")
+    ap.add_argument("--sustained-s", type=float, default=1.0, help="seconds of back-to-back rollouts (0 = skip)")
     ap.add_argument("--emit-tree", default="", help="(internal) write the configuration's tree tables to this file")
     args = ap.parse_args()
     if args.emit_tree:

@@ -77,8 +77,9 @@ RNAD_API int rnad_tree_pack(const int64_t* index, const float* value, const floa
  * K1a  States.observations (episode.py:46-68): obs (B,2,A,A) f32 for the side
  * to move (`turn` 0 = row, 1 = column; all games share it, episode.py:96-98)
  * and the mover's legal-action mask obs[:,1,:,0] (B,A) f32 (may be NULL).
+ * S = number of nodes in ev_tab; idx (B) int32 node ids in [0, S).
  * ------------------------------------------------------------------------ */
-RNAD_API int rnad_observe(const uint32_t* ev_tab, int A, const int32_t* idx, int turn, int64_t B,
+RNAD_API int rnad_observe(const uint32_t* ev_tab, int A, int64_t S, const int32_t* idx, int turn, int64_t B,
                  float* obs, float* mask, void* stream);
 
 /* ------------------------------------------------------------------------
@@ -179,7 +180,9 @@ RNAD_API int rnad_vtrace(const float* v, const float* valid, const int64_t* play
  * pi_processed (T,B,A), v_target[2] (T,B), has_played[2] (T,B) i64,
  * learning_output[2] (T,B,A).  losses: device float[2] = {loss_v, loss_nerd};
  * counts: device int32[2] = {N_0, N_1} (sum of has_played).
- * workspace: device scratch of rnad_learner_targets_workspace(T,B) bytes. */
+ * workspace: 16-byte aligned device scratch of rnad_learner_targets_workspace(T,B) bytes, ZEROED once by the caller
+ * before its first use (it holds the ticket by which the last block of a launch knows it is the last and adds the
+ * per-block loss sums in block order; every launch leaves it zeroed again). */
 typedef struct rnad_learner_io {
     const int64_t* indices; const int64_t* turns; const float* mu; const float* actions_oh;
     const float* rewards; const float* masks;
@@ -257,6 +260,19 @@ RNAD_API int rnad_learner_backward(const float* observations, int64_t N, int A, 
 RNAD_API int rnad_learner_backward_split(const float* observations, int T, int64_t B, int A, const rnad_mlp_weights* net,
                                 const float* d_logit, const float* d_v, float* player_grads,
                                 void* workspace, void* stream);
+
+/* The weight images (MMA operand order) of rnad_learner_forward and rnad_learner_backward(_split) depend only on the
+ * nets: rnad_learner_pack writes them into `workspace` (what those calls otherwise do first), and the *_prepacked
+ * variants then skip it - so that a captured learner step can pack on a side stream while the rollout runs. */
+RNAD_API int rnad_learner_pack(int A, const rnad_mlp_weights* net, const rnad_mlp_weights* target,
+                      const rnad_mlp_weights* reg, const rnad_mlp_weights* reg_, void* workspace, void* stream);
+RNAD_API int rnad_learner_forward_prepacked(const float* observations, int64_t N, int A,
+                         const rnad_mlp_weights* net, const rnad_mlp_weights* target,
+                         const rnad_mlp_weights* reg, const rnad_mlp_weights* reg_,
+                         const rnad_learner_fwd_out* out, void* workspace, void* stream);
+RNAD_API int rnad_learner_backward_split_prepacked(const float* observations, int T, int64_t B, int A,
+                                const rnad_mlp_weights* net, const float* d_logit, const float* d_v,
+                                float* player_grads, void* workspace, void* stream);
 
 /* ------------------------------------------------------------------------
  * One learner step as a replayable unit (rnad.py:495-526 loop body): the per-step scalars live in a device

@@ -29,6 +29,7 @@ EXPORTS = (
     "rnad_process_policy", "rnad_vtrace", "rnad_learner_targets_workspace", "rnad_count_played",
     "rnad_learner_targets", "rnad_learner_mlp_supported", "rnad_learner_mlp_workspace_bytes",
     "rnad_learner_param_count", "rnad_learner_forward", "rnad_learner_backward", "rnad_learner_backward_split",
+    "rnad_learner_pack", "rnad_learner_forward_prepacked", "rnad_learner_backward_split_prepacked",
     "rnad_step_control", "rnad_learner_tail", "rnad_xchg_bytes", "rnad_xchg_create", "rnad_xchg_open", "rnad_xchg_close",
     "rnad_xchg_destroy",
 )
@@ -104,7 +105,7 @@ def lib():
     L.rnad_device_sm_count.restype = c_int
     L.rnad_packed_strides.argtypes = [c_int, c_int, POINTER(c_int), POINTER(c_int)]
     L.rnad_tree_pack.argtypes = [c_void_p] * 5 + [c_int64, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]
-    L.rnad_observe.argtypes = [c_void_p, c_int, c_void_p, c_int, c_int64, c_void_p, c_void_p, c_void_p]
+    L.rnad_observe.argtypes = [c_void_p, c_int, c_int64, c_void_p, c_int, c_int64, c_void_p, c_void_p, c_void_p]
     L.rnad_step.argtypes = [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_uint64, c_int, c_int64,
                             c_int64, c_void_p, c_void_p, c_void_p]
     L.rnad_sample_categorical.argtypes = [c_void_p, c_int64, c_int, c_void_p, c_uint64, c_int, c_int64, c_void_p,
@@ -132,6 +133,9 @@ def lib():
                                         c_void_p, c_void_p]
     L.rnad_learner_backward_split.argtypes = [c_void_p, c_int, c_int64, c_int, POINTER(MlpWeights), c_void_p, c_void_p,
                                               c_void_p, c_void_p, c_void_p]
+    L.rnad_learner_backward_split_prepacked.argtypes = L.rnad_learner_backward_split.argtypes
+    L.rnad_learner_forward_prepacked.argtypes = L.rnad_learner_forward.argtypes
+    L.rnad_learner_pack.argtypes = [c_int] + [POINTER(MlpWeights)] * 4 + [c_void_p, c_void_p]
     L.rnad_step_control.argtypes = [c_void_p, c_uint64, c_float, c_void_p]
     L.rnad_learner_tail.argtypes = [POINTER(TailArgs), c_void_p]
     L.rnad_xchg_bytes.restype = c_int64

@@ -14,7 +14,10 @@
 //   warps 4..11   relu epilogue in tensor memory (bias via the constant-1 input column, else one FADD)
 //   warps 0..3    one thread per row: observation -> tensor memory (tf32); one tile later the heads: masked softmax /
 //                 log-softmax (net.py:76-80) of the three logit sets, the two values, written time-major.
-// Reference: nn/net.py:64-85.  Serves 2 <= A <= 3 (A = 4 keeps learner_fwd_kernel: its weights do not fit here).
+// Reference: nn/net.py:64-85.  A <= 3: one launch over all five trunks.  A = 4: the five first layers (160 KB) and
+// second layers do not fit one CTA's shared memory and target value + two logit sets need nine accumulator columns, so
+// the kernel is launched twice - the learner's two trunks, then target / reg / reg_ (v_target and logit_reg in the
+// first accumulator, logit_reg_ in the second); the second pass re-reads the observations (128 of ~330 bytes per row).
 #include "tc_common.cuh"
 #include "tc_pipe.cuh"
 
@@ -30,13 +33,23 @@ using namespace rnad::tcp;
 constexpr int kRowWarps = 4, kEpiWarps = RNAD_FWD2_EPI_WARPS, kMmaWarps = 4;   // 8 or 16 epilogue warps (64 or 32 columns each)
 constexpr int kMmaWarp = kRowWarps + kEpiWarps;
 constexpr int kThreads = (kMmaWarp + kMmaWarps) * 32;
-constexpr int kChunk = 128, kSlots = 3, kTrunks = 5;
-constexpr int kItemsPerTile = kTrunks * (kHidden / kChunk);          // 10
+constexpr int kChunk = 128, kSlots = 3, kAllTrunks = 5;
 constexpr int kObsCol = kSlots * kChunk;                              // 2 x 32 columns of observations
 constexpr int kD2Col = kObsCol + 64;                                  // 2 x (16 + 16) columns of accumulators
 
-template <int A>
+// A launch covers the trunks [T0, T0 + NT) of: 0 learner value, 1 learner policy, 2 target value, 3 reg policy, 4 reg_
+// policy.  Which accumulator a trunk adds into, and at which row (= accumulator column) its outputs start:
+//   (T0, NT) = (0, 5): D2a = (v, logit), D2b = (v_target, logit_reg, logit_reg_)          [A <= 3]
+//   (0, 2):            D2a = (v, logit)                                                   [A = 4, first launch]
+//   (2, 3):            D2a = (v_target, logit_reg), D2b = (logit_reg_ from column 1)      [A = 4, second launch]
+template <int A, int T0, int NT>
 struct Plan {
+    static constexpr int kTrunks = NT;
+    static constexpr int kItemsPerTile = NT * (kHidden / kChunk);
+    __host__ __device__ static constexpr bool second_acc(int trunk) { return NT == 5 ? trunk >= 2 : (T0 == 2 && trunk == 4); }
+    __host__ __device__ static constexpr int row0(int trunk) {
+        return (trunk == 0 || trunk == 2) ? 0 : (trunk == 4 && NT == 5 ? 1 + A : 1);
+    }
     static constexpr int KIN = 2 * A * A;
     static constexpr bool kBiasInK = (KIN % 8) != 0;
     static constexpr int KP = round_up(KIN + (kBiasInK ? 1 : 0), 8);
@@ -46,13 +59,13 @@ struct Plan {
     static constexpr int kW1 = 0;                                     // 5 trunks [256 x KP] tf32
     static constexpr int kW2 = kW1 + kTrunks * kTrunkBytes;           // 10 chunks
     static constexpr int kB1 = kW2 + kItemsPerTile * kW2ChunkBytes;   // first-layer biases, 5 x 256 f32
-    static constexpr int kB2 = kB1 + kTrunks * kHidden * 4;           // second-layer biases: 5 x 4 f32
+    static constexpr int kB2 = kB1 + kTrunks * kHidden * 4;           // second-layer biases: 4 f32 per trunk
     static constexpr int kImageBytes = kB2 + kTrunks * 16;
     static constexpr int kBar = round_up(kImageBytes, 8);
     static constexpr int kNumBars = 1 + 2 + 2 + 2 + 4 * kSlots;       // image, obs[2], d2 done[2], d2 free[2], d1[6], relu[6]
     static constexpr int kTmem = kBar + 8 * kNumBars;
     static constexpr int kBytes = kTmem + 16;
-    static_assert(1 + 2 * A <= 8, "target value + two logit sets must fit 8 accumulator columns");
+    static_assert(NT == 5 ? 1 + 2 * A <= 8 : 1 + A <= 8, "the outputs sharing an accumulator must fit its 8 columns");
     static_assert(kBytes <= 227 * 1024, "shared memory plan does not fit");
     static_assert(KP <= 32, "observation columns do not fit");
 };
@@ -64,9 +77,10 @@ struct Out {
     float *logit, *pi, *log_pi, *v, *v_target, *log_pi_reg, *log_pi_reg_;
 };
 
-template <int A>
+template <int A, int T0, int NT>
 __global__ void pack_image_kernel(Nets w, uint8_t* __restrict__ image) {
-    using P = Plan<A>;
+    using P = Plan<A, T0, NT>;
+    constexpr int kTrunks = kAllTrunks;
     const int thread = blockIdx.x * blockDim.x + threadIdx.x, n_threads = gridDim.x * blockDim.x;
     const float* w1[kTrunks] = {w.net.value_fc0_w, w.net.policy_fc0_w, w.target.value_fc0_w, w.reg.policy_fc0_w,
                                 w.reg_.policy_fc0_w};
@@ -76,24 +90,24 @@ __global__ void pack_image_kernel(Nets w, uint8_t* __restrict__ image) {
                                 w.reg_.policy_fc1_w};
     const float* b2[kTrunks] = {w.net.value_fc1_b, w.net.policy_fc1_b, w.target.value_fc1_b, w.reg.policy_fc1_b,
                                 w.reg_.policy_fc1_b};
-    // accumulator row of output o of trunk t: D2a = (v, logit), D2b = (v_target, logit_reg, logit_reg_)
-    const int row0[kTrunks] = {0, 1, 0, 1, 1 + A};
     const int n_out[kTrunks] = {1, A, 1, A, A};
 #pragma unroll
-    for (int t = 0; t < kTrunks; ++t) {
-        pack_trunk_operand<P::KIN, P::KP, P::kBiasInK>(w1[t], b1[t], image + P::kW1 + t * P::kTrunkBytes, thread, n_threads);
-        for (int j = thread; j < kHidden; j += n_threads) reinterpret_cast<float*>(image + P::kB1)[t * kHidden + j] = b1[t][j];
+    for (int lt = 0; lt < NT; ++lt) {
+        const int t = lt, g = T0 + lt;      // local index (position in the image), global trunk
+        const int row0_t = P::row0(g);
+        pack_trunk_operand<P::KIN, P::KP, P::kBiasInK>(w1[g], b1[g], image + P::kW1 + t * P::kTrunkBytes, thread, n_threads);
+        for (int j = thread; j < kHidden; j += n_threads) reinterpret_cast<float*>(image + P::kB1)[t * kHidden + j] = b1[g][j];
         // second layer: per 128-unit half a [16 x 128] K-major operand, rows = accumulator columns.  The first half of a
         // trunk uses rows row0 + o, the second rows 8 + row0 + o (zero elsewhere): the two halves leave their partial
         // sums in separate accumulator columns, added by the output warps in a fixed order, so the result does not
         // depend on the order in which the MMA warps got to issue (bit-reproducible).
         for (int e = thread; e < 2 * 16 * kChunk; e += n_threads) {
             const int half = e / (16 * kChunk), r = (e / kChunk) % 16, k = e % kChunk;
-            const int o = r - (8 * half + row0[t]);
-            const float v = (o >= 0 && o < n_out[t]) ? w2[t][o * kHidden + half * kChunk + k] : 0.f;
+            const int o = r - (8 * half + row0_t);
+            const float v = (o >= 0 && o < n_out[g]) ? w2[g][o * kHidden + half * kChunk + k] : 0.f;
             *reinterpret_cast<float*>(image + P::kW2 + (t * 2 + half) * P::kW2ChunkBytes + operand_offset<kChunk>(r, k)) = to_tf32(v);
         }
-        if (thread < 4) reinterpret_cast<float*>(image + P::kB2)[t * 4 + thread] = thread < n_out[t] ? b2[t][thread] : 0.f;
+        if (thread < 4) reinterpret_cast<float*>(image + P::kB2)[t * 4 + thread] = thread < n_out[g] ? b2[g][thread] : 0.f;
     }
 }
 
@@ -116,11 +130,11 @@ __device__ __forceinline__ void heads(const float (&logit)[A], uint32_t mask_bit
     }
 }
 
-template <int A>
+template <int A, int T0, int NT>
 __global__ void __launch_bounds__(kThreads, 1) learner_fwd_tc2_kernel(const float* __restrict__ obs, int64_t N,
                                                                        const uint8_t* __restrict__ image, Out out) {
-    using P = Plan<A>;
-    constexpr int KIN = P::KIN, KP = P::KP;
+    using P = Plan<A, T0, NT>;
+    constexpr int KIN = P::KIN, KP = P::KP, kItemsPerTile = P::kItemsPerTile;
     extern __shared__ __align__(1024) uint8_t smem[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t bar0 = smem_u32(smem + P::kBar);
@@ -203,7 +217,7 @@ __global__ void __launch_bounds__(kThreads, 1) learner_fwd_tc2_kernel(const floa
             mbar_wait_c(bar_relu(rb), par);
             tc_fence_after();
             if (elect_one()) {
-                const uint32_t d2 = tmem_base + kD2Col + (k_i & 1) * 32 + (c_i >= 4 ? 16 : 0);   // D2a: trunks 0, 1; D2b: 2..4
+                const uint32_t d2 = tmem_base + kD2Col + (k_i & 1) * 32 + (P::second_acc(T0 + (c_i >> 1)) ? 16 : 0);
 #pragma unroll
                 for (int s = 0; s < kChunk / 8; ++s)
                     mma_ts(d2, tmem_base + slot * kChunk + s * 8,
@@ -352,28 +366,35 @@ __global__ void __launch_bounds__(kThreads, 1) learner_fwd_tc2_kernel(const floa
                 if (lane == 0) mbar_arrive(bar_free(kp & 1));
                 if (row_prev >= 0) {
                     const int64_t row = row_prev;
-                    out.v[row] = __uint_as_float(da[0]) + b2[0];
-                    out.v_target[row] = __uint_as_float(db[0]) + b2[2 * 4];
                     float lg[A], pi[A], lp[A];
+                    if (T0 == 0) {               // the learner's trunks: local trunks 0 (value), 1 (policy), both in D2a
+                        out.v[row] = __uint_as_float(da[0]) + b2[0];
 #pragma unroll
-                    for (int a = 0; a < A; ++a) lg[a] = __uint_as_float(da[1 + a]) + b2[1 * 4 + a];
-                    heads<A>(lg, mask_prev, pi, lp);
+                        for (int a = 0; a < A; ++a) lg[a] = __uint_as_float(da[1 + a]) + b2[1 * 4 + a];
+                        heads<A>(lg, mask_prev, pi, lp);
 #pragma unroll
-                    for (int a = 0; a < A; ++a) {
-                        out.logit[row * A + a] = lg[a];
-                        out.pi[row * A + a] = pi[a];
-                        out.log_pi[row * A + a] = lp[a];
+                        for (int a = 0; a < A; ++a) {
+                            out.logit[row * A + a] = lg[a];
+                            out.pi[row * A + a] = pi[a];
+                            out.log_pi[row * A + a] = lp[a];
+                        }
                     }
+                    if (T0 + NT == kAllTrunks) { // target value, reg and reg_ policies: local trunks (2, 3, 4) - T0
+                        constexpr int lt = 2 - T0;
+                        // (0, 5): all three in D2b at columns 0, 1.., 1 + A..;  (2, 3): v_target, logit_reg in D2a, logit_reg_ in D2b
+                        const uint32_t* first = NT == 5 ? db : da;
+                        out.v_target[row] = __uint_as_float(first[0]) + b2[lt * 4];
 #pragma unroll
-                    for (int a = 0; a < A; ++a) lg[a] = __uint_as_float(db[1 + a]) + b2[3 * 4 + a];
-                    heads<A>(lg, mask_prev, pi, lp);
+                        for (int a = 0; a < A; ++a) lg[a] = __uint_as_float(first[1 + a]) + b2[(lt + 1) * 4 + a];
+                        heads<A>(lg, mask_prev, pi, lp);
 #pragma unroll
-                    for (int a = 0; a < A; ++a) out.log_pi_reg[row * A + a] = lp[a];
+                        for (int a = 0; a < A; ++a) out.log_pi_reg[row * A + a] = lp[a];
 #pragma unroll
-                    for (int a = 0; a < A; ++a) lg[a] = __uint_as_float(db[1 + A + a]) + b2[4 * 4 + a];
-                    heads<A>(lg, mask_prev, pi, lp);
+                        for (int a = 0; a < A; ++a) lg[a] = __uint_as_float(db[P::row0(4) + a]) + b2[(lt + 2) * 4 + a];
+                        heads<A>(lg, mask_prev, pi, lp);
 #pragma unroll
-                    for (int a = 0; a < A; ++a) out.log_pi_reg_[row * A + a] = lp[a];
+                        for (int a = 0; a < A; ++a) out.log_pi_reg_[row * A + a] = lp[a];
+                    }
                 }
             }
             mask_prev = mask_now;
@@ -385,42 +406,61 @@ __global__ void __launch_bounds__(kThreads, 1) learner_fwd_tc2_kernel(const floa
     if (warp == kMmaWarp) tmem_dealloc<512>(tmem_base);
 }
 
-template <int A>
-int launch(const float* obs, int64_t N, const Nets& nets, const Out& out, uint8_t* workspace, cudaStream_t st) {
-    using P = Plan<A>;
-    pack_image_kernel<A><<<64, 256, 0, st>>>(nets, workspace);
-    RNAD_CHECK_LAUNCH("learner fwd2 pack_image_kernel");
+// mode: 0 = pack the weight image, then run; 1 = the image is already in the workspace (rnad_learner_pack); 2 = pack only
+template <int A, int T0, int NT>
+int launch_part(const float* obs, int64_t N, const Nets& nets, const Out& out, uint8_t* workspace, cudaStream_t st, int mode) {
+    using P = Plan<A, T0, NT>;
+    if (mode != 1) {
+        pack_image_kernel<A, T0, NT><<<64, 256, 0, st>>>(nets, workspace);
+        RNAD_CHECK_LAUNCH("learner fwd2 pack_image_kernel");
+        if (mode == 2) return RNAD_OK;
+    }
     const size_t smem = P::kBytes > 116 * 1024 ? P::kBytes : 116 * 1024;   // one CTA per SM (all 512 TMEM columns)
-    int rc = check_cuda(cudaFuncSetAttribute(learner_fwd_tc2_kernel<A>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
+    int rc = check_cuda(cudaFuncSetAttribute(learner_fwd_tc2_kernel<A, T0, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
                         "cudaFuncSetAttribute(learner_fwd_tc2)");
     if (rc) return rc;
     int64_t blocks = (N + kTileM - 1) / kTileM;
     if (blocks > sm_count()) blocks = sm_count();
-    learner_fwd_tc2_kernel<A><<<(int)blocks, kThreads, smem, st>>>(obs, N, workspace, out);
+    learner_fwd_tc2_kernel<A, T0, NT><<<(int)blocks, kThreads, smem, st>>>(obs, N, workspace, out);
     RNAD_CHECK_LAUNCH("learner_fwd_tc2_kernel");
     return RNAD_OK;
 }
 
+template <int A>
+int launch(const float* obs, int64_t N, const Nets& nets, const Out& out, uint8_t* workspace, cudaStream_t st, int mode) {
+    if constexpr (A <= 3) {
+        return launch_part<A, 0, 5>(obs, N, nets, out, workspace, st, mode);
+    } else {
+        // two launches, each with its own image (one behind the other in the workspace)
+        int rc = launch_part<A, 0, 2>(obs, N, nets, out, workspace, st, mode);
+        if (rc) return rc;
+        return launch_part<A, 2, 3>(obs, N, nets, out, workspace + round_up(Plan<A, 0, 2>::kImageBytes, 256), st, mode);
+    }
+}
+
 }  // namespace fwd2
 
-bool learner_forward_tc2_supported(int A, int width) { return width == tc::kHidden && (A == 2 || A == 3); }
+bool learner_forward_tc2_supported(int A, int width) { return width == tc::kHidden && A >= 2 && A <= 4; }
 
 int64_t learner_forward_tc2_image_bytes(int A) {
     switch (A) {
-        case 2: return fwd2::Plan<2>::kImageBytes;
-        case 3: return fwd2::Plan<3>::kImageBytes;
+        case 2: return fwd2::Plan<2, 0, 5>::kImageBytes;
+        case 3: return fwd2::Plan<3, 0, 5>::kImageBytes;
+        case 4: return round_up(fwd2::Plan<4, 0, 2>::kImageBytes, 256) + fwd2::Plan<4, 2, 3>::kImageBytes;
     }
     return 0;
 }
 
 int learner_forward_tc2(const float* obs, int64_t N, int A, const rnad_mlp_weights* net, const rnad_mlp_weights* target,
                         const rnad_mlp_weights* reg, const rnad_mlp_weights* reg_, const rnad_learner_fwd_out* out,
-                        void* workspace, cudaStream_t st) {
+                        void* workspace, cudaStream_t st, int mode) {
     fwd2::Nets nets{*net, *target, *reg, *reg_};
-    fwd2::Out o{out->logit, out->pi, out->log_pi, out->v, out->v_target, out->log_pi_reg, out->log_pi_reg_};
+    fwd2::Out o{nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    if (out != nullptr) o = fwd2::Out{out->logit, out->pi, out->log_pi, out->v, out->v_target, out->log_pi_reg, out->log_pi_reg_};
     switch (A) {
-        case 2: return fwd2::launch<2>(obs, N, nets, o, (uint8_t*)workspace, st);
-        case 3: return fwd2::launch<3>(obs, N, nets, o, (uint8_t*)workspace, st);
+        case 2: return fwd2::launch<2>(obs, N, nets, o, (uint8_t*)workspace, st, mode);
+        case 3: return fwd2::launch<3>(obs, N, nets, o, (uint8_t*)workspace, st, mode);
+        case 4: return fwd2::launch<4>(obs, N, nets, o, (uint8_t*)workspace, st, mode);
     }
     return RNAD_EUNSUPPORTED;
 }

@@ -30,7 +30,7 @@ bool learner_forward_tc2_supported(int A, int width);
 int64_t learner_forward_tc2_image_bytes(int A);
 int learner_forward_tc2(const float* obs, int64_t N, int A, const rnad_mlp_weights* net, const rnad_mlp_weights* target,
                         const rnad_mlp_weights* reg, const rnad_mlp_weights* reg_, const rnad_learner_fwd_out* out,
-                        void* workspace, cudaStream_t st);
+                        void* workspace, cudaStream_t st, int mode);
 
 namespace tc {
 
@@ -965,7 +965,8 @@ int launch_forward(const float* obs, int64_t N, const FwdNets& nets, const FwdOu
 // player 0's (rows of even t) then player 1's (see learner_bwd_tc_kernel).
 template <int A>
 int launch_backward(const float* obs, int64_t N, int T_split, int64_t B_split, const rnad_mlp_weights& w,
-                    const float* d_logit, const float* d_v, float* flat_grad, uint8_t* workspace, cudaStream_t st) {
+                    const float* d_logit, const float* d_v, float* flat_grad, uint8_t* workspace, cudaStream_t st,
+                    int mode = 0) {
     using P = BwdPlan<A>;
     using PT = BwdTcPlan<A>;
     static_assert(PT::kImageBytes >= P::kImageBytes, "the workspace reserves the larger image");
@@ -981,7 +982,7 @@ int launch_backward(const float* obs, int64_t N, int T_split, int64_t B_split, c
         blocks = cap;
     }
     static const bool cuda_core_reduction = getenv("RNAD_LEARNER_BWD_CUDA_CORES") != nullptr;   // the previous kernel, for A/B runs
-    if (cuda_core_reduction && T_split == 0) {
+    if (cuda_core_reduction && T_split == 0 && mode == 0) {
         pack_bwd_image_kernel<A><<<24, 256, 0, st>>>(w, image);
         RNAD_CHECK_LAUNCH("pack_bwd_image_kernel");
         int rc = prepare<A>(learner_bwd_kernel<A>, P::kBytes, "cudaFuncSetAttribute(learner_bwd)");
@@ -989,8 +990,11 @@ int launch_backward(const float* obs, int64_t N, int T_split, int64_t B_split, c
         learner_bwd_kernel<A><<<(int)blocks, kLearnThreads, P::kBytes, st>>>(obs, N, image, w, d_logit, d_v, partials);
         RNAD_CHECK_LAUNCH("learner_bwd_kernel");
     } else {
-        pack_bwd_tc_image_kernel<A><<<32, 256, 0, st>>>(w, image);
-        RNAD_CHECK_LAUNCH("pack_bwd_tc_image_kernel");
+        if (mode != 1) {      // (mode as in learner_fwd_tc2.cu: 0 pack + run, 1 prepacked, 2 pack only)
+            pack_bwd_tc_image_kernel<A><<<32, 256, 0, st>>>(w, image);
+            RNAD_CHECK_LAUNCH("pack_bwd_tc_image_kernel");
+            if (mode == 2) return RNAD_OK;
+        }
         // two CTAs per SM (one per trunk, 256 TMEM columns each): pad the shared-memory request so that a third can
         // never become resident and spin inside tcgen05.alloc
         size_t smem = PT::kBytes;
@@ -1037,9 +1041,9 @@ int rnad_learner_param_count(int A, int width) {
     return 2 * width * (2 * A * A) + 2 * width + width + 1 + A * width + A;
 }
 
-int rnad_learner_forward(const float* observations, int64_t N, int A, const rnad_mlp_weights* net,
-                         const rnad_mlp_weights* target, const rnad_mlp_weights* reg, const rnad_mlp_weights* reg_,
-                         const rnad_learner_fwd_out* out, void* workspace, void* stream) {
+static int learner_forward_impl(const float* observations, int64_t N, int A, const rnad_mlp_weights* net,
+                                const rnad_mlp_weights* target, const rnad_mlp_weights* reg, const rnad_mlp_weights* reg_,
+                                const rnad_learner_fwd_out* out, void* workspace, void* stream, int prepacked) {
     RNAD_REQUIRE(observations && out && workspace, "rnad_learner_forward: null pointer");
     RNAD_REQUIRE(weights_ok(net) && weights_ok(target) && weights_ok(reg) && weights_ok(reg_),
                  "rnad_learner_forward: null weight pointer");
@@ -1055,7 +1059,9 @@ int rnad_learner_forward(const float* observations, int64_t N, int A, const rnad
     if (N == 0) return RNAD_OK;
     static const bool v1 = getenv("RNAD_LEARNER_FWD_V1") != nullptr;   // the previous kernel, for A/B runs
     if (!v1 && learner_forward_tc2_supported(A, net->width))
-        return learner_forward_tc2(observations, N, A, net, target, reg, reg_, out, workspace, (cudaStream_t)stream);
+        return learner_forward_tc2(observations, N, A, net, target, reg, reg_, out, workspace, (cudaStream_t)stream,
+                                   prepacked ? 1 : 0);
+    RNAD_REQUIRE(!prepacked, "rnad_learner_forward_prepacked: not available with RNAD_LEARNER_FWD_V1");
     tc::FwdNets nets{*net, *target, *reg, *reg_};
     tc::FwdOut o{out->logit, out->pi, out->log_pi, out->v, out->v_target, out->log_pi_reg, out->log_pi_reg_};
     cudaStream_t st = (cudaStream_t)stream;
@@ -1063,6 +1069,40 @@ int rnad_learner_forward(const float* observations, int64_t N, int A, const rnad
         case 2: return tc::launch_forward<2>(observations, N, nets, o, (uint8_t*)workspace, st);
         case 3: return tc::launch_forward<3>(observations, N, nets, o, (uint8_t*)workspace, st);
         case 4: return tc::launch_forward<4>(observations, N, nets, o, (uint8_t*)workspace, st);
+    }
+    return RNAD_EINVAL;
+}
+
+int rnad_learner_forward(const float* observations, int64_t N, int A, const rnad_mlp_weights* net,
+                         const rnad_mlp_weights* target, const rnad_mlp_weights* reg, const rnad_mlp_weights* reg_,
+                         const rnad_learner_fwd_out* out, void* workspace, void* stream) {
+    return learner_forward_impl(observations, N, A, net, target, reg, reg_, out, workspace, stream, 0);
+}
+
+int rnad_learner_forward_prepacked(const float* observations, int64_t N, int A, const rnad_mlp_weights* net,
+                                   const rnad_mlp_weights* target, const rnad_mlp_weights* reg,
+                                   const rnad_mlp_weights* reg_, const rnad_learner_fwd_out* out, void* workspace,
+                                   void* stream) {
+    return learner_forward_impl(observations, N, A, net, target, reg, reg_, out, workspace, stream, 1);
+}
+
+int rnad_learner_pack(int A, const rnad_mlp_weights* net, const rnad_mlp_weights* target, const rnad_mlp_weights* reg,
+                      const rnad_mlp_weights* reg_, void* workspace, void* stream) {
+    RNAD_REQUIRE(workspace, "rnad_learner_pack: null pointer");
+    RNAD_REQUIRE(weights_ok(net) && weights_ok(target) && weights_ok(reg) && weights_ok(reg_), "rnad_learner_pack: null weight pointer");
+    if (!rnad_learner_mlp_supported(A, net->width) || target->width != net->width || reg->width != net->width ||
+        reg_->width != net->width) {
+        set_error("rnad_learner_pack: needs four nets of width 256 and 2 <= max_actions <= 4");
+        return RNAD_EUNSUPPORTED;
+    }
+    RNAD_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "rnad_learner_pack: workspace must be 256-byte aligned");
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = learner_forward_tc2(nullptr, 0, A, net, target, reg, reg_, nullptr, workspace, st, 2);
+    if (rc) return rc;
+    switch (A) {
+        case 2: return tc::launch_backward<2>(nullptr, 0, 0, 0, *net, nullptr, nullptr, nullptr, (uint8_t*)workspace, st, 2);
+        case 3: return tc::launch_backward<3>(nullptr, 0, 0, 0, *net, nullptr, nullptr, nullptr, (uint8_t*)workspace, st, 2);
+        case 4: return tc::launch_backward<4>(nullptr, 0, 0, 0, *net, nullptr, nullptr, nullptr, (uint8_t*)workspace, st, 2);
     }
     return RNAD_EINVAL;
 }
@@ -1086,9 +1126,9 @@ int rnad_learner_backward(const float* observations, int64_t N, int A, const rna
     return RNAD_EINVAL;
 }
 
-int rnad_learner_backward_split(const float* observations, int T, int64_t B, int A, const rnad_mlp_weights* net,
-                                const float* d_logit, const float* d_v, float* player_grads, void* workspace,
-                                void* stream) {
+static int learner_backward_split_impl(const float* observations, int T, int64_t B, int A, const rnad_mlp_weights* net,
+                                       const float* d_logit, const float* d_v, float* player_grads, void* workspace,
+                                       void* stream, int prepacked) {
     RNAD_REQUIRE(observations && d_logit && d_v && player_grads && workspace, "rnad_learner_backward_split: null pointer");
     RNAD_REQUIRE(weights_ok(net), "rnad_learner_backward_split: null weight pointer");
     RNAD_REQUIRE(T >= 1 && B >= 1, "rnad_learner_backward_split: empty trajectory");
@@ -1100,11 +1140,23 @@ int rnad_learner_backward_split(const float* observations, int T, int64_t B, int
     cudaStream_t st = (cudaStream_t)stream;
     const int64_t N = (int64_t)T * B;
     switch (A) {
-        case 2: return tc::launch_backward<2>(observations, N, T, B, *net, d_logit, d_v, player_grads, (uint8_t*)workspace, st);
-        case 3: return tc::launch_backward<3>(observations, N, T, B, *net, d_logit, d_v, player_grads, (uint8_t*)workspace, st);
-        case 4: return tc::launch_backward<4>(observations, N, T, B, *net, d_logit, d_v, player_grads, (uint8_t*)workspace, st);
+        case 2: return tc::launch_backward<2>(observations, N, T, B, *net, d_logit, d_v, player_grads, (uint8_t*)workspace, st, prepacked);
+        case 3: return tc::launch_backward<3>(observations, N, T, B, *net, d_logit, d_v, player_grads, (uint8_t*)workspace, st, prepacked);
+        case 4: return tc::launch_backward<4>(observations, N, T, B, *net, d_logit, d_v, player_grads, (uint8_t*)workspace, st, prepacked);
     }
     return RNAD_EINVAL;
+}
+
+int rnad_learner_backward_split(const float* observations, int T, int64_t B, int A, const rnad_mlp_weights* net,
+                                const float* d_logit, const float* d_v, float* player_grads, void* workspace,
+                                void* stream) {
+    return learner_backward_split_impl(observations, T, B, A, net, d_logit, d_v, player_grads, workspace, stream, 0);
+}
+
+int rnad_learner_backward_split_prepacked(const float* observations, int T, int64_t B, int A, const rnad_mlp_weights* net,
+                                          const float* d_logit, const float* d_v, float* player_grads, void* workspace,
+                                          void* stream) {
+    return learner_backward_split_impl(observations, T, B, A, net, d_logit, d_v, player_grads, workspace, stream, 1);
 }
 
 }  // extern "C"

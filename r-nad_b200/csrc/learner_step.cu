@@ -57,25 +57,39 @@ __global__ void step_control_kernel(rnad_step_ctrl* ctrl, uint64_t seed, float a
     ctrl->alpha = alpha;
 }
 
-// sum of one float per thread over the block, the same value and the same bits in every thread, fixed order
-__device__ __forceinline__ float block_sum(float v, float* s_red) {
-    v = warp_sum(v);
-    __syncthreads();
-    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = v;
-    __syncthreads();
-    float tot = 0.f;
-    for (int w = 0; w < kTailThreads / 32; ++w) tot += s_red[w];
-    return tot;
+// The tail runs as ONE thread-block cluster of kTailCtas CTAs (8192 threads: one or two parameters per thread, so
+// every pass is a single round of independent loads instead of a latency-bound loop) synchronised by the hardware
+// cluster barrier; the squared gradient norm is reduced per CTA and the CTAs' partial sums are read by every CTA
+// from its peers' shared memory (DSMEM) in rank order - the same value, bit for bit, in every thread.
+constexpr int kTailCtas = 8;
+
+__device__ __forceinline__ void cluster_sync() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ float ld_dsmem(const float* local_smem_ptr, uint32_t cta) {
+    uint32_t addr = (uint32_t)__cvta_generic_to_shared(local_smem_ptr), remote;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(addr), "r"(cta));
+    float v;
+    asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(remote) : "memory");
+    return v;
 }
 
-__global__ void __launch_bounds__(kTailThreads, 1) learner_tail_kernel(rnad_tail_args a) {
+__global__ void __cluster_dims__(kTailCtas, 1, 1) __launch_bounds__(kTailThreads, 1) learner_tail_kernel(rnad_tail_args a) {
     __shared__ float s_red[kTailThreads / 32];
+    __shared__ float s_partial;
     __shared__ float s_stats[8];
     __shared__ float s_adam[3];
     const int tid = threadIdx.x;
+    const uint32_t cta = cluster_ctarank();
+    const int gtid = (int)cta * kTailThreads + tid, n_threads = kTailCtas * kTailThreads;
     const int P = a.n_params;
     const int64_t row_floats = xchg_row_floats(P);
-    const uint32_t seq = a.ctrl->seq;
+    const uint32_t seq = a.ctrl->seq;           // (rewritten only after the last cluster barrier)
     const int slot = (int)(seq & 1u);
 
     // this rank's row: G_0 | G_1 | counts | loss numerators
@@ -91,17 +105,17 @@ __global__ void __launch_bounds__(kTailThreads, 1) learner_tail_kernel(rnad_tail
 
     if (a.world > 1) {
         // ---- push the row to every rank's buffer (own included), then the flags
-        for (int r = 0; r < a.world; ++r) {
-            float* dst = a.xchg[r] + ((int64_t)slot * a.world + a.rank) * row_floats;
-            for (int i = tid; i < 2 * P + 8; i += kTailThreads) dst[i] = my_value(i);
+        for (int i = gtid; i < 2 * P + 8; i += n_threads) {
+            const float v = my_value(i);
+            for (int r = 0; r < a.world; ++r) a.xchg[r][((int64_t)slot * a.world + a.rank) * row_floats + i] = v;
         }
         __threadfence_system();
-        __syncthreads();
-        if (tid < a.world && tid != a.rank) {
+        cluster_sync();
+        if (cta == 0 && tid < a.world && tid != a.rank) {
             uint32_t* flags = reinterpret_cast<uint32_t*>(a.xchg[tid] + xchg_flag_offset_floats(P, a.world));
             st_release_sys(flags + slot * a.world + a.rank, seq + 1u);
         }
-        // ---- wait for every peer's row of this step
+        // ---- wait for every peer's row of this step (every CTA watches the flags itself)
         if (tid < a.world && tid != a.rank) {
             const uint32_t* flags = reinterpret_cast<const uint32_t*>(a.xchg[a.rank] + xchg_flag_offset_floats(P, a.world));
             const uint64_t t0 = global_timer_ns();
@@ -110,7 +124,7 @@ __global__ void __launch_bounds__(kTailThreads, 1) learner_tail_kernel(rnad_tail
                     atomicOr(&a.ctrl->error, 1u << (tid & 31));
                     break;
                 }
-                __nanosleep(200);
+                __nanosleep(100);
             }
         }
         __syncthreads();
@@ -123,7 +137,7 @@ __global__ void __launch_bounds__(kTailThreads, 1) learner_tail_kernel(rnad_tail
         return acc;
     };
     if (tid < 8) s_stats[tid] = total(2 * P + tid);
-    if (tid == 32) {     // Adam's scalars, once, in double like torch's host-side arithmetic
+    if (tid == 32) {     // Adam's scalars, once per CTA, in double like torch's host-side arithmetic
         const double step = (double)a.ctrl->adam_step + 1.0;
         const double bc1 = 1.0 - pow((double)a.beta1, step), bc2 = 1.0 - pow((double)a.beta2, step);
         s_adam[0] = (float)((double)a.lr / bc1);
@@ -133,14 +147,37 @@ __global__ void __launch_bounds__(kTailThreads, 1) learner_tail_kernel(rnad_tail
     __syncthreads();
     const float n0 = fmaxf(s_stats[0] * 4096.f + s_stats[1], 1.f), n1 = fmaxf(s_stats[2] * 4096.f + s_stats[3], 1.f);
 
-    // ---- pass 1: the gradient (vtrace.py:370-374, 387-389: each player's sum over its own step count) and its norm
+    // ---- pass 1: the gradient (vtrace.py:370-374, 387-389: each player's sum over its own step count) and its norm.
+    //      Everything pass 2 needs is fetched here as well: one round of independent loads per thread.
+    constexpr int kMaxPer = 4;                   // up to 32,768 parameters
+    float g[kMaxPer], m[kMaxPer], v[kMaxPer], p[kMaxPer], t[kMaxPer];
     float sq = 0.f;
-    for (int i = tid; i < P; i += kTailThreads) {
-        const float g = total(i) / n0 + total(P + i) / n1;
-        a.flat_grad[i] = g;
-        sq = fmaf(g, g, sq);
+#pragma unroll
+    for (int u = 0; u < kMaxPer; ++u) {
+        const int i = gtid + u * n_threads;
+        g[u] = m[u] = v[u] = p[u] = t[u] = 0.f;
+        if (i < P) {
+            g[u] = total(i) / n0 + total(P + i) / n1;
+            m[u] = a.exp_avg[i];
+            v[u] = a.exp_avg_sq[i];
+            p[u] = a.params[i];
+            t[u] = a.target_params[i];
+        }
     }
-    const float norm = sqrtf(block_sum(sq, s_red));
+#pragma unroll
+    for (int u = 0; u < kMaxPer; ++u) sq = fmaf(g[u], g[u], sq);
+    sq = warp_sum(sq);
+    if ((tid & 31) == 0) s_red[tid >> 5] = sq;
+    __syncthreads();
+    if (tid == 0) {
+        float tot = 0.f;
+        for (int w = 0; w < kTailThreads / 32; ++w) tot += s_red[w];
+        s_partial = tot;
+    }
+    cluster_sync();
+    float norm_sq = 0.f;
+    for (uint32_t c = 0; c < kTailCtas; ++c) norm_sq += ld_dsmem(&s_partial, c);
+    const float norm = sqrtf(norm_sq);
     // clip_grad_norm_ (rnad.py:456): coefficient min(max_norm / (norm + 1e-6), 1)
     const float coef = fminf(a.grad_clip / (norm + 1e-6f), 1.f);
 
@@ -148,20 +185,24 @@ __global__ void __launch_bounds__(kTailThreads, 1) learner_tail_kernel(rnad_tail
     const float step_size = s_adam[0], bc2_sqrt = s_adam[1];
     const float w1 = 1.f - a.beta1, w2 = 1.f - a.beta2;
     const float avg_new = a.gamma_averaging, avg_old = a.one_minus_gamma_averaging;
-    for (int i = tid; i < P; i += kTailThreads) {
-        const float g = a.flat_grad[i] * coef;
-        a.flat_grad[i] = g;
-        float m = a.exp_avg[i], v = a.exp_avg_sq[i];
-        m = w1 < 0.5f ? m + w1 * (g - m) : g - (g - m) * (1.f - w1);      // Tensor.lerp_
-        v = v * a.beta2 + w2 * g * g;
-        a.exp_avg[i] = m;
-        a.exp_avg_sq[i] = v;
-        const float denom = sqrtf(v) / bc2_sqrt + a.eps;
-        const float p = a.params[i] - step_size * (m / denom);
-        a.params[i] = p;
-        a.target_params[i] = __fadd_rn(__fmul_rn(avg_new, p), __fmul_rn(avg_old, a.target_params[i]));
+#pragma unroll
+    for (int u = 0; u < kMaxPer; ++u) {
+        const int i = gtid + u * n_threads;
+        if (i < P) {
+            const float gc = g[u] * coef;
+            const float mm = w1 < 0.5f ? m[u] + w1 * (gc - m[u]) : gc - (gc - m[u]) * (1.f - w1);      // Tensor.lerp_
+            const float vv = v[u] * a.beta2 + w2 * gc * gc;
+            const float denom = sqrtf(vv) / bc2_sqrt + a.eps;
+            const float pp = p[u] - step_size * (mm / denom);
+            a.flat_grad[i] = gc;
+            a.exp_avg[i] = mm;
+            a.exp_avg_sq[i] = vv;
+            a.params[i] = pp;
+            a.target_params[i] = __fadd_rn(__fmul_rn(avg_new, pp), __fmul_rn(avg_old, t[u]));
+        }
     }
-    if (tid == 0) {
+    cluster_sync();                              // every CTA has read ctrl and its peers' partial sums
+    if (cta == 0 && tid == 0) {
         // loss = sum over players of (its numerator / its step count); the NeuRD loss carries a minus sign (vtrace.py:429)
         a.losses[0] = s_stats[4] / n0 + s_stats[5] / n1;
         a.losses[1] = -(s_stats[6] / n0 + s_stats[7] / n1);
@@ -196,7 +237,8 @@ int rnad_learner_tail(const rnad_tail_args* args, void* stream) {
                  "rnad_learner_tail: rank %d of %d (at most %d ranks)", args->rank, args->world, RNAD_MAX_PEERS);
     if (args->world > 1)
         for (int r = 0; r < args->world; ++r) RNAD_REQUIRE(args->xchg[r] != nullptr, "rnad_learner_tail: exchange buffer of rank %d is null", r);
-    learner_tail_kernel<<<1, kTailThreads, 0, (cudaStream_t)stream>>>(*args);
+    RNAD_REQUIRE(args->n_params <= 4 * kTailCtas * kTailThreads, "rnad_learner_tail: at most %d parameters", 4 * kTailCtas * kTailThreads);
+    learner_tail_kernel<<<kTailCtas, kTailThreads, 0, (cudaStream_t)stream>>>(*args);
     RNAD_CHECK_LAUNCH("learner_tail_kernel");
     return RNAD_OK;
 }

@@ -233,7 +233,7 @@ __global__ void count_played_kernel(const int64_t* __restrict__ indices, const i
 }
 
 constexpr int kLearnerBlock = 128;
-constexpr int kMaxLearnerBlocks = 4096;
+constexpr int kMaxLearnerBlocks = 8192;
 
 template <int A>
 __global__ void __launch_bounds__(kLearnerBlock) learner_targets_kernel(rnad_learner_io io, rnad_learner_params p,
@@ -376,13 +376,19 @@ __global__ void __launch_bounds__(kLearnerBlock) learner_targets_kernel(rnad_lea
 constexpr int kTbGames = 32;
 constexpr int kTbMaxT = 32;
 
-template <int A>
-__global__ void __launch_bounds__(kTbGames* kTbMaxT) learner_targets_tb_kernel(rnad_learner_io io, rnad_learner_params p,
-                                                                               int T, int64_t B, float* partials) {
-    __shared__ float s_v[kTbMaxT][kTbGames], s_reward[kTbMaxT][kTbGames], s_cs[kTbMaxT][kTbGames], s_ent[kTbMaxT][kTbGames];
-    __shared__ float s_vt[kTbMaxT][kTbGames], s_q[kTbMaxT][kTbGames];
-    __shared__ int s_flags[kTbMaxT][kTbGames];
-    __shared__ float red[4][kTbMaxT];
+// kTCap: the block's capacity in half-moves (8, 16 or 32): sizes the shared-memory arrays, so that short trajectories
+// are not limited to four blocks per SM by 29 KB of shared memory they do not use.
+// `ticket` (device uint32, zero before the launch and zero again after it): the last block to finish adds the
+// per-block partial sums in block order (deterministic) - no separate reduction launch.
+template <int A, int kTCap>
+__global__ void __launch_bounds__(kTbGames* kTCap, 1024 / (kTbGames * kTCap))
+    learner_targets_tb_kernel(rnad_learner_io io, rnad_learner_params p, int T, int64_t B, float* partials,
+                              unsigned int* ticket) {
+    __shared__ float s_v[kTCap][kTbGames], s_reward[kTCap][kTbGames], s_cs[kTCap][kTbGames], s_ent[kTCap][kTbGames];
+    __shared__ float s_vt[kTCap][kTbGames], s_q[kTCap][kTbGames];
+    __shared__ int s_flags[kTCap][kTbGames];
+    __shared__ float red[4][kTCap];
+    __shared__ bool s_last;
     const int g = threadIdx.x, t = threadIdx.y;
     const int32_t* cnt = io.global_counts != nullptr ? io.global_counts : io.counts;
     float N[2] = {1.f, 1.f};
@@ -539,6 +545,43 @@ __global__ void __launch_bounds__(kTbGames* kTbMaxT) learner_targets_tb_kernel(r
         for (int w = 0; w < (int)blockDim.y; ++w) acc += red[g][w];
         partials[blockIdx.x * 4 + g] = acc;
     }
+    // ---- the last block to arrive sums the partials of all blocks, in block order
+    __threadfence();
+    __syncthreads();
+    if (t == 0 && g == 0) s_last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    const int tid = t * kTbGames + g, n_thr = blockDim.x * blockDim.y;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int i = tid; i < (int)gridDim.x; i += n_thr) {      // one round of independent 16-byte loads
+        const float4 q = __ldcg(reinterpret_cast<const float4*>(partials) + i);
+        acc[0] += q.x;
+        acc[1] += q.y;
+        acc[2] += q.z;
+        acc[3] += q.w;
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const float w = warp_sum(acc[q]);
+        if (g == 0) red[q][t] = w;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        float tot[4];
+        for (int q = 0; q < 4; ++q) {
+            float x = 0.f;
+            for (int w = 0; w < (int)blockDim.y; ++w) x += red[q][w];
+            tot[q] = x;
+        }
+        if (io.unnormalised) {            // the four numerators (critic p0, p1, NeuRD p0, p1)
+            for (int q = 0; q < 4; ++q) io.loss_sums[q] = tot[q];
+        } else {
+            io.losses[0] = tot[0] / N[0] + tot[1] / N[1];
+            io.losses[1] = -(tot[2] / N[0] + tot[3] / N[1]);
+        }
+        *ticket = 0u;                     // ready for the next launch
+    }
 }
 
 __global__ void reduce_losses_kernel(const float* __restrict__ partials, int n_blocks, const int32_t* counts,
@@ -601,21 +644,17 @@ int launch_learner(const rnad_learner_io& io, const rnad_learner_params& p, int 
     static const bool per_game = getenv("RNAD_TARGETS_PER_GAME") != nullptr;   // the previous kernel, for A/B runs
     int blocks;
     if (T <= kTbMaxT && !per_game) {
-        // one thread per (t, b) slot.  Every block gets the same number of 32-game tiles (no tail wave): with R blocks
-        // resident at once, n_tiles tiles take ceil(n_tiles / R) rounds, spread over ceil(n_tiles / rounds) blocks
+        // one thread per (t, b) slot, one 32-game tile per block while the partial-sum buffer allows: blocks of one SM
+        // are then in different phases (loads / scan / stores) and hide each other's latencies
         const dim3 block(kTbGames, T);
-        int per_sm = 0;
-        int rc = check_cuda(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, learner_targets_tb_kernel<A>,
-                                                                          kTbGames * T, 0), "occupancy(learner_targets_tb)");
-        if (rc) return rc;
-        const int64_t resident = (int64_t)(per_sm > 0 ? per_sm : 1) * sm_count();
         const int64_t n_tiles = (B + kTbGames - 1) / kTbGames;
-        const int64_t rounds = (n_tiles + resident - 1) / resident;
-        int64_t want = (n_tiles + rounds - 1) / rounds;
-        if (want > kMaxLearnerBlocks) want = kMaxLearnerBlocks;
-        blocks = (int)want;
-        learner_targets_tb_kernel<A><<<blocks, block, 0, st>>>(io, p, T, B, partials);
+        blocks = (int)(n_tiles < kMaxLearnerBlocks ? n_tiles : kMaxLearnerBlocks);
+        unsigned int* ticket = reinterpret_cast<unsigned int*>(partials + (size_t)kMaxLearnerBlocks * 4);
+        if (T <= 8) learner_targets_tb_kernel<A, 8><<<blocks, block, 0, st>>>(io, p, T, B, partials, ticket);
+        else if (T <= 16) learner_targets_tb_kernel<A, 16><<<blocks, block, 0, st>>>(io, p, T, B, partials, ticket);
+        else learner_targets_tb_kernel<A, 32><<<blocks, block, 0, st>>>(io, p, T, B, partials, ticket);
         RNAD_CHECK_LAUNCH("learner_targets_tb_kernel");
+        return RNAD_OK;
     } else {
         blocks = blocks_for(B, kLearnerBlock, kMaxLearnerBlocks);
         learner_targets_kernel<A><<<blocks, kLearnerBlock, 0, st>>>(io, p, T, B, partials);
@@ -684,7 +723,7 @@ int rnad_vtrace(const float* v, const float* valid, const int64_t* player_id, co
 int64_t rnad_learner_targets_workspace(int T, int64_t B) {
     (void)T;
     (void)B;
-    return (int64_t)kMaxLearnerBlocks * 4 * sizeof(float);
+    return (int64_t)kMaxLearnerBlocks * 4 * sizeof(float) + 256;   // per-block partial sums + the last-block ticket
 }
 
 int rnad_count_played(const int64_t* indices, const int64_t* turns, int T, int64_t B, int32_t* counts, void* stream) {
@@ -716,6 +755,7 @@ int rnad_learner_targets(const rnad_learner_io* io, const rnad_learner_params* p
         int rc = rnad_count_played(io->indices, io->turns, T, B, io->counts, stream);
         if (rc) return rc;
     }
+    RNAD_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 15) == 0, "rnad_learner_targets: workspace must be 16-byte aligned");
     RNAD_DISPATCH_A(A, launch_learner<kA>(*io, *p, T, B, (float*)workspace, st));
     return RNAD_EINVAL;
 }

@@ -125,7 +125,7 @@ class States:
         with _b200.device_guard(self._idx):
             obs = torch.empty((self.batch_size, 2, a, a), dtype=torch.float32, device=self._idx.device)
             mask = torch.empty((self.batch_size, a), dtype=torch.float32, device=self._idx.device) if want_mask else None
-            _b200.lib().rnad_observe(_b200.ptr(packed.ev_tab), a, _b200.ptr(self._idx, torch.int32), self._turn,
+            _b200.lib().rnad_observe(_b200.ptr(packed.ev_tab), a, packed.S, _b200.ptr(self._idx, torch.int32), self._turn,
                                      self.batch_size, _b200.ptr(obs), _b200.ptr(mask), _b200.stream())
         return obs, mask
 
@@ -405,7 +405,7 @@ class Episodes:
 
     def _tensor_items(self):
         self._resolve()
-        return [(k, v) for k, v in self.__dict__.items() if torch.is_tensor(v)]
+        return [(k, v) for k, v in self.__dict__.items() if torch.is_tensor(v) and not k.startswith("_rollout")]
 
     def sample(self, batch_size):
         """A uniformly random subset (without replacement) of the batch dimension (episode.py:243-256)."""
@@ -443,6 +443,104 @@ class Episodes:
         result.finished = True
         result.t_eff = t_eff
         return result
+
+
+class SelfPlay:
+    """
+    Repeated self-play with one actor net as a replayable unit: the trajectory lives in one static arena, the rollout
+    seed in device memory (`rnad_step_control`), and - after one eager call - every `play()` is one tiny kernel launch
+    plus ONE CUDA-graph replay of
+
+        [weights_host -> the actor's flat parameter buffer]  ->  rnad_rollout  ->  [per-game returns -> returns_host]
+
+    `weights_host` (optional, pinned fp32, state_dict order, `sum(p.numel())` floats): fresh actor weights arrive from
+    host memory before every batch (a learner elsewhere, a checkpoint).  `returns_host` (optional, pinned fp32, B
+    floats): every game's payoff for the row player is copied back after the batch.  `play()` does not synchronise;
+    the returned `Episodes` holds views of the arena, valid until the next `play()`.  (Reference: the loop around
+    `Episodes.generate`, rnad.py:502-505 / episode.py:175-230.)
+    """
+
+    def __init__(self, tree: Tree, batch_size: int, net: torch.nn.Module, precision: str = None,
+                 weights_host: torch.Tensor = None, returns_host: torch.Tensor = None, use_graph: bool = True):
+        from nn.net import MLP
+
+        if type(net) is not MLP:
+            raise _b200.RnadError("SelfPlay serves nn.net.MLP actors (the fused rollout kernel)")
+        L = _b200.lib()
+        self.tree, self.net, self.batch_size = tree, net, int(batch_size)
+        self.packed = packed = tree.packed()
+        self.device = dev = packed.device
+        if precision is None:
+            if L.rnad_rollout_tc2_supported(packed.A, net.width, packed.C):
+                precision = "tf32x2"
+            else:
+                precision = "tf32" if L.rnad_rollout_tc_supported(packed.A, net.width) else "fp32"
+        self.precision = precision
+        self.t_max = packed.max_half_moves
+        self.weights_host, self.returns_host = weights_host, returns_host
+        with torch.cuda.device(dev):
+            self.arena = _TrajectoryArena(self.t_max, self.batch_size, packed.A, dev)
+            self.ctrl = torch.zeros(ctypes.sizeof(_b200.StepCtrl), dtype=torch.uint8, device=dev)
+            n = sum(p.numel() for p in net.parameters())
+            self.flat = torch.empty(n, dtype=torch.float32, device=dev)
+            offset = 0
+            with torch.no_grad():
+                for p in net.parameters():             # registration order == state_dict order
+                    view = self.flat[offset: offset + p.numel()].view_as(p)
+                    view.copy_(p.detach())
+                    p.data = view
+                    offset += p.numel()
+            ws = int(L.rnad_rollout_workspace_bytes(packed.A, net.width, _b200.PRECISIONS[precision]))
+            self.workspace = torch.empty(ws, dtype=torch.uint8, device=dev) if ws else None
+            self.returns = torch.empty(self.batch_size, dtype=torch.float32, device=dev) if returns_host is not None else None
+        if weights_host is not None and (not weights_host.is_pinned() or weights_host.numel() != n):
+            raise _b200.RnadError(f"weights_host must be a pinned fp32 tensor of {n} elements")
+        if returns_host is not None and (not returns_host.is_pinned() or returns_host.numel() != self.batch_size):
+            raise _b200.RnadError(f"returns_host must be a pinned fp32 tensor of {self.batch_size} elements")
+        self._w = _b200.mlp_weights(net, dev)
+        self._traj = _b200.Trajectory(*self.arena.pointers())
+        self.episodes = Episodes(tree, self.batch_size)
+        self.episodes.finished = True
+        self.episodes.precision = precision
+        self.use_graph, self.graph, self.calls = use_graph, None, 0
+
+    def _enqueue(self):
+        L, p = _b200.lib(), self.packed
+        if self.weights_host is not None:
+            self.flat.copy_(self.weights_host, non_blocking=True)
+        L.rnad_rollout(_b200.ptr(p.ev_tab), _b200.ptr(p.tr_tab), p.A, p.C, ctypes.byref(self._w), self.batch_size,
+                       self.t_max, 0, self.ctrl.data_ptr() + _b200.StepCtrl.seed.offset, self.episodes.states.game_offset,
+                       None, _b200.PRECISIONS[self.precision], ctypes.byref(self._traj), self.arena.stats.data_ptr(),
+                       _b200.ptr(self.workspace), _b200.stream())
+        if self.returns_host is not None:
+            # a game is paid once, when it ends: its return is the sum of its rewards over time
+            torch.sum(self.arena["rewards"], dim=0, out=self.returns)
+            self.returns_host.copy_(self.returns, non_blocking=True)
+
+    def play(self) -> "Episodes":
+        seed = _fresh_seed()
+        with torch.cuda.device(self.device):
+            _b200.lib().rnad_step_control(self.ctrl.data_ptr(), seed, 0.0, _b200.stream())
+            if self.graph is not None:
+                self.graph.replay()
+            elif not self.use_graph or self.calls == 0:
+                self._enqueue()
+            else:
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph):
+                    self._enqueue()
+                self.graph = graph
+                graph.replay()
+        self.calls += 1
+        ep = self.episodes
+        ep.states.seed = seed
+        for key in Episodes._LAZY:
+            ep.__dict__.pop(key, None)
+        ep.__dict__["_pending"] = (self.arena, self.arena.stats)
+        ep.__dict__["_rollout_stats"] = self.arena.stats
+        ep._q_estimates = ep._v_estimates = None
+        ep.generation_time = 0.0
+        return ep
 
 
 class Buffer:

@@ -89,3 +89,67 @@ def all_gather_object(obj):
     out = [None] * d.get_world_size()
     d.all_gather_object(out, obj)
     return out
+
+
+class PeerExchange:
+    """
+    The exchange buffers of `rnad_learner_tail` (csrc/learner_step.cu): one cudaMalloc'ed buffer per rank, mapped into
+    every other rank's process through CUDA IPC, so that the tail kernel pushes its gradient row straight into its
+    peers' memory over NVLink and no collective library sits on the step's critical path.  torch.distributed only
+    carries the 64-byte handles once, at construction.  `pointers[r]` is rank r's buffer as seen from this process.
+    """
+
+    def __init__(self, n_params: int, device: torch.device):
+        import ctypes
+
+        import _b200
+
+        d = group()
+        assert d is not None, "PeerExchange needs an initialised multi-rank process group"
+        L = _b200.lib()
+        self.world, self.rank, self.device = d.get_world_size(), d.get_rank(), device
+        if self.world > _b200.MAX_PEERS:
+            raise _b200.RnadError(f"at most {_b200.MAX_PEERS} ranks share gradients through peer memory")
+        self._lib, self._local, self._opened = L, None, []
+        n_bytes = int(L.rnad_xchg_bytes(n_params, self.world))
+        error = None
+        handle = ctypes.create_string_buffer(_b200.IPC_HANDLE_BYTES)
+        with torch.cuda.device(device):
+            try:
+                local = ctypes.c_void_p()
+                L.rnad_xchg_create(n_bytes, ctypes.byref(local), handle)
+                self._local = local
+            except _b200.RnadError as exc:
+                error = str(exc)
+            replies = all_gather_object((self.rank, handle.raw, error))
+            self.pointers = [None] * self.world
+            if not any(e for _, _, e in replies):
+                for r, raw, _ in replies:
+                    if r == self.rank:
+                        self.pointers[r] = self._local.value
+                        continue
+                    try:
+                        peer = ctypes.c_void_p()
+                        L.rnad_xchg_open(raw, ctypes.byref(peer))
+                        self._opened.append(peer)
+                        self.pointers[r] = peer.value
+                    except _b200.RnadError as exc:
+                        error = str(exc)
+            errors = [e for e in all_gather_object(error) if e]
+        if errors:
+            self.close()
+            raise _b200.RnadError("peer-memory gradient exchange unavailable: " + errors[0])
+
+    def close(self):
+        for peer in self._opened:
+            try:
+                self._lib.rnad_xchg_close(peer)
+            except Exception:
+                pass
+        self._opened = []
+        if self._local is not None:
+            try:
+                self._lib.rnad_xchg_destroy(self._local)
+            except Exception:
+                pass
+            self._local = None

@@ -174,6 +174,10 @@ class RNaD:
         self.graph_optimizer_tail = os.environ.get("RNAD_GRAPH_TAIL", "1") != "0"   # see _GraphedTail
         self._tail = None
         self._defer_clip = False
+        # the whole learner step as one CUDA graph (learn/fused.py::LearnerStep); "0" keeps the step-by-step path,
+        # "eager" runs the same five kernels calls without capturing them
+        self.step_engine = os.environ.get("RNAD_STEP_ENGINE", "graph")
+        self._step = None
 
     # ------------------------------------------------------------------ nets
 
@@ -288,6 +292,8 @@ class RNaD:
     def __save_checkpoint(self):
         if not self._is_writer():
             return
+        if self._step is not None:
+            self._step.sync_optimizer(self)      # Adam's step count lives on the device while the step engine runs
         saved_dict = {
             "total_steps": self.total_steps,
             "net_params": self.net_params,
@@ -403,10 +409,39 @@ class RNaD:
                 if not t.is_floating_point():   # e.g. BatchNorm's num_batches_tracked
                     t.copy_(g * src[k] + (1 - g) * t)
 
+    def _step_engine_for(self):
+        """The LearnerStep serving the current nets / optimizer / hyper-parameters, or None if it does not apply."""
+        if self.step_engine in ("0", "off", "none") or self.learner_engine == "torch":
+            return None
+        if os.environ.get("RNAD_LEARNER_ENGINE") == "torch" or not fused.LearnerStep.applicable(self):
+            return None
+        if self._step is not None and self._step.trial_key != fused.LearnerStep.key_of(self):
+            self._step.sync_optimizer(self)
+            self._step.close()
+            self._step = None
+        if self._step is None:
+            try:
+                self._step = fused.LearnerStep(self, use_graph=self.step_engine != "eager")
+            except Exception as exc:   # e.g. CUDA IPC unavailable under data parallelism: keep the step-by-step path
+                logging.warning("learner step engine unavailable (%s); using the step-by-step path", exc)
+                self.step_engine = "off"
+                return None
+            self._tail = None
+        return self._step
+
     def learner_step(self, alpha: float, buffer: "episode.Buffer" = None, log: dict = None):
         """One iteration of the rnad.py:495 loop body without the schedule bookkeeping: rollout, learn, Adam, EMA."""
         if buffer is None:
             buffer = self.__dict__.setdefault("_buffer", episode.Buffer(self.n_batches_per_buffer))
+        step = self._step_engine_for() if log is None else None
+        if step is not None:
+            # rollout -> forward -> targets -> backward -> [gradient exchange] -> clip / Adam / target average: one graph
+            episodes = step.run(alpha)
+            buffer.append(episodes)
+            self.last_losses = step.losses[:2]
+            return episodes
+        if self._step is not None:
+            self._step.sync_optimizer(self)          # this step runs torch's optimizer on the shared flat state
         if self.total_steps % self.buffer_mod == 0:
             episodes = episode.Episodes(self.tree, self.batch_size)
             episodes.generate(self.net)
@@ -415,7 +450,7 @@ class RNaD:
         # With the fused learner engine the gradients live in one persistent flat buffer, so everything after them -
         # clipping, Adam, the target-net average: ~20 small launches - has fixed addresses and replays as ONE CUDA graph.
         graphed = (self.graph_optimizer_tail and log is None and isinstance(self.optimizer, torch.optim.Adam)
-                   and fused.engine_for(self.net, self.learner_engine) == "fused")
+                   and self._step is None and fused.engine_for(self.net, self.learner_engine) == "fused")
         self._defer_clip = graphed
         try:
             self.__learn(episodes_sample, alpha, log=log)
@@ -427,7 +462,10 @@ class RNaD:
             self._tail.step(self)
         else:
             self._eager_tail(clip=False)
-            self.optimizer.zero_grad()
+            if self._step is None:
+                self.optimizer.zero_grad()
+        if self._step is not None:
+            self._step.pull_optimizer(self)
         return episodes_sample
 
     def __resume(self, max_updates=10 ** 6, checkpoint_mod=1000, expl_mod=1, log_mod=20) -> None:

@@ -256,6 +256,6 @@ def learner_targets(episodes, logit, pi, log_pi, v, v_target_net, log_pi_reg, lo
                                      float(epsilon_threshold), int(n_discrete), float(neurd_clip), float(beta),
                                      float(value_weight), float(neurd_weight))
         if workspace is None:
-            workspace = torch.empty(int(L.rnad_learner_targets_workspace(t, b)), dtype=torch.uint8, device=dev)
+            workspace = torch.zeros(int(L.rnad_learner_targets_workspace(t, b)), dtype=torch.uint8, device=dev)
         L.rnad_learner_targets(ctypes.byref(io), ctypes.byref(params), t, b, a, _b200.ptr(workspace), _b200.stream())
     return res

@@ -72,7 +72,7 @@ def main():
         row_a = ep.actions[t].argmax(-1).contiguous()
         col_a = ep.actions[t + 1].argmax(-1).contiguous()
         n_alive = int((idx != 0).sum())
-        mean_o, min_o = timed(lambda: L.rnad_observe(_b200.ptr(packed.ev_tab), a, _b200.ptr(idx), 0, batch,
+        mean_o, min_o = timed(lambda: L.rnad_observe(_b200.ptr(packed.ev_tab), a, packed.S, _b200.ptr(idx), 0, batch,
                                                      _b200.ptr(obs), _b200.ptr(mask), _b200.stream()))
         work = idx.clone()
 
