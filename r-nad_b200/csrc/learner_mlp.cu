@@ -7,12 +7,15 @@
 //                          tcgen05 (kind::tf32, fp32 accumulate in TMEM), the hidden
 //                          activations never leave the SM.
 //   rnad_learner_backward  parameter gradients of the learner net given d loss/d logit
-//                          and d loss/d v (from rnad_learner_targets): recomputes the two
-//                          learner trunks on the tensor core, reduces
+//   (_split)               and d loss/d v (from rnad_learner_targets): recomputes the two
+//                          learner trunks TRANSPOSED on the tensor core and forms
 //                              dW2 = g^T relu(h),  dh = (g W2) * [h > 0],  dW1 = dh^T x
-//                          over the 128 rows of a tile in fp32 on the CUDA cores, keeps
-//                          per-CTA sums in registers across tiles, and a second kernel
-//                          adds the per-CTA partials in a fixed order (deterministic).
+//                          with tcgen05 MMAs whose A operands (relu^T, dh^T) sit in tensor
+//                          memory and whose accumulators stay there across all tiles of a
+//                          CTA (learner_bwd_tc_kernel); a second kernel adds the per-CTA
+//                          partials in a fixed order (deterministic), per player in split
+//                          mode.  learner_bwd_kernel (reduction on the CUDA cores) is the
+//                          previous build, kept for A/B runs (RNAD_LEARNER_BWD_CUDA_CORES).
 //
 // Reference: nn/net.py:64-85 (forward_batch), learn/rnad.py:373-380, 424-425.
 // In the reference these are 8 x T small GEMMs + ~40 elementwise launches forward and
@@ -897,6 +900,313 @@ __global__ void __launch_bounds__(kBwdTcThreads, 2) learner_bwd_tc_kernel(const 
     if (warp == 0) tmem_dealloc<256>(tmem_base);
 }
 
+// -------------------------------------------------------- backward, software-pipelined
+//
+// The same mathematics as learner_bwd_tc_kernel, re-cut so that the tensor core never waits for the CUDA cores and
+// vice versa: ONE CTA per SM owns all 512 tensor-memory columns and both trunks, and a stage's H^T / S^T live in one
+// of TWO 128-column buffers.  A tile (128 rows) is eight stages s = (trunk, 128-unit hidden half, 64-row half);
+//     consumers (16 warps, thread = hidden unit x 16 rows):  wait recompute(s) -> relu^T / dh^T in place in buffer s & 1
+//     issuer (one elected lane, after the consumers' barrier): grad(s) = 16 MMAs reading buffer s & 1, then
+//                                                              recompute(s + 2) INTO that buffer, one commit
+// so while the consumers work on stage s + 1 (the other buffer, whose recompute was issued a stage earlier) the tensor
+// core runs grad(s) and recompute(s + 2).  MMAs of one thread execute in issue order, which is what lets
+// recompute(s + 2) overwrite the buffer grad(s) reads.  Four producer warps (one thread per tile row) build the next
+// tile's operands - the observation tile, x^T | 1, g and g^T - in the other half of a double-buffered shared-memory
+// region behind full / empty mbarriers, so the stream of stages never drains at a tile boundary.
+// [learner_bwd_tc_kernel: two CTAs per SM, MMA -> elementwise -> MMA serialised per stage, tensor pipe 31 % active.]
+constexpr int kBwd2Consumers = 512, kBwd2Producers = 128, kBwd2Issuers = 64;
+constexpr int kBwd2Threads = kBwd2Consumers + kBwd2Producers + kBwd2Issuers;
+
+template <int A>
+struct BwdTc2Plan : Shape<A> {
+    using S = Shape<A>;
+    using PT = BwdTcPlan<A>;
+    static constexpr int kNX = PT::kNX, kNG = PT::kNG, kLbo = PT::kLbo, kSboT = PT::kSboT;
+    // shared memory: the whole weight image of pack_bwd_tc_image_kernel (both trunks), then two tile buffers
+    static constexpr int kSW1 = PT::kB, kSB1 = PT::kB1, kSW2T = PT::kW2T;
+    static constexpr int kTile = round_up(PT::kImageBytes, 128);
+    static constexpr int kX = 0;                                        // within a tile buffer
+    static constexpr int kBX = kX + kTileM * S::KP * 4;
+    static constexpr int kBG = kBX + (kNX / 8) * kSboT;
+    static constexpr int kG = kBG + (kNG / 8) * kSboT;
+    static constexpr int kTileBytes = round_up(kG + kTileM * 32, 128);
+    static constexpr int kRed = kTile + 2 * kTileBytes;                 // [4 producer warps][8] sums of g
+    static constexpr int kBar = kRed + 4 * 32;                          // image, recompute[2], consumed[2], full[2], empty[2]
+    static constexpr int kTmem = kBar + 80;
+    static constexpr int kBytes = kTmem + 16;
+    // tensor memory: two stage buffers [H^T 64 | S^T 64], then per trunk 2 x kNX of D_w1 and 2 x 16 of D_w2
+    static constexpr int kAcc = 256, kAccTrunk = 2 * kNX + 2 * kNG;
+    static_assert(kAcc + 2 * kAccTrunk <= 512, "accumulators do not fit tensor memory");
+    static_assert(kBytes <= 227 * 1024, "shared memory plan does not fit");
+    static_assert(kTile % 16 == 0 && kBX % 16 == 0 && kBG % 16 == 0 && kG % 16 == 0 && kBar % 8 == 0, "alignment");
+};
+
+// Stage s of a CTA's stream: tile k = s >> 3; within the tile  half = s & 1 (the 128-unit hidden half - also the
+// tensor-memory buffer and the issuer warp of the stage), trunk = (s >> 1) & 1, row half = (s >> 2) & 1.  Consecutive
+// stages therefore add into DIFFERENT accumulators and every accumulator is only ever touched by ONE issuing thread,
+// whose MMAs execute in issue order: the sums are bit-reproducible although two warps issue.
+template <int A>
+__global__ void __launch_bounds__(kBwd2Threads, 1) learner_bwd_tc2_kernel(const float* __restrict__ obs, int64_t N,
+                                                                           int T_split, int64_t B_split,
+                                                                           const uint8_t* __restrict__ image,
+                                                                           const float* __restrict__ d_logit,
+                                                                           const float* __restrict__ d_v,
+                                                                           float* __restrict__ partials) {
+    using P = BwdTc2Plan<A>;
+    constexpr int KIN = P::KIN, KP = P::KP;
+    constexpr int kSbo1 = (KP / 4) * 128;
+    static_assert(A <= 4, "g[n] is staged as 8 floats");
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const int tid = threadIdx.x, warp = tid >> 5, lane32 = tid & 31;
+    const uint32_t bar_img = smem_u32(smem + P::kBar);
+    auto bar_r = [&](int b) { return bar_img + 8 + 8 * b; };        // recompute into buffer b complete (and every MMA its issuer issued before)
+    auto bar_c = [&](int b) { return bar_img + 24 + 8 * b; };       // the consumers are done with buffer b (relu^T / dh^T in place)
+    auto bar_full = [&](int b) { return bar_img + 40 + 8 * b; };    // tile operands of shared-memory buffer b written
+    auto bar_empty = [&](int b) { return bar_img + 56 + 8 * b; };   // every MMA reading shared-memory buffer b complete
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + P::kTmem);
+
+    if (warp == 0) tmem_alloc<512>(tmem_slot);
+    if (tid == 0) {
+        mbar_init(bar_img, 1);
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(bar_r(b), 1);
+            mbar_init(bar_c(b), kBwd2Consumers / 32);
+            mbar_init(bar_full(b), kBwd2Producers / 32);
+            mbar_init(bar_empty(b), 2);                              // one commit per issuer
+        }
+        mbar_fence_init();
+        tma_bulk_load(smem, image, BwdTcPlan<A>::kImageBytes, bar_img);
+    }
+    // operand rows that are never written stay zero (both tile buffers)
+    for (int i = tid; i < 2 * P::kTileBytes / 4; i += kBwd2Threads) reinterpret_cast<uint32_t*>(smem + P::kTile)[i] = 0u;
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    if (tid < kBwd2Consumers) {
+        // clear the gradient accumulators: columns [256, 256 + 2 * kAccTrunk), 16 at a time, split over the four column parts
+        const uint32_t lane_base = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+        for (int c = P::kAcc + (warp >> 2) * 16; c < P::kAcc + 2 * P::kAccTrunk; c += 64)
+            asm volatile(
+                "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1};" ::"r"(lane_base + c),
+                "r"(0u)
+                : "memory");
+        tcp::tmem_st_wait();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+
+    // which tiles this CTA walks: as in learner_bwd_tc_kernel, with the CTA in the role of the CTA pair
+    const int cta = blockIdx.x, n_ctas = gridDim.x;
+    const bool split = T_split > 0;
+    const int player = split ? (cta & 1) : 0;
+    const int64_t tiles_per_t = split ? (B_split + kTileM - 1) / kTileM : 0;
+    const int64_t my_first = split ? (cta >> 1) : cta, my_stride = split ? (n_ctas >> 1) : n_ctas;
+    const int64_t num_tiles = split ? (int64_t)((T_split - player + 1) / 2) * tiles_per_t : (N + kTileM - 1) / kTileM;
+    const int64_t my_tiles = my_first < num_tiles ? (num_tiles - 1 - my_first) / my_stride + 1 : 0;
+    const int64_t n_stages = my_tiles * 8;
+    float* dst = partials + (int64_t)cta * P::kParams;
+
+    if (tid >= kBwd2Consumers + kBwd2Producers) {
+        // ------------------------------------------------------------ issuers: warp b issues the stages with s & 1 == b
+        const int b = warp - (kBwd2Consumers + kBwd2Producers) / 32;
+        mbar_wait(bar_img, 0);
+        int64_t seen_full = -1;
+        auto need_tile = [&](int64_t k) {       // (whole warp) the producers have written tile k's operands
+            if (k != seen_full) {
+                mbar_wait(bar_full((int)(k & 1)), (uint32_t)(k >> 1) & 1u);
+                seen_full = k;
+            }
+        };
+        auto recompute = [&](int64_t s) {      // H^T | S^T of stage s into tensor-memory buffer b (elected lane)
+            const int64_t k = s >> 3;
+            const int trunk = (int)(s >> 1) & 1, rh = (int)(s >> 2) & 1;
+            const uint32_t tile = smem_u32(smem + P::kTile + (int)(k & 1) * P::kTileBytes);
+            const uint32_t d = tmem_base + (uint32_t)b * 128;
+            const uint32_t a_base = smem_u32(smem + P::kSW1) + trunk * P::kTrunkBytes + b * (128 / 8) * kSbo1;
+            const uint32_t b_base = tile + P::kX + rh * (64 / 8) * kSbo1;
+#pragma unroll
+            for (int ks = 0; ks < KP / 8; ++ks)
+                mma_ss_n(d, make_desc<KP>(a_base + ks * 256), make_desc<KP>(b_base + ks * 256), idesc_tf32(64), ks > 0);
+            mma_ss_n(d + 64, make_desc<8>(smem_u32(smem + P::kSW2T) + trunk * kHidden * 32 + b * 128 * 32),
+                     make_desc<8>(tile + P::kG + rh * 64 * 32), idesc_tf32(64), false);
+        };
+        if (b < n_stages) {                     // fill the pipeline: stage b
+            need_tile(0);
+            tc_fence_after();
+            if (tcp::elect_one()) {
+                recompute(b);
+                mma_commit(bar_r(b));
+            }
+            __syncwarp();
+        }
+#pragma unroll 1
+        for (int64_t s = b; s < n_stages; s += 2) {
+            const int trunk = (int)(s >> 1) & 1, rh = (int)(s >> 2) & 1;
+            const int64_t k = s >> 3;
+            const bool more = s + 2 < n_stages;
+            if (more) need_tile((s + 2) >> 3);
+            mbar_wait(bar_c(b), (uint32_t)(s >> 1) & 1u);            // relu^T / dh^T of stage s are in buffer b
+            tc_fence_after();
+            // grad(s): D_w2 += relu^T BG^T, D_w1 += dh^T BX^T (K = the stage's 64 rows); then recompute(s + 2) into the buffer
+            // just read; one commit covers both groups
+            const uint32_t tile = smem_u32(smem + P::kTile + (int)(k & 1) * P::kTileBytes);
+            const uint64_t bx = desc_lbo_sbo(tile + P::kBX + rh * 16 * P::kLbo, P::kLbo, P::kSboT);
+            const uint64_t bg = desc_lbo_sbo(tile + P::kBG + rh * 16 * P::kLbo, P::kLbo, P::kSboT);
+            const uint32_t acc = tmem_base + P::kAcc + trunk * P::kAccTrunk;
+            const uint32_t buf = tmem_base + (uint32_t)b * 128;
+            if (tcp::elect_one()) {
+#pragma unroll
+                for (int ks = 0; ks < 8; ++ks)
+                    tcp::mma_ts(acc + 2 * P::kNX + b * P::kNG, buf + ks * 8, bg + (uint64_t)((ks * 2 * P::kLbo) >> 4),
+                                idesc_tf32(P::kNG), true);
+#pragma unroll
+                for (int ks = 0; ks < 8; ++ks)
+                    tcp::mma_ts(acc + b * P::kNX, buf + 64 + ks * 8, bx + (uint64_t)((ks * 2 * P::kLbo) >> 4),
+                                idesc_tf32(P::kNX), true);
+                if ((s & 7) >= 6) mma_commit(bar_empty((int)(k & 1)));   // this issuer's last reads of the tile's shared-memory operands
+                if (more) recompute(s + 2);
+                mma_commit(bar_r(b));
+            }
+            __syncwarp();
+        }
+    } else if (tid >= kBwd2Consumers) {
+        // ------------------------------------------------------------ producers: one thread per tile row
+        const int n = tid - kBwd2Consumers, pw = n >> 5;
+        auto off_t = [](int c, int nn) { return (c >> 3) * P::kSboT + (nn >> 2) * P::kLbo + (c & 7) * 16 + (nn & 3) * 4; };
+        float gsum[1 + A];
+#pragma unroll
+        for (int a = 0; a <= A; ++a) gsum[a] = 0.f;
+        for (int64_t k = 0; k < my_tiles; ++k) {
+            const int64_t u = my_first + k * my_stride;
+            int64_t row = u * kTileM + n;
+            bool active = row < N;
+            if (split) {
+                const int64_t tt = 2 * (u / tiles_per_t) + player, j = (u % tiles_per_t) * kTileM + n;
+                row = tt * B_split + j;
+                active = j < B_split;
+            }
+            float x[KIN], g[1 + A];
+            load_row<KIN>(obs, active ? row : 0, active, x);
+            g[0] = active ? __ldg(d_v + row) : 0.f;
+#pragma unroll
+            for (int a = 0; a < A; ++a) g[1 + a] = active ? __ldg(d_logit + row * A + a) : 0.f;
+            const int tb = (int)(k & 1);
+            if (k >= 2) mbar_wait(bar_empty(tb), (uint32_t)((k >> 1) - 1) & 1u);   // the MMAs of tile k - 2 are done with it
+            uint8_t* tile = smem + P::kTile + tb * P::kTileBytes;
+            store_operand_row<KIN, KP, P::kBiasInK>(tile + P::kX, n, x);
+#pragma unroll
+            for (int kk = 0; kk < KIN; ++kk) *reinterpret_cast<float*>(tile + P::kBX + off_t(kk, n)) = to_tf32_fast(x[kk]);
+            *reinterpret_cast<float*>(tile + P::kBX + off_t(KIN, n)) = 1.f;
+            float g8[8];
+#pragma unroll
+            for (int a = 0; a < 8; ++a) g8[a] = a <= A ? to_tf32_fast(g[a < 1 + A ? a : 0]) : 0.f;
+#pragma unroll
+            for (int a = 0; a <= A; ++a) {
+                *reinterpret_cast<float*>(tile + P::kBG + off_t(a, n)) = g8[a];
+                gsum[a] += g[a];
+            }
+            *reinterpret_cast<float4*>(tile + P::kG + operand_offset<8>(n, 0)) = make_float4(g8[0], g8[1], g8[2], g8[3]);
+            *reinterpret_cast<float4*>(tile + P::kG + operand_offset<8>(n, 4)) = make_float4(g8[4], g8[5], g8[6], g8[7]);
+            fence_async_smem();
+            __syncwarp();
+            if (lane32 == 0) tcp::mbar_arrive(bar_full(tb));
+        }
+        // output-bias gradients: sums of g over the CTA's rows
+        float* s_red = reinterpret_cast<float*>(smem + P::kRed);
+#pragma unroll
+        for (int a = 0; a <= A; ++a) {
+            const float v = warp_sum(gsum[a]);
+            if (lane32 == 0) s_red[pw * 8 + a] = v;
+        }
+    } else {
+        // ------------------------------------------------------------ consumers: thread = hidden unit x 16 rows of a stage
+        const int quad = warp & 3, cpart = warp >> 2;             // TMEM lane quadrant (hidden unit), 16-column (row) part of a stage
+        const int j_local = quad * 32 + lane32;
+        const uint32_t tmem_lane = tmem_base + ((uint32_t)(quad * 32) << 16);
+        mbar_wait(bar_img, 0);
+        const float* b1 = reinterpret_cast<const float*>(smem + P::kSB1);
+        float bias_j[4];                                           // [trunk][half]
+#pragma unroll
+        for (int c = 0; c < 4; ++c) bias_j[c] = P::kBiasInK ? 0.f : b1[(c >> 1) * kHidden + (c & 1) * 128 + j_local];
+#pragma unroll 1
+        for (int64_t s = 0; s < n_stages; ++s) {
+            const int b = (int)(s & 1), trunk = (int)(s >> 1) & 1;
+            const float bias = bias_j[trunk * 2 + b];
+            mbar_wait(bar_r(b), (uint32_t)(s >> 1) & 1u);
+            tc_fence_after();
+            // ---- this thread's 16 rows of its hidden unit: relu^T over H^T, dh^T = S^T where h > 0, both in place
+            uint32_t hr[16], dh[16];
+            const uint32_t th = tmem_lane + b * 128 + cpart * 16;
+            tmem_ld16(th, hr);
+            tmem_ld16(th + 64, dh);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                const float h = __uint_as_float(hr[i]) + bias;
+                const bool on = h > 0.f;
+                hr[i] = on ? __float_as_uint(h) : 0u;
+                dh[i] = on ? dh[i] : 0u;
+            }
+            asm volatile(
+                "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(th),
+                "r"(hr[0]), "r"(hr[1]), "r"(hr[2]), "r"(hr[3]), "r"(hr[4]), "r"(hr[5]), "r"(hr[6]), "r"(hr[7]), "r"(hr[8]),
+                "r"(hr[9]), "r"(hr[10]), "r"(hr[11]), "r"(hr[12]), "r"(hr[13]), "r"(hr[14]), "r"(hr[15])
+                : "memory");
+            asm volatile(
+                "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(th + 64),
+                "r"(dh[0]), "r"(dh[1]), "r"(dh[2]), "r"(dh[3]), "r"(dh[4]), "r"(dh[5]), "r"(dh[6]), "r"(dh[7]), "r"(dh[8]),
+                "r"(dh[9]), "r"(dh[10]), "r"(dh[11]), "r"(dh[12]), "r"(dh[13]), "r"(dh[14]), "r"(dh[15])
+                : "memory");
+            tcp::tmem_st_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane32 == 0) tcp::mbar_arrive(bar_c(b));
+        }
+        // every gradient MMA complete: the last commit of each issuer
+        if (n_stages >= 2) {
+            mbar_wait(bar_r(0), (uint32_t)(n_stages >> 1) & 1u);
+            mbar_wait(bar_r(1), (uint32_t)(n_stages >> 1) & 1u);
+        }
+        tc_fence_after();
+
+        // ---- this CTA's partial gradient, flat in state_dict order: column part c reads (trunk, half) = (c >> 1, c & 1)
+        {
+            const int trunk = cpart >> 1, half = cpart & 1;
+            const int j = half * 128 + j_local;
+            const uint32_t acc = tmem_lane + P::kAcc + trunk * P::kAccTrunk;
+            uint32_t w[P::kNX];
+#pragma unroll
+            for (int q = 0; q < P::kNX / 16; ++q) tmem_ld16(acc + half * P::kNX + q * 16, w + q * 16);
+            tmem_ld_wait();
+            float* w1_dst = dst + (trunk == 0 ? P::kOffV0w : P::kOffP0w) + j * KIN;
+#pragma unroll
+            for (int kk = 0; kk < KIN; ++kk) w1_dst[kk] = __uint_as_float(w[kk]);
+            dst[(trunk == 0 ? P::kOffV0b : P::kOffP0b) + j] = __uint_as_float(w[KIN]);
+            uint32_t w2[16];
+            tmem_ld16(acc + 2 * P::kNX + half * P::kNG, w2);
+            tmem_ld_wait();
+            if (trunk == 0) {
+                dst[P::kOffV1w + j] = __uint_as_float(w2[0]);
+            } else {
+#pragma unroll
+                for (int a = 0; a < A; ++a) dst[P::kOffP1w + a * kHidden + j] = __uint_as_float(w2[1 + a]);
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (tid <= A) {
+        const float* s_red = reinterpret_cast<const float*>(smem + P::kRed);
+        const float v = (s_red[0 * 8 + tid] + s_red[1 * 8 + tid]) + (s_red[2 * 8 + tid] + s_red[3 * 8 + tid]);
+        if (tid == 0) dst[P::kOffV1b] = v;
+        else dst[P::kOffP1b + tid - 1] = v;
+    }
+    if (warp == 0) tmem_dealloc<512>(tmem_base);
+}
+
 // Sum of the per-CTA partial gradients in a FIXED order (deterministic): eight lanes per parameter take the partials
 // p = lane, lane + 8, ... (eight loads in flight per thread as well) and meet in a shuffle tree.
 // Split mode (gridDim.y == 2): blockIdx.y = player; player p's partials are the rows p, p + 2, ... (pairs with index
@@ -994,6 +1304,21 @@ int launch_backward(const float* obs, int64_t N, int T_split, int64_t B_split, c
             pack_bwd_tc_image_kernel<A><<<32, 256, 0, st>>>(w, image);
             RNAD_CHECK_LAUNCH("pack_bwd_tc_image_kernel");
             if (mode == 2) return RNAD_OK;
+        }
+        static const bool two_ctas = getenv("RNAD_LEARNER_BWD_V1") != nullptr;   // the previous kernel (two CTAs per SM), for A/B runs
+        if (!two_ctas) {
+            using P2 = BwdTc2Plan<A>;
+            // one CTA per SM (all 512 tensor-memory columns): more than half of the shared memory keeps a second one out
+            const size_t smem2 = P2::kBytes > 116 * 1024 ? P2::kBytes : 116 * 1024;
+            int rc = prepare<A>(learner_bwd_tc2_kernel<A>, smem2, "cudaFuncSetAttribute(learner_bwd_tc2)");
+            if (rc) return rc;
+            learner_bwd_tc2_kernel<A><<<(int)blocks, kBwd2Threads, smem2, st>>>(obs, N, T_split, B_split, image, d_logit, d_v,
+                                                                               partials);
+            RNAD_CHECK_LAUNCH("learner_bwd_tc2_kernel");
+            reduce_partials_kernel<<<dim3((P::kParams * 8 + 255) / 256, T_split > 0 ? 2 : 1), 256, 0, st>>>(
+                partials, (int)blocks, P::kParams, flat_grad);
+            RNAD_CHECK_LAUNCH("reduce_partials_kernel");
+            return RNAD_OK;
         }
         // two CTAs per SM (one per trunk, 256 TMEM columns each): pad the shared-memory request so that a third can
         // never become resident and spin inside tcgen05.alloc

@@ -6,9 +6,11 @@
 // work on one side's half-move, the other side's head warps sample actions, advance
 // the games and publish the next observations.  Game g of a tile is TMEM lane g.
 //
-//   warp 16 (elected lane)  issues every tcgen05.mma as ONE stream of chunks
+//   warps 16..19            issue the tcgen05.mma of ONE stream of chunks
 //                           (side 0, t) c0..c3, (side 1, t) c0..c3, (side 0, t+1) ...
-//                           A chunk is 128 hidden units of [value trunk | policy trunk]:
+//                           (one elected lane each; warp 16 + c issues the chunks with index c: several issuers
+//                           keep the tensor core's queue fed).  A chunk is 128 hidden units of
+//                           [policy trunk | value trunk]:
 //                             MMA1  D[128 x 128]  = obs[128 x KP] (TMEM) x W1_c^T (smem)      kind::tf32, 3 slots
 //                             MMA2  D2[128 x 16] += relu(D)[128 x 128] (TMEM) x W2_c^T (smem)
 //                           both with the A operand in tensor memory.  The policy trunk's chunks come

@@ -30,11 +30,13 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--config", default="cfg3")
     ap.add_argument("--reps", type=int, default=5)
+    ap.add_argument("--batch", type=int, default=0, help="games (default: the configuration's)")
     args = ap.parse_args()
     from environment.episode import Episodes
     from nn.net import MLP
 
     depth, a, c, batch = bench.CONFIGS[args.config]
+    batch = args.batch or batch
     dev = torch.device("cuda")
     tree = bench.fast_tree(args.config, depth, a, c, dev) if args.config in bench.FAST_TREE_CONFIGS else None
     if tree is None:

@@ -34,10 +34,16 @@ def nashconv(tree, net):
     return float(data.row_best[1] + data.col_best[1])
 
 
-def run_curve(rec, cfg, engine, dev):
-    from environment.tree import Tree
-    from learn.rnad import RNaD
+TREE_KEYS = ("index_tensor", "value_tensor", "chance_tensor", "expected_value_tensor", "legal_tensor",
+             "root_value_tensor", "solution_tensor")
 
+
+def build_tree(job):
+    """(worker process, CPU only) the reference's tree for (depth, seed), rebuilt from the seed; saved to a file."""
+    name, rec, cfg, path = job
+    from environment.tree import Tree
+
+    torch.set_num_threads(1)
     seed = rec["seed"]
     np.random.seed(seed)
     random.seed(seed)
@@ -48,6 +54,19 @@ def run_curve(rec, cfg, engine, dev):
                 depth_bound_lambda=lambda t: t.depth_bound - 1 - 2 * (random.random() < 0.5))
     tree.generate()
     assert int(tree.index_tensor.shape[0]) == rec["nodes"], "the seeded tree differs from the reference's"
+    torch.save({k: getattr(tree, k) for k in TREE_KEYS} | {"hash": tree.hash}, path)
+    return name
+
+
+def run_curve(rec, cfg, engine, dev, tree_file):
+    from environment.tree import Tree
+    from learn.rnad import RNaD
+
+    torch.manual_seed(rec["seed"])
+    tree = Tree(device=torch.device("cpu"), max_actions=cfg["max_actions"], max_transitions=cfg["max_transitions"],
+                transition_threshold=cfg["transition_threshold"], depth_bound=rec["depth"])
+    for key, value in torch.load(tree_file).items():
+        setattr(tree, key, value)
     tree.to(dev)
     trial = RNaD(tree=tree, device=dev, directory_name=f"cfg5_{engine}_d{rec['depth']}_s{seed}_{os.getpid()}", eta=cfg["eta"],
                  bounds=[cfg["updates"]], delta_m=[cfg["delta_m"]], lr=cfg["lr"], gamma_averaging=cfg["gamma_averaging"],
@@ -84,13 +103,26 @@ def main():
     depths = [int(d) for d in args.depths.split(",")]
     dev = torch.device("cuda")
     out = {"config": cfg, "engines": {}, "reference": {}}
+    # phase 1, host cores only: the 60 trees, rebuilt from their seeds in parallel (0.3 ms per node and process)
+    import multiprocessing as mp
+    import tempfile
+
+    tmp = tempfile.mkdtemp(prefix="cfg5_trees_")
+    jobs = [(name, rec, cfg, os.path.join(tmp, name + ".pt")) for name, rec in ref["curves"].items()
+            if rec["depth"] in depths and int(name.split("_s")[1]) < args.seeds]
+    jobs.sort(key=lambda j: -j[1]["nodes"])
+    t0 = time.time()
+    with mp.get_context("spawn").Pool(min(len(jobs), max(1, (os.cpu_count() or 2) - 1))) as pool:
+        pool.map(build_tree, jobs, chunksize=1)
+    tree_files = {name: path for name, _, _, path in jobs}
+    print(f"{len(jobs)} trees rebuilt in {time.time() - t0:.0f} s", flush=True)
     for engine in args.engines.split(","):
         out["engines"][engine] = {}
         for name, rec in ref["curves"].items():
-            if rec["depth"] not in depths or int(name.split("_s")[1]) >= args.seeds:
+            if name not in tree_files:
                 continue
             t0 = time.time()
-            curve = run_curve(rec, cfg, engine, dev)
+            curve = run_curve(rec, cfg, engine, dev, tree_files[name])
             out["engines"][engine][name] = curve
             out["reference"][name] = {"updates": rec["updates"], "nashconv": rec["nashconv"], "nodes": rec["nodes"], "depth": rec["depth"]}
             print(f"{engine} {name}: {rec['nodes']} nodes, NashConv {curve[0]:.3f} -> {curve[-1]:.3f} "
