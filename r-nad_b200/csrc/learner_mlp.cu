@@ -913,7 +913,13 @@ __global__ void __launch_bounds__(kBwdTcThreads, 2) learner_bwd_tc_kernel(const 
 // recompute(s + 2) overwrite the buffer grad(s) reads.  Four producer warps (one thread per tile row) build the next
 // tile's operands - the observation tile, x^T | 1, g and g^T - in the other half of a double-buffered shared-memory
 // region behind full / empty mbarriers, so the stream of stages never drains at a tile boundary.
-// [learner_bwd_tc_kernel: two CTAs per SM, MMA -> elementwise -> MMA serialised per stage, tensor pipe 31 % active.]
+// [learner_bwd_tc_kernel: two CTAs per SM, MMA -> elementwise -> MMA serialised per stage, tensor pipe 31 % active,
+//  147 us at cfg2; this kernel: 128 us, 35 %.  What bounds a stage (measured, scripts/microbench/tmem_ldst.cu and
+//  mma_shapes.cu): ~350 cycles of MMAs + ~320 cycles in which the consumers read and rewrite the stage's 64 KB of
+//  tensor memory (tcgen05.ld -> ALU -> tcgen05.st sustains ~200 B / cycle / SM each way, the load side being the slow
+//  one) + ~300 issue cycles of relu / mask arithmetic per SM sub-partition, and the tensor core's own tensor-memory
+//  traffic (A operands and accumulators) does not overlap with the consumers' - a variant with three buffers and two
+//  stages of slack ran no faster (133 us), i.e. the stage time is the SUM of these, not their maximum.]
 constexpr int kBwd2Consumers = 512, kBwd2Producers = 128, kBwd2Issuers = 64;
 constexpr int kBwd2Threads = kBwd2Consumers + kBwd2Producers + kBwd2Issuers;
 
@@ -1012,11 +1018,11 @@ __global__ void __launch_bounds__(kBwd2Threads, 1) learner_bwd_tc2_kernel(const 
     if (tid >= kBwd2Consumers + kBwd2Producers) {
         // ------------------------------------------------------------ issuers: warp b issues the stages with s & 1 == b
         const int b = warp - (kBwd2Consumers + kBwd2Producers) / 32;
-        mbar_wait(bar_img, 0);
+        tcp::mbar_wait_c(bar_img, 0);
         int64_t seen_full = -1;
         auto need_tile = [&](int64_t k) {       // (whole warp) the producers have written tile k's operands
             if (k != seen_full) {
-                mbar_wait(bar_full((int)(k & 1)), (uint32_t)(k >> 1) & 1u);
+                tcp::mbar_wait_c(bar_full((int)(k & 1)), (uint32_t)(k >> 1) & 1u);
                 seen_full = k;
             }
         };
@@ -1048,7 +1054,7 @@ __global__ void __launch_bounds__(kBwd2Threads, 1) learner_bwd_tc2_kernel(const 
             const int64_t k = s >> 3;
             const bool more = s + 2 < n_stages;
             if (more) need_tile((s + 2) >> 3);
-            mbar_wait(bar_c(b), (uint32_t)(s >> 1) & 1u);            // relu^T / dh^T of stage s are in buffer b
+            tcp::mbar_wait_c(bar_c(b), (uint32_t)(s >> 1) & 1u);            // relu^T / dh^T of stage s are in buffer b
             tc_fence_after();
             // grad(s): D_w2 += relu^T BG^T, D_w1 += dh^T BX^T (K = the stage's 64 rows); then recompute(s + 2) into the buffer
             // just read; one commit covers both groups
@@ -1094,7 +1100,7 @@ __global__ void __launch_bounds__(kBwd2Threads, 1) learner_bwd_tc2_kernel(const 
 #pragma unroll
             for (int a = 0; a < A; ++a) g[1 + a] = active ? __ldg(d_logit + row * A + a) : 0.f;
             const int tb = (int)(k & 1);
-            if (k >= 2) mbar_wait(bar_empty(tb), (uint32_t)((k >> 1) - 1) & 1u);   // the MMAs of tile k - 2 are done with it
+            if (k >= 2) tcp::mbar_wait_c(bar_empty(tb), (uint32_t)((k >> 1) - 1) & 1u);   // the MMAs of tile k - 2 are done with it
             uint8_t* tile = smem + P::kTile + tb * P::kTileBytes;
             store_operand_row<KIN, KP, P::kBiasInK>(tile + P::kX, n, x);
 #pragma unroll
@@ -1126,7 +1132,7 @@ __global__ void __launch_bounds__(kBwd2Threads, 1) learner_bwd_tc2_kernel(const 
         const int quad = warp & 3, cpart = warp >> 2;             // TMEM lane quadrant (hidden unit), 16-column (row) part of a stage
         const int j_local = quad * 32 + lane32;
         const uint32_t tmem_lane = tmem_base + ((uint32_t)(quad * 32) << 16);
-        mbar_wait(bar_img, 0);
+        tcp::mbar_wait_c(bar_img, 0);
         const float* b1 = reinterpret_cast<const float*>(smem + P::kSB1);
         float bias_j[4];                                           // [trunk][half]
 #pragma unroll
@@ -1135,7 +1141,7 @@ __global__ void __launch_bounds__(kBwd2Threads, 1) learner_bwd_tc2_kernel(const 
         for (int64_t s = 0; s < n_stages; ++s) {
             const int b = (int)(s & 1), trunk = (int)(s >> 1) & 1;
             const float bias = bias_j[trunk * 2 + b];
-            mbar_wait(bar_r(b), (uint32_t)(s >> 1) & 1u);
+            tcp::mbar_wait_c(bar_r(b), (uint32_t)(s >> 1) & 1u);
             tc_fence_after();
             // ---- this thread's 16 rows of its hidden unit: relu^T over H^T, dh^T = S^T where h > 0, both in place
             uint32_t hr[16], dh[16];
@@ -1167,8 +1173,8 @@ __global__ void __launch_bounds__(kBwd2Threads, 1) learner_bwd_tc2_kernel(const 
         }
         // every gradient MMA complete: the last commit of each issuer
         if (n_stages >= 2) {
-            mbar_wait(bar_r(0), (uint32_t)(n_stages >> 1) & 1u);
-            mbar_wait(bar_r(1), (uint32_t)(n_stages >> 1) & 1u);
+            tcp::mbar_wait_c(bar_r(0), (uint32_t)(n_stages >> 1) & 1u);
+            tcp::mbar_wait_c(bar_r(1), (uint32_t)(n_stages >> 1) & 1u);
         }
         tc_fence_after();
 

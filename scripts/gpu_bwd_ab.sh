@@ -1,0 +1,11 @@
+#!/bin/bash
+TAG=${1:-ab}
+mkdir -p gpurun_out
+timeout 600 python -m pytest tests/test_gpu_learner.py -m gpu -q --tb=short -x -k "backward or fused_engine" 2>&1 | tail -3
+timeout 600 python bench.py --steps 10 --warmup 3 --cpu-budget 0 --fp32-steps 0 --sustained-s 0 > gpurun_out/bench_${TAG}.json 2> gpurun_out/bench_${TAG}.err
+python - <<P
+import json
+d=json.loads(open('gpurun_out/bench_${TAG}.json').read().strip().splitlines()[-1])
+l=d['learner']; print('${TAG}', l['ms_per_update'], l['free_running']['ms_per_update'], {k:round(x['ms'],4) for k,x in l['roofline']['kernels'].items()})
+P
+tail -2 gpurun_out/bench_${TAG}.err
