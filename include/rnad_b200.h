@@ -132,6 +132,9 @@ typedef struct rnad_mlp_weights {
 typedef struct rnad_trajectory {
     int64_t* indices; int64_t* turns; float* observations; float* policy;
     float* actions; float* rewards; float* values; float* masks;
+    /* optional, may be NULL: the policy head's logits (T,B,A) f32 - not part of the reference's Episodes; an on-policy
+     * learner (actor == learner net) reuses them and `values` instead of evaluating its own net again (rnad.py:373) */
+    float* logits;
 } rnad_trajectory;
 
 RNAD_API int rnad_rollout(const uint32_t* ev_tab, const uint32_t* tr_tab, int A, int C,
@@ -175,7 +178,9 @@ RNAD_API int rnad_vtrace(const float* v, const float* valid, const int64_t* play
  * Inputs (T,B,...): indices i64 (valid = indices != 0), turns i64, mu = the
  * acting policy, actions_oh, rewards (player 0's; player 1 gets the negation),
  * masks, and from the nets: logit/pi/log_pi/v (learner), v_target_net
- * (target), log_pi_reg, log_pi_reg_ (regularisation nets).
+ * (target), log_pi_reg, log_pi_reg_ (regularisation nets).  pi and log_pi may both be
+ * NULL: they are then derived from logit and masks with net.py:76-80's formulas
+ * (e = mask ? exp(logit) : 0; pi = e / max(sum e, 1e-12); log_pi = mask ? logit - log(sum e) : 0).
  * Outputs: d_logit (T,B,A), d_v (T,B) required; the rest may be NULL:
  * pi_processed (T,B,A), v_target[2] (T,B), has_played[2] (T,B) i64,
  * learning_output[2] (T,B,A).  losses: device float[2] = {loss_v, loss_nerd};
@@ -264,12 +269,16 @@ RNAD_API int rnad_learner_backward_split(const float* observations, int T, int64
 /* The weight images (MMA operand order) of rnad_learner_forward and rnad_learner_backward(_split) depend only on the
  * nets: rnad_learner_pack writes them into `workspace` (what those calls otherwise do first), and the *_prepacked
  * variants then skip it - so that a captured learner step can pack on a side stream while the rollout runs. */
+/* others_only != 0 (in both calls alike): only the target net's value trunk and the regularisation nets' policy
+ * trunks are packed / evaluated - v_target, log_pi_reg, log_pi_reg_ are written, the learner's logit / pi / log_pi / v
+ * outputs are not touched (an on-policy step takes them from the rollout: rnad_trajectory.logits, .values). */
 RNAD_API int rnad_learner_pack(int A, const rnad_mlp_weights* net, const rnad_mlp_weights* target,
-                      const rnad_mlp_weights* reg, const rnad_mlp_weights* reg_, void* workspace, void* stream);
+                      const rnad_mlp_weights* reg, const rnad_mlp_weights* reg_, int others_only,
+                      void* workspace, void* stream);
 RNAD_API int rnad_learner_forward_prepacked(const float* observations, int64_t N, int A,
                          const rnad_mlp_weights* net, const rnad_mlp_weights* target,
                          const rnad_mlp_weights* reg, const rnad_mlp_weights* reg_,
-                         const rnad_learner_fwd_out* out, void* workspace, void* stream);
+                         const rnad_learner_fwd_out* out, int others_only, void* workspace, void* stream);
 RNAD_API int rnad_learner_backward_split_prepacked(const float* observations, int T, int64_t B, int A,
                                 const rnad_mlp_weights* net, const float* d_logit, const float* d_v,
                                 float* player_grads, void* workspace, void* stream);

@@ -48,7 +48,7 @@ class MlpWeights(Structure):
 
 class Trajectory(Structure):
     _fields_ = [(n, c_void_p) for n in ("indices", "turns", "observations", "policy", "actions", "rewards",
-                                        "values", "masks")]
+                                        "values", "masks", "logits")]
 
 
 class LearnerIO(Structure):
@@ -134,8 +134,9 @@ def lib():
     L.rnad_learner_backward_split.argtypes = [c_void_p, c_int, c_int64, c_int, POINTER(MlpWeights), c_void_p, c_void_p,
                                               c_void_p, c_void_p, c_void_p]
     L.rnad_learner_backward_split_prepacked.argtypes = L.rnad_learner_backward_split.argtypes
-    L.rnad_learner_forward_prepacked.argtypes = L.rnad_learner_forward.argtypes
-    L.rnad_learner_pack.argtypes = [c_int] + [POINTER(MlpWeights)] * 4 + [c_void_p, c_void_p]
+    L.rnad_learner_forward_prepacked.argtypes = [c_void_p, c_int64, c_int] + [POINTER(MlpWeights)] * 4 + [
+        POINTER(LearnerFwdOut), c_int, c_void_p, c_void_p]
+    L.rnad_learner_pack.argtypes = [c_int] + [POINTER(MlpWeights)] * 4 + [c_int, c_void_p, c_void_p]
     L.rnad_step_control.argtypes = [c_void_p, c_uint64, c_float, c_void_p]
     L.rnad_learner_tail.argtypes = [POINTER(TailArgs), c_void_p]
     L.rnad_xchg_bytes.restype = c_int64

@@ -95,12 +95,18 @@ struct TrajPtrs {
     float* rewards;
     float* values;
     float* masks;
+    float* logits;   // optional (may be null): the policy head's logits, (T,B,A)
 };
 
 // the per-(t, b) record except the observation (episode.py:196-211)
 template <int A>
 __device__ __forceinline__ void write_record(const TrajPtrs& o, int64_t slot, int node, int turn, int n_legal,
-                                             const float (&policy)[A], int action, float value, float reward) {
+                                             const float (&policy)[A], int action, float value, float reward,
+                                             const float (&logit)[A]) {
+    if (o.logits != nullptr) {
+#pragma unroll
+        for (int a = 0; a < A; ++a) st_stream(o.logits + slot * A + a, logit[a]);
+    }
     st_stream(o.indices + slot, (int64_t)node);
     st_stream(o.turns + slot, (int64_t)turn);
     st_stream(o.values + slot, value);

@@ -205,6 +205,10 @@ __global__ void __launch_bounds__(kThreads, 1) learner_fwd_tc2_kernel(const floa
         int slot = w % kSlots, rb = w % (2 * kSlots);
         uint32_t par = 0;
         int k_i = 0, c_i = w, k_j = 0, c_j = w + kSlots;
+        while (c_j >= kItemsPerTile) {           // (a launch over two or three trunks has only four or six items per tile)
+            c_j -= kItemsPerTile;
+            ++k_j;
+        }
 #pragma unroll 1
         for (uint32_t i = w; i < n_items; i += kMmaWarps) {
             const bool has_j = i + kSlots < n_items;
@@ -427,7 +431,9 @@ int launch_part(const float* obs, int64_t N, const Nets& nets, const Out& out, u
 }
 
 template <int A>
-int launch(const float* obs, int64_t N, const Nets& nets, const Out& out, uint8_t* workspace, cudaStream_t st, int mode) {
+int launch(const float* obs, int64_t N, const Nets& nets, const Out& out, uint8_t* workspace, cudaStream_t st, int mode,
+           bool others_only) {
+    if (others_only) return launch_part<A, 2, 3>(obs, N, nets, out, workspace, st, mode);
     if constexpr (A <= 3) {
         return launch_part<A, 0, 5>(obs, N, nets, out, workspace, st, mode);
     } else {
@@ -453,14 +459,14 @@ int64_t learner_forward_tc2_image_bytes(int A) {
 
 int learner_forward_tc2(const float* obs, int64_t N, int A, const rnad_mlp_weights* net, const rnad_mlp_weights* target,
                         const rnad_mlp_weights* reg, const rnad_mlp_weights* reg_, const rnad_learner_fwd_out* out,
-                        void* workspace, cudaStream_t st, int mode) {
+                        void* workspace, cudaStream_t st, int mode, bool others_only) {
     fwd2::Nets nets{*net, *target, *reg, *reg_};
     fwd2::Out o{nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     if (out != nullptr) o = fwd2::Out{out->logit, out->pi, out->log_pi, out->v, out->v_target, out->log_pi_reg, out->log_pi_reg_};
     switch (A) {
-        case 2: return fwd2::launch<2>(obs, N, nets, o, (uint8_t*)workspace, st, mode);
-        case 3: return fwd2::launch<3>(obs, N, nets, o, (uint8_t*)workspace, st, mode);
-        case 4: return fwd2::launch<4>(obs, N, nets, o, (uint8_t*)workspace, st, mode);
+        case 2: return fwd2::launch<2>(obs, N, nets, o, (uint8_t*)workspace, st, mode, others_only);
+        case 3: return fwd2::launch<3>(obs, N, nets, o, (uint8_t*)workspace, st, mode, others_only);
+        case 4: return fwd2::launch<4>(obs, N, nets, o, (uint8_t*)workspace, st, mode, others_only);
     }
     return RNAD_EUNSUPPORTED;
 }

@@ -33,7 +33,7 @@ bool learner_forward_tc2_supported(int A, int width);
 int64_t learner_forward_tc2_image_bytes(int A);
 int learner_forward_tc2(const float* obs, int64_t N, int A, const rnad_mlp_weights* net, const rnad_mlp_weights* target,
                         const rnad_mlp_weights* reg, const rnad_mlp_weights* reg_, const rnad_learner_fwd_out* out,
-                        void* workspace, cudaStream_t st, int mode);
+                        void* workspace, cudaStream_t st, int mode, bool others_only);
 
 namespace tc {
 
@@ -1374,11 +1374,13 @@ int rnad_learner_param_count(int A, int width) {
 
 static int learner_forward_impl(const float* observations, int64_t N, int A, const rnad_mlp_weights* net,
                                 const rnad_mlp_weights* target, const rnad_mlp_weights* reg, const rnad_mlp_weights* reg_,
-                                const rnad_learner_fwd_out* out, void* workspace, void* stream, int prepacked) {
+                                const rnad_learner_fwd_out* out, void* workspace, void* stream, int prepacked,
+                                int others_only = 0) {
     RNAD_REQUIRE(observations && out && workspace, "rnad_learner_forward: null pointer");
     RNAD_REQUIRE(weights_ok(net) && weights_ok(target) && weights_ok(reg) && weights_ok(reg_),
                  "rnad_learner_forward: null weight pointer");
-    RNAD_REQUIRE(out->logit && out->pi && out->log_pi && out->v && out->v_target && out->log_pi_reg && out->log_pi_reg_,
+    RNAD_REQUIRE(out->v_target && out->log_pi_reg && out->log_pi_reg_ &&
+                     (others_only || (out->logit && out->pi && out->log_pi && out->v)),
                  "rnad_learner_forward: null output pointer");
     RNAD_REQUIRE(N >= 0, "rnad_learner_forward: negative row count");
     if (!rnad_learner_mlp_supported(A, net->width) || target->width != net->width || reg->width != net->width ||
@@ -1391,8 +1393,8 @@ static int learner_forward_impl(const float* observations, int64_t N, int A, con
     static const bool v1 = getenv("RNAD_LEARNER_FWD_V1") != nullptr;   // the previous kernel, for A/B runs
     if (!v1 && learner_forward_tc2_supported(A, net->width))
         return learner_forward_tc2(observations, N, A, net, target, reg, reg_, out, workspace, (cudaStream_t)stream,
-                                   prepacked ? 1 : 0);
-    RNAD_REQUIRE(!prepacked, "rnad_learner_forward_prepacked: not available with RNAD_LEARNER_FWD_V1");
+                                   prepacked ? 1 : 0, others_only != 0);
+    RNAD_REQUIRE(!prepacked && !others_only, "rnad_learner_forward_prepacked: not available with RNAD_LEARNER_FWD_V1");
     tc::FwdNets nets{*net, *target, *reg, *reg_};
     tc::FwdOut o{out->logit, out->pi, out->log_pi, out->v, out->v_target, out->log_pi_reg, out->log_pi_reg_};
     cudaStream_t st = (cudaStream_t)stream;
@@ -1412,13 +1414,13 @@ int rnad_learner_forward(const float* observations, int64_t N, int A, const rnad
 
 int rnad_learner_forward_prepacked(const float* observations, int64_t N, int A, const rnad_mlp_weights* net,
                                    const rnad_mlp_weights* target, const rnad_mlp_weights* reg,
-                                   const rnad_mlp_weights* reg_, const rnad_learner_fwd_out* out, void* workspace,
-                                   void* stream) {
-    return learner_forward_impl(observations, N, A, net, target, reg, reg_, out, workspace, stream, 1);
+                                   const rnad_mlp_weights* reg_, const rnad_learner_fwd_out* out, int others_only,
+                                   void* workspace, void* stream) {
+    return learner_forward_impl(observations, N, A, net, target, reg, reg_, out, workspace, stream, 1, others_only);
 }
 
 int rnad_learner_pack(int A, const rnad_mlp_weights* net, const rnad_mlp_weights* target, const rnad_mlp_weights* reg,
-                      const rnad_mlp_weights* reg_, void* workspace, void* stream) {
+                      const rnad_mlp_weights* reg_, int others_only, void* workspace, void* stream) {
     RNAD_REQUIRE(workspace, "rnad_learner_pack: null pointer");
     RNAD_REQUIRE(weights_ok(net) && weights_ok(target) && weights_ok(reg) && weights_ok(reg_), "rnad_learner_pack: null weight pointer");
     if (!rnad_learner_mlp_supported(A, net->width) || target->width != net->width || reg->width != net->width ||
@@ -1428,7 +1430,7 @@ int rnad_learner_pack(int A, const rnad_mlp_weights* net, const rnad_mlp_weights
     }
     RNAD_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "rnad_learner_pack: workspace must be 256-byte aligned");
     cudaStream_t st = (cudaStream_t)stream;
-    int rc = learner_forward_tc2(nullptr, 0, A, net, target, reg, reg_, nullptr, workspace, st, 2);
+    int rc = learner_forward_tc2(nullptr, 0, A, net, target, reg, reg_, nullptr, workspace, st, 2, others_only != 0);
     if (rc) return rc;
     switch (A) {
         case 2: return tc::launch_backward<2>(nullptr, 0, 0, 0, *net, nullptr, nullptr, nullptr, (uint8_t*)workspace, st, 2);

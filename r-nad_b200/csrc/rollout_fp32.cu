@@ -106,7 +106,7 @@ __global__ void __launch_bounds__(128) rollout_fp32_kernel(RolloutArgs g) {
                 transition(g.tr_tab, A, g.C, node, row_action, action, u.chance, child, reward);
                 node = child;
             }
-            write_record<A>(g.out, slot, node_now, turn, n_legal, policy, action, value, reward);
+            write_record<A>(g.out, slot, node_now, turn, n_legal, policy, action, value, reward, logit);
         }
     }
     publish_stats(g.stats, last_valid, n_valid0, n_valid1, threadIdx.x & 31);

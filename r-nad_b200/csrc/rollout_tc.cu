@@ -288,7 +288,7 @@ __global__ void __launch_bounds__(kThreads, 2) rollout_tc_kernel(RolloutArgs g, 
                     transition(g.tr_tab, A, g.C, node, row_action, action, u.chance, child, reward);
                     node = child;
                 }
-                if (active) write_record<A>(g.out, slot, node_now, turn, n_legal, policy, action, value, reward);
+                if (active) write_record<A>(g.out, slot, node_now, turn, n_legal, policy, action, value, reward, logit);
             }
         }
     }

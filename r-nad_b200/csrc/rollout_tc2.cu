@@ -720,7 +720,7 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tc2_kernel(RolloutArgs g)
                     const float value = take_value();
                     ph_d2 ^= 1u;
                     if (active)
-                        write_record<A>(g.out, (int64_t)t * g.B + b, node_now, turn, n_legal, policy, action, value, reward);
+                        write_record<A>(g.out, (int64_t)t * g.B + b, node_now, turn, n_legal, policy, action, value, reward, logit);
                 }
                 if (more) {
                     store_obs(t + 1);

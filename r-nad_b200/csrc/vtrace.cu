@@ -162,6 +162,26 @@ __device__ __forceinline__ void vtrace_step(Carry& k, const Scalars& s, bool own
     vt_out = own ? vt : 0.f;
 }
 
+// net.py:76-80 (forward_batch): masked softmax / log-softmax of one row of logits
+template <int A>
+__device__ __forceinline__ void policy_from_logits(const float (&logit)[A], const float (&mask)[A], float (&pi)[A],
+                                                   float (&log_pi)[A]) {
+    float e[A];
+    float sum = 0.f;
+#pragma unroll
+    for (int a = 0; a < A; ++a) {
+        e[a] = mask[a] != 0.f ? expf(logit[a]) : 0.f;
+        sum += e[a];
+    }
+    const float denom = fmaxf(sum, 1e-12f);
+    const float log_sum = logf(sum);
+#pragma unroll
+    for (int a = 0; a < A; ++a) {
+        pi[a] = e[a] / denom;
+        log_pi[a] = mask[a] != 0.f ? logit[a] - log_sum : 0.f;
+    }
+}
+
 // vtrace.py:180-204: sum(a_oh * pi) * valid + (1 - valid)
 template <int A>
 __device__ __forceinline__ float select_prob(const float (&a_oh)[A], const float (&pi)[A], float valid) {
@@ -266,17 +286,26 @@ __global__ void __launch_bounds__(kLearnerBlock) learner_targets_kernel(rnad_lea
             const int turn = (int)io.turns[i];
             float a_oh[A], mu[A], pi[A], mask[A], L[A], ones[A], prod[A], pt[A], logit[A];
 #pragma unroll
+            float log_pi[A];
             for (int a = 0; a < A; ++a) {
                 a_oh[a] = io.actions_oh[i * A + a];
                 mu[a] = io.mu[i * A + a];
-                pi[a] = io.pi[i * A + a];
                 mask[a] = io.masks[i * A + a];
                 logit[a] = io.logit[i * A + a];
-                // rnad.py:382  log_pi - (alpha*log_pi_reg + (1-alpha)*log_pi_reg_)
-                L[a] = sub(io.log_pi[i * A + a],
-                           add(mul(p.alpha, io.log_pi_reg[i * A + a]), mul(one_minus_alpha, io.log_pi_reg_[i * A + a])));
                 ones[a] = 1.f;
             }
+            if (io.pi != nullptr) {
+#pragma unroll
+                for (int a = 0; a < A; ++a) {
+                    pi[a] = io.pi[i * A + a];
+                    log_pi[a] = io.log_pi[i * A + a];
+                }
+            } else {
+                policy_from_logits<A>(logit, mask, pi, log_pi);      // net.py:76-80
+            }
+#pragma unroll
+            for (int a = 0; a < A; ++a)   // rnad.py:382  log_pi - (alpha*log_pi_reg + (1-alpha)*log_pi_reg_)
+                L[a] = sub(log_pi[a], add(mul(p.alpha, io.log_pi_reg[i * A + a]), mul(one_minus_alpha, io.log_pi_reg_[i * A + a])));
             process_policy_row<A>(pi, mask, n_disc, p.eps_threshold, pt);
 #pragma unroll
             for (int a = 0; a < A; ++a) prod[a] = mul(pt[a], L[a]);
@@ -418,17 +447,26 @@ __global__ void __launch_bounds__(kTbGames* kTCap, 1024 / (kTbGames * kTCap))
         const int turn = active ? (int)io.turns[i] : 0;
         float a_oh[A], mu[A], pi[A], mask[A], L[A], ones[A], prod[A], pt[A], logit[A];
 #pragma unroll
+        float log_pi[A];
         for (int a = 0; a < A; ++a) {
             a_oh[a] = io.actions_oh[i * A + a];
             mu[a] = io.mu[i * A + a];
-            pi[a] = io.pi[i * A + a];
             mask[a] = io.masks[i * A + a];
             logit[a] = io.logit[i * A + a];
-            // rnad.py:382  log_pi - (alpha*log_pi_reg + (1-alpha)*log_pi_reg_)
-            L[a] = sub(io.log_pi[i * A + a],
-                       add(mul(p.alpha, io.log_pi_reg[i * A + a]), mul(one_minus_alpha, io.log_pi_reg_[i * A + a])));
             ones[a] = 1.f;
         }
+        if (io.pi != nullptr) {
+#pragma unroll
+            for (int a = 0; a < A; ++a) {
+                pi[a] = io.pi[i * A + a];
+                log_pi[a] = io.log_pi[i * A + a];
+            }
+        } else {
+            policy_from_logits<A>(logit, mask, pi, log_pi);      // net.py:76-80
+        }
+#pragma unroll
+        for (int a = 0; a < A; ++a)   // rnad.py:382  log_pi - (alpha*log_pi_reg + (1-alpha)*log_pi_reg_)
+            L[a] = sub(log_pi[a], add(mul(p.alpha, io.log_pi_reg[i * A + a]), mul(one_minus_alpha, io.log_pi_reg_[i * A + a])));
         const float v_net = io.v_target_net[i];
         const float reward = io.rewards[i];
         const float v_learner = io.v[i];
@@ -742,8 +780,9 @@ int rnad_count_played(const int64_t* indices, const int64_t* turns, int T, int64
 int rnad_learner_targets(const rnad_learner_io* io, const rnad_learner_params* p, int T, int64_t B, int A,
                          void* workspace, void* stream) {
     RNAD_REQUIRE(io && p && workspace, "rnad_learner_targets: null pointer");
+    RNAD_REQUIRE((io->pi == nullptr) == (io->log_pi == nullptr), "rnad_learner_targets: pi and log_pi must be given together");
     RNAD_REQUIRE(io->indices && io->turns && io->mu && io->actions_oh && io->rewards && io->masks && io->logit &&
-                     io->pi && io->log_pi && io->v && io->v_target_net && io->log_pi_reg && io->log_pi_reg_ &&
+                     io->v && io->v_target_net && io->log_pi_reg && io->log_pi_reg_ &&
                      io->d_logit && io->d_v,
                  "rnad_learner_targets: null tensor pointer");
     RNAD_REQUIRE(io->unnormalised ? io->loss_sums != nullptr : (io->losses && io->counts),

@@ -131,6 +131,10 @@ class LearnerStep:
                         for k in ("logit", "pi", "log_pi", "log_pi_reg", "log_pi_reg_")}
             self.fwd["v"] = torch.empty((self.t, self.b, 1), dtype=torch.float32, device=dev)
             self.fwd["v_target"] = torch.empty((self.t, self.b, 1), dtype=torch.float32, device=dev)
+            # the rollout's own policy-head logits: with the actor == the learner net (always, here) they and the recorded
+            # values ARE the learner's forward_batch outputs (rnad.py:373), so the step does not evaluate that net again
+            self.logits = torch.empty(shape, dtype=torch.float32, device=dev)
+            self.reuse_actor_outputs = os.environ.get("RNAD_STEP_REUSE", "1") != "0"
             self.d_logit = torch.empty(shape, dtype=torch.float32, device=dev)
             self.d_v = torch.empty((self.t, self.b), dtype=torch.float32, device=dev)
             self.loss_sums = torch.zeros(4, dtype=torch.float32, device=dev)
@@ -233,6 +237,7 @@ class LearnerStep:
         ctrl = self.ctrl.data_ptr()
         self._seed_dev = ctrl + _b200.StepCtrl.seed.offset
         self._traj = _b200.Trajectory(*self.arena.pointers())
+        self._traj.logits = self.logits.data_ptr()
         self._w = [_b200.mlp_weights(x, dev) for x in (trial.net, trial.net_target, trial.net_reg, trial.net_reg_)]
         self._fwd_out = _b200.LearnerFwdOut(**{k: v.data_ptr() for k, v in self.fwd.items()})
         io = _b200.LearnerIO()
@@ -244,7 +249,11 @@ class LearnerStep:
             setattr(io, name, self.fwd[key].data_ptr())
         io.d_logit, io.d_v = self.d_logit.data_ptr(), self.d_v.data_ptr()
         io.unnormalised, io.loss_sums = 1, self.loss_sums.data_ptr()
-        self._io = io
+        self._io_full = io                 # every net output from rnad_learner_forward (given trajectories: learn_from)
+        reuse = _b200.LearnerIO.from_buffer_copy(io)
+        reuse.logit, reuse.v = self.logits.data_ptr(), self.arena["values"].data_ptr()
+        reuse.pi = reuse.log_pi = None     # derived from the logits inside the kernel (net.py:76-80)
+        self._io = reuse                   # on-policy step: the learner's own outputs are the rollout's
         self._params = _b200.LearnerParams(0.0, float(trial.eta), 1.0, float(trial.c_bar), float(trial.roh_bar),
                                            float(trial.vtrace_gamma), float(trial.epsilon_threshold), int(trial.n_discrete),
                                            float(trial.neurd_clip), float(trial.beta), float(trial.value_weight),
@@ -265,10 +274,12 @@ class LearnerStep:
                 tail.xchg[r] = pointer
         self._tail = tail
 
-    def _calls(self):
-        """The step's five C-ABI calls, in order, as (name, thunk)."""
+    def _calls(self, reuse=None):
+        """The step's C-ABI calls, in order, as (name, thunk).  `reuse`: take the learner net's outputs from the rollout."""
         L, p = _b200.lib(), self.packed
         obs = self.arena["observations"].data_ptr()
+        reuse = self.reuse_actor_outputs if reuse is None else reuse
+        io = self._io if reuse else self._io_full
 
         def rollout():
             L.rnad_rollout(_b200.ptr(p.ev_tab), _b200.ptr(p.tr_tab), self.a, self.c, ctypes.byref(self._w[0]), self.b,
@@ -277,14 +288,16 @@ class LearnerStep:
                            _b200.ptr(self.rollout_ws), _b200.stream())
 
         def pack():
-            L.rnad_learner_pack(self.a, *[ctypes.byref(w) for w in self._w], _b200.ptr(self.workspace), _b200.stream())
+            L.rnad_learner_pack(self.a, *[ctypes.byref(w) for w in self._w], int(reuse), _b200.ptr(self.workspace),
+                                _b200.stream())
 
         def forward():
             L.rnad_learner_forward_prepacked(obs, self.t * self.b, self.a, *[ctypes.byref(w) for w in self._w],
-                                             ctypes.byref(self._fwd_out), _b200.ptr(self.workspace), _b200.stream())
+                                             ctypes.byref(self._fwd_out), int(reuse), _b200.ptr(self.workspace),
+                                             _b200.stream())
 
         def targets():
-            L.rnad_learner_targets(ctypes.byref(self._io), ctypes.byref(self._params), self.t, self.b, self.a,
+            L.rnad_learner_targets(ctypes.byref(io), ctypes.byref(self._params), self.t, self.b, self.a,
                                    _b200.ptr(self.targets_ws), _b200.stream())
 
         def backward():
@@ -301,7 +314,7 @@ class LearnerStep:
     def _enqueue(self, rollout=True):
         """The step's calls in stream order - except that the weight images of the learner's net passes, which depend on
         the nets only, are packed on a side stream while the rollout runs (a fork / join the CUDA graph keeps)."""
-        calls = dict(self._calls())
+        calls = dict(self._calls(reuse=self.reuse_actor_outputs and rollout))
         main = torch.cuda.current_stream(self.device)
         if self._side is None:
             self._side = torch.cuda.Stream(self.device)

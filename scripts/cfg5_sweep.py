@@ -62,7 +62,8 @@ def run_curve(rec, cfg, engine, dev, tree_file):
     from environment.tree import Tree
     from learn.rnad import RNaD
 
-    torch.manual_seed(rec["seed"])
+    seed = rec["seed"]
+    torch.manual_seed(seed)
     tree = Tree(device=torch.device("cpu"), max_actions=cfg["max_actions"], max_transitions=cfg["max_transitions"],
                 transition_threshold=cfg["transition_threshold"], depth_bound=rec["depth"])
     for key, value in torch.load(tree_file).items():

@@ -201,6 +201,43 @@ def test_graph_replay_equals_eager_equals_stepwise_path():
     assert float(trials["graph"].optimizer.state[next(trials["graph"].net.parameters())]["step"]) == 5.0
 
 
+def test_on_policy_step_reuses_the_rollouts_own_net_outputs():
+    """With the actor == the learner net the rollout's recorded logits and values ARE the learner's forward_batch outputs
+    (rnad.py:373): bit-identical to the forward kernel's on the same rows, so the step evaluates only the three other
+    trunks - and that three-trunk launch, several tiles per CTA, equals the five-trunk one on its outputs; the targets
+    kernel fed with logits alone (pi / log_pi derived inside, net.py:76-80) equals the one fed with the forward's."""
+    import _b200
+
+    tree = seeded_tree(ragged=True, depth=4)
+    trial = fresh_trial(tree, 24000, "pytest_step_reuse", "eager")      # 8 x 24,000 rows = 1,500 tiles on 148 CTAs
+    step = trial._step_engine_for()
+    reuse, full = dict(step._calls(reuse=True)), dict(step._calls(reuse=False))
+    _b200.lib().rnad_step_control(step.ctrl.data_ptr(), 777, 0.5, _b200.stream())
+    reuse["rollout"]()
+    full["pack"]()
+    full["forward"]()
+    full["targets"]()
+    torch.cuda.synchronize()
+    valid = step.arena["indices"] != 0
+    assert 0.3 < float(valid.float().mean()) < 0.95
+    assert torch.equal(step.logits, step.fwd["logit"]), "rollout logits != learner forward logits"
+    assert torch.equal(step.arena["values"], step.fwd["v"].squeeze(-1)), "rollout values != learner forward values"
+    close(step.arena["policy"][valid], step.fwd["pi"][valid], rtol=0, atol=1e-6)      # fast softmax in the rollout heads
+    ref = {k: step.fwd[k].clone() for k in ("v_target", "log_pi_reg", "log_pi_reg_")}
+    d_logit, d_v, sums = step.d_logit.clone(), step.d_v.clone(), step.loss_sums.clone()
+    for k in ref:
+        step.fwd[k].fill_(float("nan"))
+    reuse["pack"]()
+    reuse["forward"]()
+    reuse["targets"]()
+    torch.cuda.synchronize()
+    for k, want in ref.items():
+        assert torch.equal(step.fwd[k], want), f"three-trunk launch: {k} differs from the five-trunk launch"
+    assert torch.equal(step.d_v, d_v)
+    close(step.d_logit, d_logit, rtol=1e-5, atol=1e-6)
+    close(step.loss_sums, sums, rtol=1e-5, atol=1e-4)
+
+
 def test_logging_step_in_between_keeps_the_optimizer_state_consistent():
     """A step on the step-by-step path (as wandb logging takes) between graph steps shares params, moments and step count."""
     tree = seeded_tree()
