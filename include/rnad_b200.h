@@ -135,6 +135,8 @@ typedef struct rnad_trajectory {
     /* optional, may be NULL: the policy head's logits (T,B,A) f32 - not part of the reference's Episodes; an on-policy
      * learner (actor == learner net) reuses them and `values` instead of evaluating its own net again (rnad.py:373) */
     float* logits;
+    /* optional, may be NULL: every game's payoff for the row player (B) f32 = the sum of its rewards over time */
+    float* returns;
 } rnad_trajectory;
 
 RNAD_API int rnad_rollout(const uint32_t* ev_tab, const uint32_t* tr_tab, int A, int C,
@@ -296,11 +298,14 @@ typedef struct rnad_step_ctrl {   /* DEVICE memory, 32 bytes, zero-initialised b
     uint32_t seq;                 /* completed rnad_learner_tail calls: slot parity and flag value of the exchange */
     float adam_step;              /* Adam's step count (torch keeps it as a float) */
     uint32_t error;               /* bit r set: gave up waiting for rank r's gradients */
-    uint32_t reserved[2];
+    uint32_t seed_state[2];       /* rnad_step_advance: 64-bit splitmix64 state (low word, high word) */
 } rnad_step_ctrl;
 
 /* writes seed and alpha into *ctrl in stream order (a one-thread kernel; the arguments travel by value) */
 RNAD_API int rnad_step_control(rnad_step_ctrl* ctrl, uint64_t seed, float alpha, void* stream);
+/* the next rollout seed WITHOUT the host: state += 0x9E3779B97F4A7C15, seed = splitmix64's mix of the state >> 2 (a
+ * one-thread kernel; inside a captured graph every replay plays a new, host-predictable seed) */
+RNAD_API int rnad_step_advance(rnad_step_ctrl* ctrl, void* stream);
 
 /* rnad_learner_tail: [sum over ranks of (G_0 | G_1 | N_0, N_1 | loss numerators) over NVLink peer memory] ->
  * g = G_0 / N_0 + G_1 / N_1 -> clip_grad_norm_(grad_clip) (rnad.py:456) -> Adam (torch.optim.Adam semantics without

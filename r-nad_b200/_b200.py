@@ -30,7 +30,7 @@ EXPORTS = (
     "rnad_learner_targets", "rnad_learner_mlp_supported", "rnad_learner_mlp_workspace_bytes",
     "rnad_learner_param_count", "rnad_learner_forward", "rnad_learner_backward", "rnad_learner_backward_split",
     "rnad_learner_pack", "rnad_learner_forward_prepacked", "rnad_learner_backward_split_prepacked",
-    "rnad_step_control", "rnad_learner_tail", "rnad_xchg_bytes", "rnad_xchg_create", "rnad_xchg_open", "rnad_xchg_close",
+    "rnad_step_control", "rnad_step_advance", "rnad_learner_tail", "rnad_xchg_bytes", "rnad_xchg_create", "rnad_xchg_open", "rnad_xchg_close",
     "rnad_xchg_destroy",
 )
 MAX_PEERS = 16
@@ -48,7 +48,7 @@ class MlpWeights(Structure):
 
 class Trajectory(Structure):
     _fields_ = [(n, c_void_p) for n in ("indices", "turns", "observations", "policy", "actions", "rewards",
-                                        "values", "masks", "logits")]
+                                        "values", "masks", "logits", "returns")]
 
 
 class LearnerIO(Structure):
@@ -74,7 +74,7 @@ class LearnerParams(Structure):
 class StepCtrl(Structure):
     """rnad_step_ctrl (device memory; mirrored here for offsets and for reading it back)."""
     _fields_ = [("seed", c_uint64), ("alpha", c_float), ("seq", ctypes.c_uint32), ("adam_step", c_float),
-                ("error", ctypes.c_uint32), ("reserved", ctypes.c_uint32 * 2)]
+                ("error", ctypes.c_uint32), ("seed_state", ctypes.c_uint32 * 2)]
 
 
 class TailArgs(Structure):
@@ -138,6 +138,7 @@ def lib():
         POINTER(LearnerFwdOut), c_int, c_void_p, c_void_p]
     L.rnad_learner_pack.argtypes = [c_int] + [POINTER(MlpWeights)] * 4 + [c_int, c_void_p, c_void_p]
     L.rnad_step_control.argtypes = [c_void_p, c_uint64, c_float, c_void_p]
+    L.rnad_step_advance.argtypes = [c_void_p, c_void_p]
     L.rnad_learner_tail.argtypes = [POINTER(TailArgs), c_void_p]
     L.rnad_xchg_bytes.restype = c_int64
     L.rnad_xchg_bytes.argtypes = [c_int, c_int]

@@ -96,6 +96,7 @@ struct TrajPtrs {
     float* values;
     float* masks;
     float* logits;   // optional (may be null): the policy head's logits, (T,B,A)
+    float* returns;  // optional (may be null): every game's payoff for the row player = the sum of its rewards, (B)
 };
 
 // the per-(t, b) record except the observation (episode.py:196-211)

@@ -57,6 +57,17 @@ __global__ void step_control_kernel(rnad_step_ctrl* ctrl, uint64_t seed, float a
     ctrl->alpha = alpha;
 }
 
+// splitmix64 (Steele, Lea, Flood 2014): state += golden gamma, seed = the mixed state's upper 62 bits
+__global__ void step_advance_kernel(rnad_step_ctrl* ctrl) {
+    uint64_t state = ((uint64_t)ctrl->seed_state[1] << 32 | ctrl->seed_state[0]) + 0x9E3779B97F4A7C15ull;
+    ctrl->seed_state[0] = (uint32_t)state;
+    ctrl->seed_state[1] = (uint32_t)(state >> 32);
+    uint64_t z = state;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    ctrl->seed = (z ^ (z >> 31)) >> 2;
+}
+
 // The tail runs as ONE thread-block cluster of kTailCtas CTAs (8192 threads: one or two parameters per thread, so
 // every pass is a single round of independent loads instead of a latency-bound loop) synchronised by the hardware
 // cluster barrier; the squared gradient norm is reduced per CTA and the CTAs' partial sums are read by every CTA
@@ -224,6 +235,13 @@ int rnad_step_control(rnad_step_ctrl* ctrl, uint64_t seed, float alpha, void* st
     RNAD_REQUIRE(ctrl != nullptr, "rnad_step_control: null pointer");
     step_control_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(ctrl, seed, alpha);
     RNAD_CHECK_LAUNCH("step_control_kernel");
+    return RNAD_OK;
+}
+
+int rnad_step_advance(rnad_step_ctrl* ctrl, void* stream) {
+    RNAD_REQUIRE(ctrl != nullptr, "rnad_step_advance: null pointer");
+    step_advance_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(ctrl);
+    RNAD_CHECK_LAUNCH("step_advance_kernel");
     return RNAD_OK;
 }
 

@@ -38,7 +38,7 @@ extern "C" int rnad_rollout(const uint32_t* ev_tab, const uint32_t* tr_tab, int 
     g.game_offset = game_offset;
     g.uniforms = uniforms;
     g.out = TrajPtrs{out->indices, out->turns, out->observations, out->policy,
-                     out->actions, out->rewards, out->values, out->masks, out->logits};
+                     out->actions, out->rewards, out->values, out->masks, out->logits, out->returns};
     g.stats = stats;
     switch (precision) {
         case RNAD_PREC_FP32: return rollout_fp32(g, st);

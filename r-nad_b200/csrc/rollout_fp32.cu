@@ -43,6 +43,7 @@ __global__ void __launch_bounds__(128) rollout_fp32_kernel(RolloutArgs g) {
     for (int64_t b = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; b < g.B; b += (int64_t)gridDim.x * blockDim.x) {
         int node = 1;   // every game starts at the root (episode.py:22)
         int row_action = 0;
+        float game_return = 0.f;
         Node<A> n;
         for (int t = 0; t < g.T; ++t) {
             const int turn = t & 1;
@@ -106,8 +107,10 @@ __global__ void __launch_bounds__(128) rollout_fp32_kernel(RolloutArgs g) {
                 transition(g.tr_tab, A, g.C, node, row_action, action, u.chance, child, reward);
                 node = child;
             }
+            game_return += reward;
             write_record<A>(g.out, slot, node_now, turn, n_legal, policy, action, value, reward, logit);
         }
+        if (g.out.returns != nullptr) g.out.returns[b] = game_return;
     }
     publish_stats(g.stats, last_valid, n_valid0, n_valid1, threadIdx.x & 31);
 }

@@ -152,6 +152,7 @@ __global__ void __launch_bounds__(kThreads, 2) rollout_tc_kernel(RolloutArgs g, 
         const int tile_games = (int)min((int64_t)kTileM, g.B - tile_base);
         int node = active ? 1 : 0;
         int row_action = 0;
+        float game_return = 0.f;
         Node<A> n;
 #pragma unroll
         for (int i = 0; i < A * A; ++i) n.ev[i] = 0.f;
@@ -288,9 +289,11 @@ __global__ void __launch_bounds__(kThreads, 2) rollout_tc_kernel(RolloutArgs g, 
                     transition(g.tr_tab, A, g.C, node, row_action, action, u.chance, child, reward);
                     node = child;
                 }
+                game_return += reward;
                 if (active) write_record<A>(g.out, slot, node_now, turn, n_legal, policy, action, value, reward, logit);
             }
         }
+        if (half == 0 && active && g.out.returns != nullptr) g.out.returns[b] = game_return;
     }
 
     publish_stats(g.stats, last_valid, n_valid0, n_valid1, tid & 31);

@@ -559,6 +559,7 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tc2_kernel(RolloutArgs g)
             const bool active = b < g.B;                      // (a side without a tile plays along with idle lanes)
             int node = active ? 1 : 0;
             int row_action = 0;
+            float game_return = 0.f;
             Node<A> n;
 #pragma unroll
             for (int i = 0; i < A * A; ++i) n.ev[i] = 0.f;
@@ -719,6 +720,7 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tc2_kernel(RolloutArgs g)
                     // ---- from here on off the critical path: the tensor core and the epilogue warps are busy
                     const float value = take_value();
                     ph_d2 ^= 1u;
+                    game_return += reward;
                     if (active)
                         write_record<A>(g.out, (int64_t)t * g.B + b, node_now, turn, n_legal, policy, action, value, reward, logit);
                 }
@@ -730,6 +732,7 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tc2_kernel(RolloutArgs g)
                 }
                 if (t >= 0 && lane_g == 0) TR(side, t, 4);
             }
+            if (active && g.out.returns != nullptr) g.out.returns[b] = game_return;
         }
         publish_stats(g.stats, last_valid, n_valid0, n_valid1, lane);
     }

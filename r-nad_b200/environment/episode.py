@@ -448,10 +448,12 @@ class Episodes:
 class SelfPlay:
     """
     Repeated self-play with one actor net as a replayable unit: the trajectory lives in one static arena, the rollout
-    seed in device memory (`rnad_step_control`), and - after one eager call - every `play()` is one tiny kernel launch
-    plus ONE CUDA-graph replay of
+    seed in device memory, and - after one eager call - every `play()` is ONE CUDA-graph replay of
 
-        [weights_host -> the actor's flat parameter buffer]  ->  rnad_rollout  ->  [per-game returns -> returns_host]
+        [weights_host -> the actor's flat parameter buffer]  ->  next seed  ->  rnad_rollout  ->  [returns -> returns_host]
+
+    The seeds are a splitmix64 sequence started from one draw of torch's generator at construction and advanced on the
+    device (`rnad_step_advance`); the host mirrors it, so `episodes.states.seed` names every batch's seed.
 
     `weights_host` (optional, pinned fp32, state_dict order, `sum(p.numel())` floats): fresh actor weights arrive from
     host memory before every batch (a learner elsewhere, a checkpoint).  `returns_host` (optional, pinned fp32, B
@@ -480,7 +482,10 @@ class SelfPlay:
         self.weights_host, self.returns_host = weights_host, returns_host
         with torch.cuda.device(dev):
             self.arena = _TrajectoryArena(self.t_max, self.batch_size, packed.A, dev)
-            self.ctrl = torch.zeros(ctypes.sizeof(_b200.StepCtrl), dtype=torch.uint8, device=dev)
+            self._seed_state = _fresh_seed()
+            host = _b200.StepCtrl()
+            host.seed_state[0], host.seed_state[1] = self._seed_state & 0xFFFFFFFF, self._seed_state >> 32
+            self.ctrl = torch.frombuffer(bytearray(bytes(host)), dtype=torch.uint8).to(dev)
             n = sum(p.numel() for p in net.parameters())
             self.flat = torch.empty(n, dtype=torch.float32, device=dev)
             offset = 0
@@ -499,6 +504,8 @@ class SelfPlay:
             raise _b200.RnadError(f"returns_host must be a pinned fp32 tensor of {self.batch_size} elements")
         self._w = _b200.mlp_weights(net, dev)
         self._traj = _b200.Trajectory(*self.arena.pointers())
+        if self.returns is not None:
+            self._traj.returns = self.returns.data_ptr()     # the kernel sums each game's rewards itself
         self.episodes = Episodes(tree, self.batch_size)
         self.episodes.finished = True
         self.episodes.precision = precision
@@ -508,19 +515,26 @@ class SelfPlay:
         L, p = _b200.lib(), self.packed
         if self.weights_host is not None:
             self.flat.copy_(self.weights_host, non_blocking=True)
+        L.rnad_step_advance(self.ctrl.data_ptr(), _b200.stream())
         L.rnad_rollout(_b200.ptr(p.ev_tab), _b200.ptr(p.tr_tab), p.A, p.C, ctypes.byref(self._w), self.batch_size,
                        self.t_max, 0, self.ctrl.data_ptr() + _b200.StepCtrl.seed.offset, self.episodes.states.game_offset,
                        None, _b200.PRECISIONS[self.precision], ctypes.byref(self._traj), self.arena.stats.data_ptr(),
                        _b200.ptr(self.workspace), _b200.stream())
         if self.returns_host is not None:
-            # a game is paid once, when it ends: its return is the sum of its rewards over time
-            torch.sum(self.arena["rewards"], dim=0, out=self.returns)
             self.returns_host.copy_(self.returns, non_blocking=True)
 
+    def _next_seed(self) -> int:
+        """The host's mirror of rnad_step_advance (splitmix64)."""
+        mask = 0xFFFFFFFFFFFFFFFF
+        self._seed_state = (self._seed_state + 0x9E3779B97F4A7C15) & mask
+        z = self._seed_state
+        z = ((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9) & mask
+        z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & mask
+        return (z ^ (z >> 31)) >> 2
+
     def play(self) -> "Episodes":
-        seed = _fresh_seed()
+        seed = self._next_seed()
         with torch.cuda.device(self.device):
-            _b200.lib().rnad_step_control(self.ctrl.data_ptr(), seed, 0.0, _b200.stream())
             if self.graph is not None:
                 self.graph.replay()
             elif not self.use_graph or self.calls == 0:

@@ -417,3 +417,41 @@ def test_rollout_with_weights_that_are_views_of_a_flat_buffer(golden, precision)
     ep = Episodes(tree, 700)
     ep.generate(net, precision=precision)
     check_rollout_against_oracle(ep, tables_of(g), w, seed=ep.states.seed, tol=TOL[precision], precision=precision)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "tf32", "tf32x2"])
+def test_selfplay_graph_equals_generate_and_carries_host_buffers(golden, precision):
+    """environment.episode.SelfPlay: [weights H2D] -> rollout -> [returns D2H] replayed as one CUDA graph == Episodes.generate
+    under the same seed and weights; fresh weights in the pinned host buffer are the next batch's actor; the per-game
+    returns the kernel sums itself equal the rewards summed over time."""
+    from environment.episode import Episodes, SelfPlay
+
+    name, g = golden
+    tree = tree_from_golden(g, DEV)
+    net, w = wide_net(tree.max_actions, 3, DEV)
+    net.device = torch.device(DEV)
+    batch = 3000
+    n_params = sum(p.numel() for p in net.parameters())
+    weights_host = torch.cat([p.detach().cpu().flatten() for p in net.parameters()]).pin_memory()
+    returns_host = torch.empty(batch, dtype=torch.float32).pin_memory()
+    assert weights_host.numel() == n_params
+    torch.manual_seed(40)
+    play = SelfPlay(tree, batch, net, precision=precision, weights_host=weights_host, returns_host=returns_host)
+    seeds = set()
+    for i in range(4):                         # eager, capture + replay, replay, replay with new weights
+        if i == 3:
+            weights_host.mul_(1.5)            # "a learner elsewhere" sent new weights
+        ep = play.play()
+        torch.cuda.synchronize()
+        got = {k: ep.full(k).clone() for k in ("indices", "policy", "actions", "rewards", "values", "observations")}
+        seed = ep.states.seed
+        assert torch.equal(torch.cat([p.detach().flatten() for p in net.parameters()]).cpu(), weights_host)
+        ref = Episodes(tree, batch)
+        ref.states.seed = seed               # the seed the device-side splitmix64 sequence gave this batch, as mirrored on the host
+        ref.generate(net, precision=precision)
+        for k, v in got.items():
+            assert torch.equal(v, ref.full(k)), f"play {i}: {k} differs from Episodes.generate"
+        assert torch.equal(returns_host, got["rewards"].sum(0).cpu()), "per-game returns"
+        assert ep.t_eff == ref.t_eff
+        seeds.add(seed)
+    assert play.graph is not None and len(seeds) == 4
