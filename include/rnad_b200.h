@@ -40,6 +40,9 @@ extern "C" {
 #define RNAD_PREC_FP32 0 /* FFMA on the CUDA cores, fp32 throughout (validation build) */
 #define RNAD_PREC_TF32 1 /* first layer on tcgen05 tensor cores, kind::tf32, fp32 accumulate in TMEM */
 #define RNAD_PREC_TF32X2 2 /* both layers on tcgen05 (kind::tf32); the second reads relu(hidden) from tensor memory */
+#define RNAD_PREC_F16X2 3 /* the same pipeline with kind::f16: fp16 operands (11-bit significand like tf32, round to nearest
+                           * even; observations, weights and activations of this net are far inside fp16's range), fp32
+                           * accumulate; K = 16 per MMA: half the tensor-core dispatches, hidden activations packed in pairs */
 /* Reproducibility: for one seed, tables and weights every engine writes the same bits on every launch (no result depends
  * on the order in which warps or CTAs were scheduled). */
 
@@ -119,7 +122,7 @@ RNAD_API int rnad_sample_categorical(const float* p, int64_t B, int N, const flo
  *       normalisers N_0, N_1 of both losses (vtrace.py:370-374, 387-389), so that nobody has to count them
  *       again;  [3] reserved.
  * workspace: 16-byte aligned device scratch of rnad_rollout_workspace_bytes() (RNAD_PREC_TF32 only: the
- * weight image in MMA operand order; RNAD_PREC_TF32X2 and RNAD_PREC_FP32 need none); may be NULL when 0.
+ * weight image in MMA operand order; RNAD_PREC_TF32X2, RNAD_PREC_F16X2 and RNAD_PREC_FP32 need none); may be NULL when 0.
  * ------------------------------------------------------------------------ */
 typedef struct rnad_mlp_weights {
     const float* value_fc0_w; const float* value_fc0_b;
@@ -150,7 +153,7 @@ RNAD_API int64_t rnad_rollout_workspace_bytes(int A, int width, int precision);
 
 /* 1 if the RNAD_PREC_TF32 engine serves this net shape (width == 256, 2 <= A <= 4), else 0 */
 RNAD_API int rnad_rollout_tc_supported(int A, int width);
-/* 1 if the RNAD_PREC_TF32X2 engine serves this shape (width == 256, 2 <= A <= 4, max_transitions C <= 4), else 0 */
+/* 1 if the RNAD_PREC_TF32X2 / RNAD_PREC_F16X2 engine serves this shape (width == 256, 2 <= A <= 4, max_transitions C <= 4), else 0 */
 RNAD_API int rnad_rollout_tc2_supported(int A, int width, int C);
 
 /* ------------------------------------------------------------------------

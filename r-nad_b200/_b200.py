@@ -20,7 +20,8 @@ LIB_PATH = os.environ.get("RNAD_B200_LIB") or os.path.join(_HERE, "lib", "librna
 PREC_FP32 = 0
 PREC_TF32 = 1
 PREC_TF32X2 = 2
-PRECISIONS = {"fp32": PREC_FP32, "tf32": PREC_TF32, "tf32x2": PREC_TF32X2}
+PREC_F16X2 = 3
+PRECISIONS = {"fp32": PREC_FP32, "tf32": PREC_TF32, "tf32x2": PREC_TF32X2, "f16x2": PREC_F16X2}
 
 EXPORTS = (
     "rnad_last_error", "rnad_version", "rnad_device_sm_count", "rnad_packed_strides", "rnad_tree_pack",

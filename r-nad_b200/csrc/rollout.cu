@@ -43,7 +43,8 @@ extern "C" int rnad_rollout(const uint32_t* ev_tab, const uint32_t* tr_tab, int 
     switch (precision) {
         case RNAD_PREC_FP32: return rollout_fp32(g, st);
         case RNAD_PREC_TF32: return rollout_tc(g, workspace, st);
-        case RNAD_PREC_TF32X2: return rollout_tc2(g, workspace, st);
+        case RNAD_PREC_TF32X2: return rollout_tc2(g, workspace, st, false);
+        case RNAD_PREC_F16X2: return rollout_tc2(g, workspace, st, true);
     }
     set_error("rnad_rollout: unknown precision %d", precision);
     return RNAD_EINVAL;
@@ -58,6 +59,6 @@ extern "C" int rnad_rollout_tc2_supported(int A, int width, int C) { return roll
 // bytes of device scratch rnad_rollout needs for this net shape and engine (0 = none)
 extern "C" int64_t rnad_rollout_workspace_bytes(int A, int width, int precision) {
     if (precision == RNAD_PREC_TF32 && rollout_tc_supported(A, width)) return rollout_tc_workspace_bytes(A);
-    if (precision == RNAD_PREC_TF32X2 && rollout_tc2_supported(A, width, 1)) return rollout_tc2_workspace_bytes(A);
+    if ((precision == RNAD_PREC_TF32X2 || precision == RNAD_PREC_F16X2) && rollout_tc2_supported(A, width, 1)) return rollout_tc2_workspace_bytes(A);
     return 0;
 }

@@ -36,7 +36,7 @@ int rollout_fp32(const RolloutArgs& g, cudaStream_t st);
 int rollout_tc(const RolloutArgs& g, void* workspace, cudaStream_t st);
 bool rollout_tc_supported(int A, int width);
 int64_t rollout_tc_workspace_bytes(int A);
-int rollout_tc2(const RolloutArgs& g, void* workspace, cudaStream_t st);
+int rollout_tc2(const RolloutArgs& g, void* workspace, cudaStream_t st, bool f16);
 int64_t rollout_tc2_workspace_bytes(int A);
 bool rollout_tc2_supported(int A, int width, int C);
 

@@ -83,16 +83,24 @@ __host__ __device__ constexpr int obs_col(int side) { return kSideCol + 64 * sid
 // observation only needs the sampled action, so the heads work on it while the value chunks are still in the ring.
 __host__ __device__ constexpr int chunk_hidden(int c) { return c < 2 ? kHidden + c * kChunk : (c - 2) * kChunk; }
 
-template <int A>
+// F16 = false: kind::tf32 (RNAD_PREC_TF32X2); F16 = true: kind::f16 with fp16 operands (RNAD_PREC_F16X2) - the same 11-bit
+// significand as tf32 (payoffs, weights and activations of this net sit far inside fp16's range), but K = 16 per MMA
+// instead of 8: half the tensor-core dispatches for both layers, and relu(hidden) goes back into tensor memory as packed
+// pairs (half the tcgen05.st bytes, one cvt.rn.relu.f16x2 per two hidden units).
+template <int A, bool F16>
 struct Plan {
     static constexpr int KIN = 2 * A * A;
-    static constexpr bool kBiasInK = (KIN % 8) != 0;
-    static constexpr int KP = round_up(KIN + (kBiasInK ? 1 : 0), 8);
+    static constexpr int kEsz = F16 ? 2 : 4;                         // bytes per operand element
+    static constexpr int kKStep = 32 / kEsz;                         // K of one MMA
+    static constexpr bool kBiasInK = (KIN % kKStep) != 0;
+    static constexpr int KP = round_up(KIN + (kBiasInK ? 1 : 0), kKStep);
+    static constexpr int kObsCols = KP * kEsz / 4;                   // tensor-memory columns of one observation row
     static constexpr int kCandWords = A * A + 3;                     // child, reward, ev[A*A], rows|cols
-    static constexpr int kSbo1 = (KP / 4) * 128;                     // bytes between 8-row groups of a [rows x KP] operand
-    static constexpr int kW1 = 0;                                    // [512 x KP] tf32
-    static constexpr int kW2 = kW1 + 2 * kHidden * KP * 4;           // [16 x 512] tf32: rows 0..7 serve the first chunk of a trunk, 8..15 the second
-    static constexpr int kB1 = kW2 + kN2 * kK2 * 4;                  // first-layer biases, 512 f32 (used when !kBiasInK)
+    static constexpr int kSbo1 = KP * kEsz * 8;                      // bytes between 8-row groups of a [rows x KP] operand
+    static constexpr int kSbo2 = kK2 * kEsz * 8;                     // ... of the [16 x 512] second-layer operand
+    static constexpr int kW1 = 0;                                    // [512 x KP] tf32 / fp16
+    static constexpr int kW2 = kW1 + 2 * kHidden * KP * kEsz;        // [16 x 512]: rows 0..7 serve the first chunk of a trunk, 8..15 the second
+    static constexpr int kB1 = kW2 + kN2 * kK2 * kEsz;               // first-layer biases, 512 f32 (used when !kBiasInK)
     static constexpr int kB2 = kB1 + 2 * kHidden * 4;                // value bias, policy biases (8 f32)
     static constexpr int kImageBytes = kB2 + 32;
     static constexpr int kObs = kImageBytes;                         // fp32 observation staging, [side][128 x KIN]
@@ -105,12 +113,50 @@ struct Plan {
     static_assert(kBytes <= 227 * 1024, "shared memory plan does not fit");
     static_assert(kImageBytes % 16 == 0 && kObs % 16 == 0 && kCand % 16 == 0 && kBar % 8 == 0 && (32 * KIN * 4) % 16 == 0,
                   "alignment");
-    static_assert(KP <= 32, "observation columns do not fit");
+    static_assert(kObsCols <= 32 && kObsCols % 8 == 0, "observation columns do not fit");
     static_assert(kMmaWarps == kChunks, "one MMA warp per chunk index");
 };
 
-__host__ __device__ constexpr uint32_t instr_desc(int n) {
-    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
+// D = f32; A and B formats: 0 = f16, 2 = tf32; both K-major
+__host__ __device__ constexpr uint32_t instr_desc(int n, bool f16) {
+    return (1u << 4) | ((f16 ? 0u : 2u) << 7) | ((f16 ? 0u : 2u) << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
+}
+
+// operand element (row, k) of a K-major, no-swizzle [rows x KP] operand with ESZ-byte elements: 8-row x 16-byte core
+// matrices, the K chunks of a row group adjacent (LBO = 128 B), row groups KP * ESZ * 8 bytes apart
+template <int KP, int ESZ>
+__host__ __device__ __forceinline__ uint32_t op_off(int row, int k) {
+    constexpr int kPer = 16 / ESZ;
+    return (uint32_t)((row >> 3) * (KP * ESZ * 8) + (k / kPer) * 128 + (row & 7) * 16 + (k % kPer) * ESZ);
+}
+
+// two fp32 -> one 32-bit word of two fp16 (round to nearest even), element `lo` in bits 0..15: a tensor-memory column of a
+// 16-bit A operand holds two K-adjacent elements, the even one in the low half
+__device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
+    uint32_t d;
+    asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+    return d;
+}
+__device__ __forceinline__ uint32_t pack_relu_f16x2(float lo, float hi) {
+    uint32_t d;
+    asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+    return d;
+}
+
+template <bool F16>
+__device__ __forceinline__ void mma_ts_k(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, bool acc) {
+    if constexpr (F16) {
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "setp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+            "}\n" ::"r"(d_tmem),
+            "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"((uint32_t)acc)
+            : "memory");
+    } else {
+        mma_ts(d_tmem, a_tmem, b_desc, idesc, acc);
+    }
 }
 
 // register re-allocation between the warp roles (all four warps of a warpgroup execute the same one)
@@ -141,14 +187,14 @@ __device__ __forceinline__ float relu_split_scale(int hidden) { return (hidden &
 
 // The weight image in MMA-operand order, written straight into the CTA's shared memory by all of its threads
 // (43 KB of fp32 nn.Linear tensors from L2 -> 66 KB of tf32 operands): no pre-kernel, no workspace.
-template <int A>
+template <int A, bool F16>
 __device__ __forceinline__ void pack_weights(const rnad_mlp_weights& w, uint8_t* __restrict__ image, int thread) {
-    using P = Plan<A>;
+    using P = Plan<A, F16>;
     constexpr int KIN = P::KIN, KP = P::KP;
     static_assert(kThreads >= 2 * kHidden, "one thread per first-layer row");
     if (thread < 2 * kHidden) {
         // first layers: thread n owns hidden unit n of [value trunk | policy trunk]: one row of 2A^2 inputs (scalar loads,
-        // all in flight at once; the tensors are only guaranteed 4-byte aligned) -> KP / 4 sixteen-byte operand chunks
+        // all in flight at once; the tensors are only guaranteed 4-byte aligned) -> sixteen-byte operand chunks
         const int n = thread, j = n & (kHidden - 1);
         const float* src = (n < kHidden ? w.value_fc0_w : w.policy_fc0_w) + j * KIN;
         float x[KP];
@@ -157,10 +203,18 @@ __device__ __forceinline__ void pack_weights(const rnad_mlp_weights& w, uint8_t*
         const float bias = __ldg((n < kHidden ? w.value_fc0_b : w.policy_fc0_b) + j);
 #pragma unroll
         for (int k = KIN; k < KP; ++k) x[k] = (P::kBiasInK && k == KIN) ? bias : 0.f;
+        if constexpr (F16) {
 #pragma unroll
-        for (int q = 0; q < KP / 4; ++q)
-            *reinterpret_cast<float4*>(image + P::kW1 + operand_offset<KP>(n, 4 * q)) =
-                make_float4(to_tf32_fast(x[4 * q]), to_tf32_fast(x[4 * q + 1]), to_tf32_fast(x[4 * q + 2]), to_tf32_fast(x[4 * q + 3]));
+            for (int q = 0; q < KP / 8; ++q)
+                *reinterpret_cast<uint4*>(image + P::kW1 + op_off<KP, 2>(n, 8 * q)) =
+                    make_uint4(pack_f16x2(x[8 * q], x[8 * q + 1]), pack_f16x2(x[8 * q + 2], x[8 * q + 3]),
+                               pack_f16x2(x[8 * q + 4], x[8 * q + 5]), pack_f16x2(x[8 * q + 6], x[8 * q + 7]));
+        } else {
+#pragma unroll
+            for (int q = 0; q < KP / 4; ++q)
+                *reinterpret_cast<float4*>(image + P::kW1 + op_off<KP, 4>(n, 4 * q)) =
+                    make_float4(to_tf32_fast(x[4 * q]), to_tf32_fast(x[4 * q + 1]), to_tf32_fast(x[4 * q + 2]), to_tf32_fast(x[4 * q + 3]));
+        }
         reinterpret_cast<float*>(image + P::kB1)[n] = bias;
         // second layers as ONE [16 x 512] operand; thread k owns column k (hidden unit k of [value trunk | policy trunk]).
         // Row 0 = value_fc1, rows 1..A = policy_fc1 for the hidden units of a trunk's FIRST 128-chunk, rows 8 and 9..8+A
@@ -184,9 +238,15 @@ __device__ __forceinline__ void pack_weights(const rnad_mlp_weights& w, uint8_t*
                 col[9 + a] = r0 == 8 ? wp : 0.f;
             }
         }
+        if constexpr (F16) {
 #pragma unroll
-        for (int r = 0; r < kN2; ++r)    // (relu_split: the epilogue hands odd hidden units over doubled)
-            *reinterpret_cast<float*>(image + P::kW2 + operand_offset<kK2>(r, k)) = to_tf32_fast(col[r]) * relu_split_scale(k);
+            for (int r = 0; r < kN2; ++r)
+                *reinterpret_cast<uint16_t*>(image + P::kW2 + op_off<kK2, 2>(r, k)) = (uint16_t)(pack_f16x2(col[r], 0.f) & 0xffffu);
+        } else {
+#pragma unroll
+            for (int r = 0; r < kN2; ++r)    // (relu_split: the epilogue hands odd hidden units over doubled)
+                *reinterpret_cast<float*>(image + P::kW2 + op_off<kK2, 4>(r, k)) = to_tf32_fast(col[r]) * relu_split_scale(k);
+        }
     }
     if (thread < 8) {
         float v = 0.f;
@@ -284,10 +344,11 @@ __device__ __forceinline__ void gather_candidates(const uint32_t* __restrict__ t
     }
 }
 
-template <int A, int C>
+template <int A, int C, bool F16>
 __global__ void __launch_bounds__(kThreads, 1) rollout_tc2_kernel(RolloutArgs g) {
-    using P = Plan<A>;
+    using P = Plan<A, F16>;
     constexpr int KIN = P::KIN, KP = P::KP;
+    static_assert(!F16 || (kEpiWarps == 8 && !kEpiWide), "the fp16 epilogue exists for the default warp layout only");
     static_assert(A <= 4, "value + logits must fit the 8 useful columns of the second-layer accumulator");
     extern __shared__ __align__(1024) uint8_t smem[];
     const int tid = threadIdx.x;
@@ -326,7 +387,7 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tc2_kernel(RolloutArgs g)
     // every game starts at the root (node 1): its record is fetched once, underneath the weight packing
     uint32_t root_word = 0;
     if (tid < ev_stride_of(A)) root_word = __ldg(g.ev_tab + ev_stride_of(A) + tid);
-    pack_weights<A>(g.w, smem, tid);
+    pack_weights<A, F16>(g.w, smem, tid);
     if (tid < ev_stride_of(A)) reinterpret_cast<uint32_t*>(smem + P::kRoot)[tid] = root_word;
     fence_async_smem();          // generic-proxy writes -> visible to the tensor core's (async proxy) operand reads
     tc_fence_before();
@@ -346,8 +407,8 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tc2_kernel(RolloutArgs g)
         // The whole warp runs the loop converged and one elected lane issues: the descriptors then live in
         // uniform registers (an `if (lane == 0)` branch makes ptxas wrap every UTCHMMA in a waterfall loop).
         const uint64_t w1_desc = desc_sbo(smem_u32(smem + P::kW1), P::kSbo1);
-        const uint64_t w2_desc = desc_sbo(smem_u32(smem + P::kW2), 8 * kK2 * 4);
-        constexpr uint32_t kIdesc1 = instr_desc(kChunk), kIdesc2 = instr_desc(kN2);
+        const uint64_t w2_desc = desc_sbo(smem_u32(smem + P::kW2), P::kSbo2);
+        constexpr uint32_t kIdesc1 = instr_desc(kChunk, F16), kIdesc2 = instr_desc(kN2, F16);
         // Stream item i = ((pair * T + t) * kSides + side) * kChunks + c lives in slot i % kSlots.  Its step is
         //     wait relu(i) -> MMA2(i) -> MMA1(i + kSlots) into the slot MMA2(i) has just read -> commit,
         // and MMA warp w takes the items with c == w: issuing blocks while the tensor core's queue is full and every
@@ -370,9 +431,9 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tc2_kernel(RolloutArgs g)
         // first layers of a chunk: A = observations in tensor memory (called by the elected lane)
         auto mma1 = [&](int c, int side, int slot, int bar_index) {
 #pragma unroll
-            for (int s = 0; s < KP / 8; ++s)
-                mma_ts(tmem_base + slot * kChunk, tmem_base + obs_col(side) + s * 8,
-                       w1_desc + (uint64_t)(((chunk_hidden(c) / 8) * P::kSbo1 + s * 256) >> 4), kIdesc1, s > 0);
+            for (int s = 0; s < KP / P::kKStep; ++s)   // (8 tensor-memory columns and 256 operand bytes per K step, either kind)
+                mma_ts_k<F16>(tmem_base + slot * kChunk, tmem_base + obs_col(side) + s * 8,
+                              w1_desc + (uint64_t)(((chunk_hidden(c) / 8) * P::kSbo1 + s * 256) >> 4), kIdesc1, s > 0);
             mma_commit(bar_d1(bar_index));
         };
         if (w == 0 && n_items > 0) {             // fill the ring: items 0 .. kSlots-1 are chunks 0 .. 2 of (side 0, half-move 0)
@@ -400,9 +461,11 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tc2_kernel(RolloutArgs g)
             TRI(2, i, 0);
             if (elect_one()) {
 #pragma unroll
-                for (int s = 0; s < kChunk / 8; ++s)   // second layers: A = relu(hidden) in tensor memory
-                    mma_ts(tmem_base + (w < 2 ? d2p_col(side) : d2v_col(side)), tmem_base + slot * kChunk + s * 8,
-                           w2_desc + (uint64_t)(((chunk_hidden(w) / 8 + s) * 256) >> 4), kIdesc2, true);
+                for (int s = 0; s < kChunk / P::kKStep; ++s)   // second layers: A = relu(hidden) in tensor memory
+                    // (fp16: the epilogue warps of a 64-column half pack it into the first 32 columns of that half)
+                    mma_ts_k<F16>(tmem_base + (w < 2 ? d2p_col(side) : d2v_col(side)),
+                                  tmem_base + slot * kChunk + (F16 ? (s >> 2) * 64 + (s & 3) * 8 : s * 8),
+                                  w2_desc + (uint64_t)(((chunk_hidden(w) / P::kKStep + s) * 256) >> 4), kIdesc2, true);
                 mma_commit(w < 2 ? bar_d2p(side) : bar_d2v(side));
                 TRI(2, i, 1);
                 if (has_j) mma1(cj, side_j, slot, rb >= kSlots ? rb - kSlots : rb + kSlots);   // item i + 3, into the slot just read
@@ -466,10 +529,18 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tc2_kernel(RolloutArgs g)
                         r[4 * k + 3] = __float_as_uint(__uint_as_float(r[4 * k + 3]) + bb.w);
                     }
                 }
+                if constexpr (F16) {
+                    uint32_t pk[kCols / 2];        // relu, round to fp16, pack: one instruction per two hidden units
 #pragma unroll
-                for (int k = 0; k < kCols; ++k) r[k] = __float_as_uint(relu_split(__uint_as_float(r[k]), k));
+                    for (int k = 0; k < kCols / 2; ++k)
+                        pk[k] = pack_relu_f16x2(__uint_as_float(r[2 * k]), __uint_as_float(r[2 * k + 1]));
+                    tmem_st32(taddr, pk);
+                } else {
 #pragma unroll
-                for (int q = 0; q < kCols / 32; ++q) tmem_st32(taddr + q * 32, r + q * 32);
+                    for (int k = 0; k < kCols; ++k) r[k] = __float_as_uint(relu_split(__uint_as_float(r[k]), k));
+#pragma unroll
+                    for (int q = 0; q < kCols / 32; ++q) tmem_st32(taddr + q * 32, r + q * 32);
+                }
               }
             } else {
 #pragma unroll
@@ -585,14 +656,17 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tc2_kernel(RolloutArgs g)
                     tmem_st8(my_d2p, zero);  // the second-layer MMAs of the next half-move only ever accumulate
                     tmem_st8(my_d2p + 8, zero);
                 }
+                auto obs_k = [&](int kk) {   // element kk of the padded observation row (the constant 1 carries the bias)
+                    return kk < KIN ? x[kk < KIN ? kk : 0] : ((P::kBiasInK && kk == KIN) ? 1.f : 0.f);
+                };
 #pragma unroll
-                for (int q = 0; q < KP / 8; ++q) {
+                for (int q = 0; q < P::kObsCols / 8; ++q) {
                     uint32_t v[8];
 #pragma unroll
                     for (int u = 0; u < 8; ++u) {
-                        const int kk = 8 * q + u;
-                        v[u] = __float_as_uint(kk < KIN ? to_tf32_fast(x[kk < KIN ? kk : 0])
-                                                        : ((P::kBiasInK && kk == KIN) ? 1.f : 0.f));
+                        const int col = 8 * q + u;
+                        if constexpr (F16) v[u] = pack_f16x2(obs_k(2 * col), obs_k(2 * col + 1));
+                        else v[u] = __float_as_uint(col < KIN ? to_tf32_fast(obs_k(col)) : obs_k(col));
                     }
                     tmem_st8(my_obs + 8 * q, v);
                 }
@@ -745,9 +819,9 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_tc2_kernel(RolloutArgs g)
     if (warp == kMmaWarp) tmem_dealloc<kTmemCols>(tmem_base);
 }
 
-template <int A, int C>
+template <int A, int C, bool F16>
 static int launch(const RolloutArgs& g, cudaStream_t st) {
-    using P = Plan<A>;
+    using P = Plan<A, F16>;
     // One CTA per SM owns all 512 TMEM columns: ask for more than half of the shared memory so that a second
     // CTA can never become resident and spin inside tcgen05.alloc.
     size_t smem = P::kBytes;
@@ -759,10 +833,10 @@ static int launch(const RolloutArgs& g, cudaStream_t st) {
     int rc = check_cuda(cudaGetDevice(&device), "cudaGetDevice");
     if (rc) return rc;
     if (configured_device.load(std::memory_order_acquire) != device) {
-        rc = check_cuda(cudaFuncSetAttribute(rollout_tc2_kernel<A, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
+        rc = check_cuda(cudaFuncSetAttribute(rollout_tc2_kernel<A, C, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
                         "cudaFuncSetAttribute(rollout_tc2, smem)");
         if (rc) return rc;
-        rc = check_cuda(cudaFuncSetAttribute(rollout_tc2_kernel<A, C>, cudaFuncAttributePreferredSharedMemoryCarveout,
+        rc = check_cuda(cudaFuncSetAttribute(rollout_tc2_kernel<A, C, F16>, cudaFuncAttributePreferredSharedMemoryCarveout,
                                              cudaSharedmemCarveoutMaxShared),
                         "cudaFuncSetAttribute(rollout_tc2, carveout)");
         if (rc) return rc;
@@ -771,7 +845,7 @@ static int launch(const RolloutArgs& g, cudaStream_t st) {
     const int64_t tiles = (g.B + kTileM - 1) / kTileM;
     int64_t blocks = (tiles + kSides - 1) / kSides;
     if (blocks > sm_count()) blocks = sm_count();
-    rollout_tc2_kernel<A, C><<<(int)blocks, kThreads, smem, st>>>(g);
+    rollout_tc2_kernel<A, C, F16><<<(int)blocks, kThreads, smem, st>>>(g);
     RNAD_CHECK_LAUNCH("rollout_tc2_kernel");
     return RNAD_OK;
 }
@@ -791,7 +865,7 @@ int64_t rollout_tc2_workspace_bytes(int A) {
     return 0;   // the weight image is built in shared memory by the kernel itself
 }
 
-int rollout_tc2(const RolloutArgs& g, void* workspace, cudaStream_t st) {
+int rollout_tc2(const RolloutArgs& g, void* workspace, cudaStream_t st, bool f16) {
     if (!rollout_tc2_supported(g.A, g.w.width, g.C)) {
         set_error("rnad_rollout(tf32x2): needs width == 256, 2 <= max_actions <= 4 and max_transitions <= 4 "
                   "(got width %d, max_actions %d, max_transitions %d)", g.w.width, g.A, g.C);
@@ -799,7 +873,7 @@ int rollout_tc2(const RolloutArgs& g, void* workspace, cudaStream_t st) {
     }
     (void)workspace;
 #define RNAD_TC2_CASE(a, c) \
-    if (g.A == a && g.C == c) return tc2::launch<a, c>(g, st);
+    if (g.A == a && g.C == c) return f16 ? tc2::launch<a, c, true>(g, st) : tc2::launch<a, c, false>(g, st);
     RNAD_TC2_CASE(2, 1) RNAD_TC2_CASE(2, 2) RNAD_TC2_CASE(2, 3) RNAD_TC2_CASE(2, 4)
     RNAD_TC2_CASE(3, 1) RNAD_TC2_CASE(3, 2) RNAD_TC2_CASE(3, 3) RNAD_TC2_CASE(3, 4)
     RNAD_TC2_CASE(4, 1) RNAD_TC2_CASE(4, 2) RNAD_TC2_CASE(4, 3) RNAD_TC2_CASE(4, 4)
