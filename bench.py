@@ -453,7 +453,8 @@ def run_native(args):
         bytes_per_launch = algorithmic_bytes_per_env_step(a, c) * env_steps
         achieved_gbs = bytes_per_launch / per_launch_s / 1e9
         tflops = flops_per_env_step(a) * env_steps / per_launch_s / 1e12
-        kernel_name = {"tf32": "rollout_tc_kernel", "tf32x2": "rollout_tc2_kernel", "fp32": "rollout_fp32_kernel"}[precision]
+        kernel_name = {"tf32": "rollout_tc_kernel", "tf32x2": "rollout_tc2_kernel", "f16x2": "rollout_tc2_kernel",
+                       "fp32": "rollout_fp32_kernel"}[precision]
         cpu = None
         if world == 1 and args.cpu_budget > 0:   # rank 0 at N = 1 only
             threads = os.cpu_count() or 1
@@ -501,6 +502,7 @@ def run_native(args):
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": kernel_ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": {"tf32": "tf32 (tcgen05, fp32 accumulate) + fp32", "tf32x2": "tf32 (tcgen05, fp32 accumulate)",
+                                          "f16x2": "fp16 operands (tcgen05 kind::f16, 11-bit significand like tf32), fp32 accumulate",
                                           "fp32": "fp32"}[precision],
             "data": "synthetic",
             "config": workload_config(args.config, depth, a, c, n_nodes, batch, T),
@@ -715,7 +717,7 @@ def main():
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--config", default="cfg2", choices=sorted(CONFIGS))
     ap.add_argument("--batch", type=int, default=0, help="games per GPU (default: the config's)")
-    ap.add_argument("--precision", default="tf32x2", choices=["tf32", "tf32x2", "fp32"])
+    ap.add_argument("--precision", default="f16x2", choices=["tf32", "tf32x2", "f16x2", "fp32"])
     ap.add_argument("--cpu-budget", type=float, default=15.0, help="seconds of CPU work for cpu_baseline")
     ap.add_argument("--reference-batch", type=int, default=65536)
     ap.add_argument("--learner-steps", type=int, default=200, help="timed learner updates (at least --steps)")

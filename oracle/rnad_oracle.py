@@ -170,13 +170,18 @@ def tf32_trunc(x: torch.Tensor) -> torch.Tensor:
     return (bits & ~0x1FFF).view(torch.float32)
 
 
-def tc_bias_in_k(A: int) -> bool:
+def f16_rn(x: torch.Tensor) -> torch.Tensor:
+    """fp32 -> fp16 -> fp32 as PTX `cvt.rn.f16.f32`: nearest, ties to even (11-bit significand, like tf32)."""
+    return x.detach().to(torch.float32).to(torch.float16).to(torch.float32)
+
+
+def tc_bias_in_k(A: int, k_step: int = 8) -> bool:
     """
     Whether the tensor-core engines carry the first-layer bias as a constant-1 input column (then it is
-    tf32-rounded like a weight) or add it in fp32 after the MMA: in K when 2A^2 is not a multiple of the
-    tf32 MMA K of 8, i.e. when K has padding to spare.
+    rounded like a weight) or add it in fp32 after the MMA: in K when 2A^2 is not a multiple of the
+    MMA's K (8 for kind::tf32, 16 for kind::f16), i.e. when K has padding to spare.
     """
-    return (2 * A * A) % 8 != 0
+    return (2 * A * A) % k_step != 0
 
 
 def mlp_forward_tc(w, obs_flat, second_layer="fp32", dtype=torch.float64):
@@ -188,19 +193,27 @@ def mlp_forward_tc(w, obs_flat, second_layer="fp32", dtype=torch.float64):
       second layers  second_layer="fp32" (precision "tf32" rollout engine, learner kernels): fp32 operands;
                      second_layer="tf32" (precision "tf32x2" rollout engine): relu(h) in fp32 truncated to
                      tf32 by the tensor core, W rounded to tf32 (cvt.rna), bias added in fp32.
+      second_layer="f16" (precision "f16x2", kind::f16): x, W, the bias when it rides in K (2A^2 not a multiple of
+                     16), relu(h) and the second-layer W all rounded to fp16 (cvt.rn), fp32 accumulation, the second
+                     bias added in fp32.
     Returns logits, policy, value, exp_logits, hidden_value, hidden_policy (pre-activation) in `dtype`.
     """
     A = w["policy_fc1.weight"].shape[0]
-    bias_k = tc_bias_in_k(A)
-    x = tf32_rna(obs_flat).to(dtype)
+    f16 = second_layer == "f16"
+    rnd = f16_rn if f16 else tf32_rna
+    bias_k = tc_bias_in_k(A, 16 if f16 else 8)
+    x = rnd(obs_flat).to(dtype)
     mask = obs_flat[:, A * A: 2 * A * A: A] != 0
 
     def trunk(name):
-        w0 = tf32_rna(w[name + "_fc0.weight"]).to(dtype)
-        b0 = (tf32_rna(w[name + "_fc0.bias"]) if bias_k else w[name + "_fc0.bias"]).to(dtype)
+        w0 = rnd(w[name + "_fc0.weight"]).to(dtype)
+        b0 = (rnd(w[name + "_fc0.bias"]) if bias_k else w[name + "_fc0.bias"]).to(dtype)
         pre = x @ w0.T + b0
         h = torch.relu(pre)
-        if second_layer == "tf32":
+        if f16:
+            h = f16_rn(h.to(torch.float32)).to(dtype)
+            w1 = f16_rn(w[name + "_fc1.weight"]).to(dtype)
+        elif second_layer == "tf32":
             h = tf32_trunc(h.to(torch.float32)).to(dtype)
             w1 = tf32_rna(w[name + "_fc1.weight"]).to(dtype)
         else:

@@ -5,14 +5,19 @@
 // A tile is 128 trajectory rows (row = TMEM lane).  Its ten *chunks* - 128 hidden units of, in turn, the learner's
 // value and policy trunks, the target net's value trunk and the two regularisation nets' policy trunks - stream
 // through a ring of three 128-column TMEM slots:
-//     MMA1  D[128 x 128]   = obs[128 x KP] (TMEM) x W1_chunk^T (smem)                     kind::tf32
+//     MMA1  D[128 x 128]   = obs[128 x KP] (TMEM) x W1_chunk^T (smem)                     kind::f16, fp32 accumulate
 //     MMA2  D2[128 x 16]  += relu(D)[128 x 128] (TMEM) x W2_chunk^T (smem)
+// Operands are fp16 (11-bit significand like tf32, round to nearest even; observations, weights and activations of this
+// net are far inside fp16's range): K = 16 per MMA, relu(hidden) goes back into tensor memory as packed pairs with one
+// cvt.rn.relu.f16x2 per two hidden units - the SAME numerics, K order and partial-sum order as the rollout engine
+// RNAD_PREC_F16X2 (rollout_tc2.cu), so an on-policy learner step may take the learner net's logits / values from the
+// rollout (bit-identical to this kernel's).
 // with two 16-column accumulators per tile: D2a = (v, logit[0..A)) of the learner, D2b = (v_target, logit_reg[0..A),
 // logit_reg_[0..A)).  Observations and accumulators are double-buffered across tiles.
 //   warps 12..15  issue the MMAs (stream item i by warp i % 4; MMA2s only ever ADD into accumulators the output
 //                 warps cleared, each half of a trunk into its own columns, so their order across warps is free)
 //   warps 4..11   relu epilogue in tensor memory (bias via the constant-1 input column, else one FADD)
-//   warps 0..3    one thread per row: observation -> tensor memory (tf32); one tile later the heads: masked softmax /
+//   warps 0..3    one thread per row: observation -> tensor memory (fp16 pairs); one tile later the heads: masked softmax /
 //                 log-softmax (net.py:76-80) of the three logit sets, the two values, written time-major.
 // Reference: nn/net.py:64-85.  A <= 3: one launch over all five trunks.  A = 4: the five first layers (160 KB) and
 // second layers do not fit one CTA's shared memory and target value + two logit sets need nine accumulator columns, so
@@ -27,10 +32,8 @@ namespace fwd2 {
 using namespace rnad::tc;
 using namespace rnad::tcp;
 
-#ifndef RNAD_FWD2_EPI_WARPS
-#define RNAD_FWD2_EPI_WARPS 8
-#endif
-constexpr int kRowWarps = 4, kEpiWarps = RNAD_FWD2_EPI_WARPS, kMmaWarps = 4;   // 8 or 16 epilogue warps (64 or 32 columns each)
+constexpr int kRowWarps = 4, kEpiWarps = 8, kMmaWarps = 4;   // epilogue: 4 lane quadrants x 2 halves of 64 columns
+constexpr int kKStep = 16, kEsz = 2;                         // K of one kind::f16 MMA, bytes per operand element
 constexpr int kMmaWarp = kRowWarps + kEpiWarps;
 constexpr int kThreads = (kMmaWarp + kMmaWarps) * 32;
 constexpr int kChunk = 128, kSlots = 3, kAllTrunks = 5;
@@ -51,12 +54,14 @@ struct Plan {
         return (trunk == 0 || trunk == 2) ? 0 : (trunk == 4 && NT == 5 ? 1 + A : 1);
     }
     static constexpr int KIN = 2 * A * A;
-    static constexpr bool kBiasInK = (KIN % 8) != 0;
-    static constexpr int KP = round_up(KIN + (kBiasInK ? 1 : 0), 8);
-    static constexpr int kSbo1 = (KP / 4) * 128;
-    static constexpr int kTrunkBytes = kHidden * KP * 4;
-    static constexpr int kW2ChunkBytes = 16 * kChunk * 4;             // a [16 x 128] operand: rows 0..7 used by a trunk's first half, 8..15 by its second
-    static constexpr int kW1 = 0;                                     // 5 trunks [256 x KP] tf32
+    static constexpr bool kBiasInK = (KIN % kKStep) != 0;
+    static constexpr int KP = round_up(KIN + (kBiasInK ? 1 : 0), kKStep);
+    static constexpr int kObsCols = KP * kEsz / 4;                    // tensor-memory columns of one observation row
+    static constexpr int kSbo1 = KP * kEsz * 8;                       // bytes between 8-row groups of a [rows x KP] operand
+    static constexpr int kSbo2 = kChunk * kEsz * 8;                   // ... of a [16 x 128] second-layer operand
+    static constexpr int kTrunkBytes = kHidden * KP * kEsz;
+    static constexpr int kW2ChunkBytes = 16 * kChunk * kEsz;          // a [16 x 128] operand: rows 0..7 used by a trunk's first half, 8..15 by its second
+    static constexpr int kW1 = 0;                                     // 5 trunks [256 x KP] fp16
     static constexpr int kW2 = kW1 + kTrunks * kTrunkBytes;           // 10 chunks
     static constexpr int kB1 = kW2 + kItemsPerTile * kW2ChunkBytes;   // first-layer biases, 5 x 256 f32
     static constexpr int kB2 = kB1 + kTrunks * kHidden * 4;           // second-layer biases: 4 f32 per trunk
@@ -67,8 +72,38 @@ struct Plan {
     static constexpr int kBytes = kTmem + 16;
     static_assert(NT == 5 ? 1 + 2 * A <= 8 : 1 + A <= 8, "the outputs sharing an accumulator must fit its 8 columns");
     static_assert(kBytes <= 227 * 1024, "shared memory plan does not fit");
-    static_assert(KP <= 32, "observation columns do not fit");
+    static_assert(kObsCols <= 32 && kObsCols % 8 == 0, "observation columns do not fit");
 };
+
+// element (row, k) of a K-major, no-swizzle [rows x KP] fp16 operand: 8-row x 16-byte core matrices, the K chunks of a
+// row group adjacent (LBO = 128 B), row groups KP * 16 bytes apart
+template <int KP>
+__host__ __device__ __forceinline__ uint32_t op_off(int row, int k) {
+    return (uint32_t)((row >> 3) * (KP * kEsz * 8) + (k >> 3) * 128 + (row & 7) * 16 + (k & 7) * kEsz);
+}
+// two fp32 -> one word of two fp16 (round to nearest even), `lo` in bits 0..15: a tensor-memory column of a 16-bit A
+// operand holds two K-adjacent elements, the even one in the low half
+__device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
+    uint32_t d;
+    asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+    return d;
+}
+__device__ __forceinline__ uint32_t pack_relu_f16x2(float lo, float hi) {
+    uint32_t d;
+    asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+    return d;
+}
+__device__ __forceinline__ uint16_t to_f16(float x) { return (uint16_t)(pack_f16x2(x, 0.f) & 0xffffu); }
+__device__ __forceinline__ void mma_ts_f16(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, bool acc) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+        "}\n" ::"r"(d_tmem),
+        "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"((uint32_t)acc)
+        : "memory");
+}
 
 struct Nets {
     rnad_mlp_weights net, target, reg, reg_;
@@ -95,7 +130,13 @@ __global__ void pack_image_kernel(Nets w, uint8_t* __restrict__ image) {
     for (int lt = 0; lt < NT; ++lt) {
         const int t = lt, g = T0 + lt;      // local index (position in the image), global trunk
         const int row0_t = P::row0(g);
-        pack_trunk_operand<P::KIN, P::KP, P::kBiasInK>(w1[g], b1[g], image + P::kW1 + t * P::kTrunkBytes, thread, n_threads);
+        for (int e = thread; e < kHidden * P::KP; e += n_threads) {       // first layer (+ bias in K): [256 x KP] fp16
+            const int j = e / P::KP, k = e % P::KP;
+            float v = 0.f;
+            if (k < P::KIN) v = w1[g][j * P::KIN + k];
+            else if (P::kBiasInK && k == P::KIN) v = b1[g][j];
+            *reinterpret_cast<uint16_t*>(image + P::kW1 + t * P::kTrunkBytes + op_off<P::KP>(j, k)) = to_f16(v);
+        }
         for (int j = thread; j < kHidden; j += n_threads) reinterpret_cast<float*>(image + P::kB1)[t * kHidden + j] = b1[g][j];
         // second layer: per 128-unit half a [16 x 128] K-major operand, rows = accumulator columns.  The first half of a
         // trunk uses rows row0 + o, the second rows 8 + row0 + o (zero elsewhere): the two halves leave their partial
@@ -105,7 +146,7 @@ __global__ void pack_image_kernel(Nets w, uint8_t* __restrict__ image) {
             const int half = e / (16 * kChunk), r = (e / kChunk) % 16, k = e % kChunk;
             const int o = r - (8 * half + row0_t);
             const float v = (o >= 0 && o < n_out[g]) ? w2[g][o * kHidden + half * kChunk + k] : 0.f;
-            *reinterpret_cast<float*>(image + P::kW2 + (t * 2 + half) * P::kW2ChunkBytes + operand_offset<kChunk>(r, k)) = to_tf32(v);
+            *reinterpret_cast<uint16_t*>(image + P::kW2 + (t * 2 + half) * P::kW2ChunkBytes + op_off<kChunk>(r, k)) = to_f16(v);
         }
         if (thread < 4) reinterpret_cast<float*>(image + P::kB2)[t * 4 + thread] = thread < n_out[g] ? b2[g][thread] : 0.f;
     }
@@ -175,15 +216,16 @@ __global__ void __launch_bounds__(kThreads, 1) learner_fwd_tc2_kernel(const floa
         const int w = warp - kMmaWarp;
         mbar_wait_c(bar_img, 0);
         const uint64_t w1_desc = desc_sbo(smem_u32(smem + P::kW1), P::kSbo1);
-        const uint64_t w2_desc = desc_sbo(smem_u32(smem + P::kW2), (kChunk / 4) * 128);
-        constexpr uint32_t kIdesc1 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kChunk >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
-        constexpr uint32_t kIdesc2 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(16 >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
+        const uint64_t w2_desc = desc_sbo(smem_u32(smem + P::kW2), P::kSbo2);
+        // D = f32, A and B = f16 (format 0), both K-major
+        constexpr uint32_t kIdesc1 = (1u << 4) | ((uint32_t)(kChunk >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
+        constexpr uint32_t kIdesc2 = (1u << 4) | ((uint32_t)(16 >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
         int seen_obs = -1, seen_free = -1;       // tiles whose observations / cleared accumulators this warp has seen
         // first layers of chunk c of local tile k into `slot`; barrier index of the item
         auto mma1 = [&](int k, int c, int slot, int bar_index) {
 #pragma unroll
-            for (int s = 0; s < KP / 8; ++s)
-                mma_ts(tmem_base + slot * kChunk, tmem_base + kObsCol + (k & 1) * 32 + s * 8,
+            for (int s = 0; s < KP / kKStep; ++s)      // (8 tensor-memory columns and 256 operand bytes per K step)
+                mma_ts_f16(tmem_base + slot * kChunk, tmem_base + kObsCol + (k & 1) * 32 + s * 8,
                        w1_desc + (uint64_t)(((c >> 1) * P::kTrunkBytes + (c & 1) * (kChunk / 8) * P::kSbo1 + s * 256) >> 4),
                        kIdesc1, s > 0);
             mma_commit(bar_d1(bar_index));
@@ -223,9 +265,9 @@ __global__ void __launch_bounds__(kThreads, 1) learner_fwd_tc2_kernel(const floa
             if (elect_one()) {
                 const uint32_t d2 = tmem_base + kD2Col + (k_i & 1) * 32 + (P::second_acc(T0 + (c_i >> 1)) ? 16 : 0);
 #pragma unroll
-                for (int s = 0; s < kChunk / 8; ++s)
-                    mma_ts(d2, tmem_base + slot * kChunk + s * 8,
-                           w2_desc + (uint64_t)((c_i * P::kW2ChunkBytes + s * 256) >> 4), kIdesc2, true);
+                for (int s = 0; s < kChunk / kKStep; ++s)   // the epilogue warp of a 64-column half packs it into that half's first 32 columns
+                    mma_ts_f16(d2, tmem_base + slot * kChunk + (s >> 2) * 64 + (s & 3) * 8,
+                               w2_desc + (uint64_t)((c_i * P::kW2ChunkBytes + s * 256) >> 4), kIdesc2, true);
                 mma_commit(bar_d2(k_i & 1));
                 if (has_j) mma1(k_j, c_j, slot, rb >= kSlots ? rb - kSlots : rb + kSlots);
             }
@@ -277,10 +319,11 @@ __global__ void __launch_bounds__(kThreads, 1) learner_fwd_tc2_kernel(const floa
                     r[4 * k + 3] = __float_as_uint(__uint_as_float(r[4 * k + 3]) + bb.w);
                 }
             }
+            static_assert(kCols == 64, "one packed 32-column store per warp and item");
+            uint32_t pk[kCols / 2];              // relu, round to fp16, pack: one instruction per two hidden units
 #pragma unroll
-            for (int k = 0; k < kCols; ++k) r[k] = __float_as_uint(fmaxf(__uint_as_float(r[k]), 0.f));
-#pragma unroll
-            for (int q = 0; q < kCols / 32; ++q) tmem_st32(taddr + q * 32, r + q * 32);
+            for (int k = 0; k < kCols / 2; ++k) pk[k] = pack_relu_f16x2(__uint_as_float(r[2 * k]), __uint_as_float(r[2 * k + 1]));
+            tmem_st32(taddr, pk);
             tmem_st_wait();
             tc_fence_before();
             __syncwarp();
@@ -325,14 +368,14 @@ __global__ void __launch_bounds__(kThreads, 1) learner_fwd_tc2_kernel(const floa
 #pragma unroll
                 for (int a = 0; a < A; ++a) mask_now |= (x[A * A + a * A] != 0.f ? 1u : 0u) << a;   // obs[:, 1, :, 0]
                 row_now = active ? row : -1;
+                auto obs_k = [&](int kk) {   // element kk of the padded observation row (the constant 1 carries the bias)
+                    return kk < KIN ? x[kk < KIN ? kk : 0] : ((P::kBiasInK && kk == KIN) ? 1.f : 0.f);
+                };
 #pragma unroll
-                for (int q = 0; q < KP / 8; ++q) {
+                for (int q = 0; q < P::kObsCols / 8; ++q) {
                     uint32_t v[8];
 #pragma unroll
-                    for (int u = 0; u < 8; ++u) {
-                        const int kk = 8 * q + u;
-                        v[u] = __float_as_uint(kk < KIN ? to_tf32_fast(x[kk < KIN ? kk : 0]) : ((P::kBiasInK && kk == KIN) ? 1.f : 0.f));
-                    }
+                    for (int u = 0; u < 8; ++u) v[u] = pack_f16x2(obs_k(2 * (8 * q + u)), obs_k(2 * (8 * q + u) + 1));
                     tmem_st8(tmem_lane + kObsCol + (k & 1) * 32 + 8 * q, v);
                 }
                 tmem_st_wait();

@@ -306,7 +306,8 @@ class Episodes:
     def generate(self, net: torch.nn.Module, precision: str = None, uniforms: torch.Tensor = None):
         """
         Plays the batch to the end with `net` as the actor (episode.py:175-230).
-        precision: "tf32x2" (both layers of the net on tcgen05 tensor cores) | "tf32" (first
+        precision: "f16x2" (both layers of the net on tcgen05, fp16 operands: the default) | "tf32x2" (the same with tf32
+        operands) | "tf32" (first
         layers on tcgen05, second on the CUDA cores) | "fp32" (CUDA cores throughout) | None =
         the net's `rollout_precision`, else $RNAD_ROLLOUT_PRECISION, else the fastest engine
         that supports the net and tree shape.  uniforms: optional (T, B, 2)
@@ -335,7 +336,7 @@ class Episodes:
             precision = getattr(net, "rollout_precision", None) or os.environ.get("RNAD_ROLLOUT_PRECISION")
         if precision is None:
             if L.rnad_rollout_tc2_supported(a, net.width, packed.C):
-                precision = "tf32x2"
+                precision = "f16x2"
             else:
                 precision = "tf32" if L.rnad_rollout_tc_supported(a, net.width) else "fp32"
         t_max = packed.max_half_moves
@@ -474,7 +475,7 @@ class SelfPlay:
         self.device = dev = packed.device
         if precision is None:
             if L.rnad_rollout_tc2_supported(packed.A, net.width, packed.C):
-                precision = "tf32x2"
+                precision = "f16x2"
             else:
                 precision = "tf32" if L.rnad_rollout_tc_supported(packed.A, net.width) else "fp32"
         self.precision = precision

@@ -120,7 +120,7 @@ class LearnerStep:
         self.a, self.c, self.b, self.t = packed.A, packed.C, int(trial.batch_size), packed.max_half_moves
         self.use_graph, self.graph, self.calls, self._side = use_graph, None, 0, None
         if L.rnad_rollout_tc2_supported(self.a, net.width, packed.C):
-            self.precision = "tf32x2"
+            self.precision = "f16x2"
         else:
             self.precision = "tf32" if L.rnad_rollout_tc_supported(self.a, net.width) else "fp32"
         with torch.cuda.device(dev):

@@ -53,7 +53,7 @@ class MLP(nn.Module):
         self.policy_fc1 = nn.Linear(width, max_actions, device=device, dtype=dtype)
         self.max_actions = max_actions
         self.width = width
-        self.rollout_precision = None   # None = auto (the fastest engine for the shape); "fp32" | "tf32" | "tf32x2"
+        self.rollout_precision = None   # None = auto (the fastest engine for the shape); "fp32" | "tf32" | "tf32x2" | "f16x2"
 
     def _trunks(self, flat):
         value = self.value_fc1(torch.relu(self.value_fc0(flat)))

@@ -1,5 +1,5 @@
 """
-Parity on the configurations bench.py measures (BASELINE.json configs 2-4), at their FULL batch sizes: the tf32x2
+Parity on the configurations bench.py measures (BASELINE.json configs 2-4), at their FULL batch sizes: the f16x2 (default)
 rollout is launched exactly as benchmarked - cfg2: Tree(3, 2, depth_bound=4), 65,536 games = 256 tile pairs, most CTAs
 playing two pairs; cfg3: max_transitions 3, depth 6, 14.9 M nodes (HBM-resident tables), 262,144 games; cfg4: A = 4,
 T = 16, thinned ragged tree, 131,072 games (one GPU's share) - and a random sample of its games is replayed on the
@@ -71,7 +71,7 @@ def test_benchmarked_rollout_replays_on_the_oracle(config, sample):
     torch.manual_seed(99)
     ep = Episodes(tree, batch)
     ep.generate(net)
-    assert ep.precision == "tf32x2"
+    assert ep.precision == "f16x2"
     t_max = tree.packed().max_half_moves
     assert t_max == 2 * depth
     _whole_batch_properties(ep, t_max, regular=config != "cfg4")
@@ -83,4 +83,4 @@ def test_benchmarked_rollout_replays_on_the_oracle(config, sample):
     tiles = np.concatenate([np.arange(0, 256), np.arange(batch - 384, batch), np.arange(batch // 2 + 64, batch // 2 + 448)])
     games = np.unique(np.concatenate([tiles, rng.choice(batch, size=sample, replace=False)]))
     tables = _tables(tree)
-    check_rollout_against_oracle(ep, tables, w, seed=ep.states.seed, tol=TOL["tf32x2"], precision="tf32x2", games=games)
+    check_rollout_against_oracle(ep, tables, w, seed=ep.states.seed, tol=TOL["f16x2"], precision="f16x2", games=games)

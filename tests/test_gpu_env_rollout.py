@@ -126,7 +126,8 @@ def test_mlp_forward_matches_reference(golden):
 
 # --------------------------------------------------------------------- K2
 
-TOL = {"fp32": dict(rtol=1e-5, atol=2e-6), "tf32": dict(rtol=0, atol=4e-3), "tf32x2": dict(rtol=0, atol=6e-3)}
+TOL = {"fp32": dict(rtol=1e-5, atol=2e-6), "tf32": dict(rtol=0, atol=4e-3), "tf32x2": dict(rtol=0, atol=6e-3),
+       "f16x2": dict(rtol=0, atol=6e-3)}
 # The tensor-core engines against their own numerics restated on the CPU (oracle.mlp_forward_tc).  What is left is the
 # fp32 accumulation order inside the MMAs: ~1e-7 typically (the MEAN error bound below), and - rarely - a hidden
 # activation that the two orders put on different sides of a tf32 truncation boundary (one tf32 ulp, 2^-10, of one of
@@ -134,7 +135,7 @@ TOL = {"fp32": dict(rtol=1e-5, atol=2e-6), "tf32": dict(rtol=0, atol=4e-3), "tf3
 # rounding instead of truncating the activations in the emulation gives mean 2.4e-4.
 TOL_TC = dict(rtol=0, atol=5e-4)
 TOL_TC_MEAN = 5e-6
-SECOND_LAYER = {"tf32": "fp32", "tf32x2": "tf32"}
+SECOND_LAYER = {"tf32": "fp32", "tf32x2": "tf32", "f16x2": "f16"}
 
 
 class _GameSubset:
@@ -252,7 +253,7 @@ def wide_net(a, seed, device):
     return net.to(device), w
 
 
-@pytest.mark.parametrize("precision", ["fp32", "tf32", "tf32x2"])
+@pytest.mark.parametrize("precision", ["fp32", "tf32", "tf32x2", "f16x2"])
 @pytest.mark.parametrize("batch", [96, 128, 1000, 20000, 40000])
 def test_fused_rollout_width256_vs_oracle(golden, precision, batch):
     """The tensor-core engine (and the fp32 engine on the same nets): width 256, A in 2..4, ragged and regular trees."""
@@ -269,7 +270,7 @@ def test_fused_rollout_width256_vs_oracle(golden, precision, batch):
     check_rollout_against_oracle(ep, tables_of(g), w, seed=ep.states.seed, tol=TOL[precision], precision=precision)
 
 
-@pytest.mark.parametrize("precision", ["tf32", "tf32x2"])
+@pytest.mark.parametrize("precision", ["tf32", "tf32x2", "f16x2"])
 def test_fused_rollout_repeated_launches_have_no_ordering_race(golden, precision):
     """The warp roles of the fused kernel are ordered by mbarriers only; an ordering hole shows up as a rare, gross error
     in whole lane quadrants (seen once: the heads overwrote the observation the value trunk's MMAs were still reading,
@@ -311,11 +312,11 @@ def test_default_precision_is_tensor_core_when_supported(golden):
     net, _ = wide_net(tree.max_actions, 3, DEV)
     ep = Episodes(tree, 256)
     ep.generate(net)
-    assert ep.precision == "tf32x2"              # both layers of the net on tcgen05: the fastest engine for this shape
+    assert ep.precision == "f16x2"               # both layers of the net on tcgen05: the fastest engine for this shape
     small = mlp_from_golden(g, "net", DEV)
     ep = Episodes(tree, 256)
     ep.generate(small)
-    assert ep.precision == ("tf32x2" if small.width == 256 else "fp32")
+    assert ep.precision == ("f16x2" if small.width == 256 else "fp32")
     assert ep.q_estimates.shape == ep.policy.shape and float(ep.q_estimates.abs().sum()) == 0
     assert ep.v_estimates.shape == ep.rewards.shape and float(ep.v_estimates.abs().sum()) == 0
 
@@ -395,7 +396,7 @@ def test_buffer_and_collate(golden):
     assert sub.policy.shape == (eps[0].t_eff + 1, 10, tree.max_actions)
 
 
-@pytest.mark.parametrize("precision", ["fp32", "tf32", "tf32x2"])
+@pytest.mark.parametrize("precision", ["fp32", "tf32", "tf32x2", "f16x2"])
 def test_rollout_with_weights_that_are_views_of_a_flat_buffer(golden, precision):
     """nn.Linear tensors are only 4-byte aligned when they view one flat parameter buffer (bench.py's e2e path)."""
     from environment.episode import Episodes
@@ -419,7 +420,7 @@ def test_rollout_with_weights_that_are_views_of_a_flat_buffer(golden, precision)
     check_rollout_against_oracle(ep, tables_of(g), w, seed=ep.states.seed, tol=TOL[precision], precision=precision)
 
 
-@pytest.mark.parametrize("precision", ["fp32", "tf32", "tf32x2"])
+@pytest.mark.parametrize("precision", ["fp32", "tf32", "tf32x2", "f16x2"])
 def test_selfplay_graph_equals_generate_and_carries_host_buffers(golden, precision):
     """environment.episode.SelfPlay: [weights H2D] -> rollout -> [returns D2H] replayed as one CUDA graph == Episodes.generate
     under the same seed and weights; fresh weights in the pinned host buffer are the next batch's actor; the per-game

@@ -289,7 +289,7 @@ def test_fused_learner_forward_vs_oracle(a, T, B):
     ref_tgt = orc.mlp_forward_batch(weights[1], obs)
     ref_reg = orc.mlp_forward_batch(weights[2], obs)
     ref_reg_ = orc.mlp_forward_batch(weights[3], obs)
-    tol = dict(rtol=0, atol=5e-3)             # tf32 first layer (10-bit mantissa), fp32 everywhere else
+    tol = dict(rtol=0, atol=5e-3)             # fp16 operands (11-bit significand), fp32 accumulation
     close(cpu(out["logit"]), ref_net[0], **tol)
     close(cpu(out["log_pi"]), ref_net[1], **tol)
     close(cpu(out["pi"]), ref_net[2], **tol)
@@ -301,13 +301,13 @@ def test_fused_learner_forward_vs_oracle(a, T, B):
     assert bool((cpu(out["pi"])[mask == 0] == 0).all()) and bool((cpu(out["log_pi"])[mask == 0] == 0).all())
     close(cpu(out["pi"]).sum(-1), torch.ones(T, B), rtol=0, atol=1e-6)
     err = (cpu(out["logit"]) - ref_net[0]).abs().max().item()
-    # tight check against the engine's numerics restated on the CPU (oracle.mlp_forward_tc): tf32-rounded first-layer
-    # operands and (pipelined kernel, both layers on the tensor core; A = 4 in two launches) tf32 second layers with the
-    # activations truncated; fp64 accumulation.  What is left is fp32 accumulation order - and, rarely, an activation
-    # on the other side of a tf32 truncation boundary (see tests/test_gpu_env_rollout.py::TOL_TC).
+    # tight check against the engine's numerics restated on the CPU (oracle.mlp_forward_tc): fp16-rounded operands in
+    # both layers (pipelined kernel, both layers on the tensor core with kind::f16; A = 4 in two launches), activations
+    # rounded to fp16; fp64 accumulation.  What is left is fp32 accumulation order - and, rarely, an activation on the
+    # other side of an fp16 rounding boundary (see tests/test_gpu_env_rollout.py::TOL_TC).
     flat = obs.reshape(T * B, -1)
-    second = "tf32"
-    tol_max, tol_mean = (5e-4, 5e-6) if second == "tf32" else (2e-5, 2e-6)
+    second = "f16"
+    tol_max, tol_mean = (5e-4, 5e-6)
     for key_l, key_v, wts in (("logit", "v", weights[0]), (None, "v_target", weights[1])):
         e_logit, _, e_v, _, _, _ = orc.mlp_forward_tc(wts, flat, second)
         if key_l:
@@ -330,7 +330,7 @@ def test_fused_learner_forward_vs_oracle(a, T, B):
         again = fl.forward(obs_dev, *nets)
         for k, v in first.items():
             assert torch.equal(again[k], v), f"launch {it}: {k} differs from the first launch by {float((again[k] - v).abs().max()):.3e}"
-    print(f"fused forward A={a}: max |logit error| = {err:.2e} vs fp32 net, {err_tc:.2e} vs tf32-aware oracle")
+    print(f"fused forward A={a}: max |logit error| = {err:.2e} vs fp32 net, {err_tc:.2e} vs fp16-aware oracle")
 
 
 @pytest.mark.parametrize("a,T,B", [(2, 4, 300), (3, 8, 4099), (4, 5, 2048), (3, 2, 77)])
