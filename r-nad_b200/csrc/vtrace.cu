@@ -445,16 +445,21 @@ __global__ void __launch_bounds__(kTbGames* kTCap, 1024 / (kTbGames * kTCap))
         const bool is_valid = active && io.indices[i] != 0;
         const float val = is_valid ? 1.f : 0.f;
         const int turn = active ? (int)io.turns[i] : 0;
-        float a_oh[A], mu[A], pi[A], mask[A], L[A], ones[A], prod[A], pt[A], logit[A];
+        float a_oh[A], mu[A], pi[A], mask[A], L[A], ones[A], prod[A], pt[A], logit[A], log_pi[A], lreg[A], lreg_[A];
+        // every load of the slot first, in one round trip to memory (the arithmetic below depends on the first of them)
 #pragma unroll
-        float log_pi[A];
         for (int a = 0; a < A; ++a) {
             a_oh[a] = io.actions_oh[i * A + a];
             mu[a] = io.mu[i * A + a];
             mask[a] = io.masks[i * A + a];
             logit[a] = io.logit[i * A + a];
+            lreg[a] = io.log_pi_reg[i * A + a];
+            lreg_[a] = io.log_pi_reg_[i * A + a];
             ones[a] = 1.f;
         }
+        const float v_net = io.v_target_net[i];
+        const float reward = io.rewards[i];
+        const float v_learner = io.v[i];
         if (io.pi != nullptr) {
 #pragma unroll
             for (int a = 0; a < A; ++a) {
@@ -466,10 +471,7 @@ __global__ void __launch_bounds__(kTbGames* kTCap, 1024 / (kTbGames * kTCap))
         }
 #pragma unroll
         for (int a = 0; a < A; ++a)   // rnad.py:382  log_pi - (alpha*log_pi_reg + (1-alpha)*log_pi_reg_)
-            L[a] = sub(log_pi[a], add(mul(p.alpha, io.log_pi_reg[i * A + a]), mul(one_minus_alpha, io.log_pi_reg_[i * A + a])));
-        const float v_net = io.v_target_net[i];
-        const float reward = io.rewards[i];
-        const float v_learner = io.v[i];
+            L[a] = sub(log_pi[a], add(mul(p.alpha, lreg[a]), mul(one_minus_alpha, lreg_[a])));
         process_policy_row<A>(pi, mask, n_disc, p.eps_threshold, pt);
 #pragma unroll
         for (int a = 0; a < A; ++a) prod[a] = mul(pt[a], L[a]);
