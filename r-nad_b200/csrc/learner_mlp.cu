@@ -23,6 +23,7 @@
 // re-read from HBM about ten times per update.
 #include <cstdlib>
 
+#include "learner_bwd.cuh"
 #include "tc_common.cuh"
 #include "tc_pipe.cuh"
 
@@ -39,25 +40,6 @@ namespace tc {
 
 constexpr int kLearnThreads = 256;   // two threads per trajectory row
 constexpr int kFwdTrunks = 5;        // learner value, learner policy, target value, reg policy, reg_ policy
-
-template <int A>
-struct Shape {
-    static constexpr int KIN = 2 * A * A;
-    static constexpr bool kBiasInK = (KIN % 8) != 0;
-    static constexpr int KP = round_up(KIN + (kBiasInK ? 1 : 0), 8);
-    static constexpr int kTrunkBytes = kHidden * KP * 4;
-    // number of learner parameters, in state_dict order:
-    // value_fc0.{weight,bias}, value_fc1.{weight,bias}, policy_fc0.{weight,bias}, policy_fc1.{weight,bias}
-    static constexpr int kOffV0w = 0;
-    static constexpr int kOffV0b = kOffV0w + kHidden * KIN;
-    static constexpr int kOffV1w = kOffV0b + kHidden;
-    static constexpr int kOffV1b = kOffV1w + kHidden;
-    static constexpr int kOffP0w = kOffV1b + 1;
-    static constexpr int kOffP0b = kOffP0w + kHidden * KIN;
-    static constexpr int kOffP1w = kOffP0b + kHidden;
-    static constexpr int kOffP1b = kOffP1w + A * kHidden;
-    static constexpr int kParams = kOffP1b + A;
-};
 
 // ------------------------------------------------------------------ forward
 
@@ -127,18 +109,6 @@ __global__ void pack_fwd_image_kernel(FwdNets w, uint8_t* __restrict__ image) {
                                        w.reg_.policy_fc1_b};
         const int n = (tr == 0 || tr == 2) ? 1 : A;
         reinterpret_cast<float*>(image + P::kB2)[thread] = a < n ? b2[tr][a] : 0.f;
-    }
-}
-
-// row of the observation tensor -> registers (8-byte loads; KIN is even)
-template <int KIN>
-__device__ __forceinline__ void load_row(const float* __restrict__ obs, int64_t row, bool active, float (&x)[KIN]) {
-    const float2* src = reinterpret_cast<const float2*>(obs + row * KIN);
-#pragma unroll
-    for (int i = 0; i < KIN / 2; ++i) {
-        const float2 v = active ? __ldg(src + i) : make_float2(0.f, 0.f);
-        x[2 * i] = v.x;
-        x[2 * i + 1] = v.y;
     }
 }
 
@@ -604,15 +574,6 @@ __host__ __device__ constexpr uint32_t idesc_tf32(int n) {
     return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
 }
 
-__device__ __forceinline__ uint64_t desc_lbo_sbo(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-    uint64_t d = 0;
-    d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
-    d |= (uint64_t)(lbo_bytes >> 4) << 16;
-    d |= (uint64_t)(sbo_bytes >> 4) << 32;
-    d |= (uint64_t)1 << 46;
-    return d;
-}
-
 __device__ __forceinline__ void mma_ss_n(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, bool acc) {
     asm volatile(
         "{\n\t"
@@ -623,16 +584,6 @@ __device__ __forceinline__ void mma_ss_n(uint32_t d_tmem, uint64_t a_desc, uint6
         "l"(a_desc), "l"(b_desc), "r"(idesc), "r"((uint32_t)acc)
         : "memory");
 }
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-        : "r"(taddr)
-        : "memory");
-}
-
 template <int A>
 __global__ void pack_bwd_tc_image_kernel(rnad_mlp_weights w, uint8_t* __restrict__ image) {
     using P = BwdTcPlan<A>;
@@ -920,6 +871,14 @@ __global__ void __launch_bounds__(kBwdTcThreads, 2) learner_bwd_tc_kernel(const 
 //  one) + ~300 issue cycles of relu / mask arithmetic per SM sub-partition, and the tensor core's own tensor-memory
 //  traffic (A operands and accumulators) does not overlap with the consumers' - a variant with three buffers and two
 //  stages of slack ran no faster (133 us), i.e. the stage time is the SUM of these, not their maximum.]
+#ifdef RNAD_TRACE_BWD
+// development aid: cycle stamps of CTA 0, stages 16..79: [role][stage - 16][event]; role 0 = consumer warp 0, 1 = consumer
+// warp 15, 2 = issuer 0, 3 = issuer 1, 4 = producer warp 0 (per tile)
+__device__ long long g_bwd_trace[5][64][8];
+#define BTR(role, s, ev) do { if (blockIdx.x == 0 && (s) >= 16 && (s) < 80 && lane32 == 0) g_bwd_trace[role][(s) - 16][ev] = clock64(); } while (0)
+#else
+#define BTR(role, s, ev) do { } while (0)
+#endif
 constexpr int kBwd2Consumers = 512, kBwd2Producers = 128, kBwd2Issuers = 64;
 constexpr int kBwd2Threads = kBwd2Consumers + kBwd2Producers + kBwd2Issuers;
 
@@ -1053,9 +1012,12 @@ __global__ void __launch_bounds__(kBwd2Threads, 1) learner_bwd_tc2_kernel(const 
             const int trunk = (int)(s >> 1) & 1, rh = (int)(s >> 2) & 1;
             const int64_t k = s >> 3;
             const bool more = s + 2 < n_stages;
+            BTR(2 + b, s, 0);
             if (more) need_tile((s + 2) >> 3);
+            BTR(2 + b, s, 1);
             tcp::mbar_wait_c(bar_c(b), (uint32_t)(s >> 1) & 1u);            // relu^T / dh^T of stage s are in buffer b
             tc_fence_after();
+            BTR(2 + b, s, 2);
             // grad(s): D_w2 += relu^T BG^T, D_w1 += dh^T BX^T (K = the stage's 64 rows); then recompute(s + 2) into the buffer
             // just read; one commit covers both groups
             const uint32_t tile = smem_u32(smem + P::kTile + (int)(k & 1) * P::kTileBytes);
@@ -1077,6 +1039,7 @@ __global__ void __launch_bounds__(kBwd2Threads, 1) learner_bwd_tc2_kernel(const 
                 mma_commit(bar_r(b));
             }
             __syncwarp();
+            BTR(2 + b, s, 3);
         }
     } else if (tid >= kBwd2Consumers) {
         // ------------------------------------------------------------ producers: one thread per tile row
@@ -1100,7 +1063,9 @@ __global__ void __launch_bounds__(kBwd2Threads, 1) learner_bwd_tc2_kernel(const 
 #pragma unroll
             for (int a = 0; a < A; ++a) g[1 + a] = active ? __ldg(d_logit + row * A + a) : 0.f;
             const int tb = (int)(k & 1);
+            if (pw == 0) BTR(4, 8 * k, 0);
             if (k >= 2) tcp::mbar_wait_c(bar_empty(tb), (uint32_t)((k >> 1) - 1) & 1u);   // the MMAs of tile k - 2 are done with it
+            if (pw == 0) BTR(4, 8 * k, 1);
             uint8_t* tile = smem + P::kTile + tb * P::kTileBytes;
             store_operand_row<KIN, KP, P::kBiasInK>(tile + P::kX, n, x);
 #pragma unroll
@@ -1119,6 +1084,7 @@ __global__ void __launch_bounds__(kBwd2Threads, 1) learner_bwd_tc2_kernel(const 
             fence_async_smem();
             __syncwarp();
             if (lane32 == 0) tcp::mbar_arrive(bar_full(tb));
+            if (pw == 0) BTR(4, 8 * k, 2);
         }
         // output-bias gradients: sums of g over the CTA's rows
         float* s_red = reinterpret_cast<float*>(smem + P::kRed);
@@ -1141,14 +1107,17 @@ __global__ void __launch_bounds__(kBwd2Threads, 1) learner_bwd_tc2_kernel(const 
         for (int64_t s = 0; s < n_stages; ++s) {
             const int b = (int)(s & 1), trunk = (int)(s >> 1) & 1;
             const float bias = bias_j[trunk * 2 + b];
+            if (warp == 0 || warp == 15) BTR(warp == 0 ? 0 : 1, s, 0);
             tcp::mbar_wait_c(bar_r(b), (uint32_t)(s >> 1) & 1u);
             tc_fence_after();
+            if (warp == 0 || warp == 15) BTR(warp == 0 ? 0 : 1, s, 1);
             // ---- this thread's 16 rows of its hidden unit: relu^T over H^T, dh^T = S^T where h > 0, both in place
             uint32_t hr[16], dh[16];
             const uint32_t th = tmem_lane + b * 128 + cpart * 16;
             tmem_ld16(th, hr);
             tmem_ld16(th + 64, dh);
             tmem_ld_wait();
+            if (warp == 0 || warp == 15) BTR(warp == 0 ? 0 : 1, s, 2);
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
                 const float h = __uint_as_float(hr[i]) + bias;
@@ -1167,9 +1136,11 @@ __global__ void __launch_bounds__(kBwd2Threads, 1) learner_bwd_tc2_kernel(const 
                 "r"(dh[9]), "r"(dh[10]), "r"(dh[11]), "r"(dh[12]), "r"(dh[13]), "r"(dh[14]), "r"(dh[15])
                 : "memory");
             tcp::tmem_st_wait();
+            if (warp == 0 || warp == 15) BTR(warp == 0 ? 0 : 1, s, 3);
             tc_fence_before();
             __syncwarp();
             if (lane32 == 0) tcp::mbar_arrive(bar_c(b));
+            if (warp == 0 || warp == 15) BTR(warp == 0 ? 0 : 1, s, 4);
         }
         // every gradient MMA complete: the last commit of each issuer
         if (n_stages >= 2) {
@@ -1213,6 +1184,16 @@ __global__ void __launch_bounds__(kBwd2Threads, 1) learner_bwd_tc2_kernel(const 
     if (warp == 0) tmem_dealloc<512>(tmem_base);
 }
 
+#ifdef RNAD_TRACE_BWD
+}  // namespace tc
+}  // namespace rnad
+extern "C" __attribute__((visibility("default"))) int rnad_debug_bwd_trace(long long* host_out) {
+    return (int)cudaMemcpyFromSymbol(host_out, rnad::tc::g_bwd_trace, sizeof(rnad::tc::g_bwd_trace));
+}
+namespace rnad {
+namespace tc {
+#endif
+
 // Sum of the per-CTA partial gradients in a FIXED order (deterministic): eight lanes per parameter take the partials
 // p = lane, lane + 8, ... (eight loads in flight per thread as well) and meet in a shuffle tree.
 // Split mode (gridDim.y == 2): blockIdx.y = player; player p's partials are the rows p, p + 2, ... (pairs with index
@@ -1239,7 +1220,6 @@ __global__ void reduce_partials_kernel(const float* __restrict__ partials, int n
     if (i < n_params && sub == 0) flat_grad[(int64_t)blockIdx.y * n_params + i] = acc;
 }
 
-constexpr int kMaxBwdCtas = 160;
 
 // the forward kernels' weight image sits at the start of the workspace: room for the larger of the two builds
 template <int A>

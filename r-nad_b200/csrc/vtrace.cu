@@ -410,7 +410,10 @@ constexpr int kTbMaxT = 32;
 // `ticket` (device uint32, zero before the launch and zero again after it): the last block to finish adds the
 // per-block partial sums in block order (deterministic) - no separate reduction launch.
 template <int A, int kTCap>
-__global__ void __launch_bounds__(kTbGames* kTCap, 1024 / (kTbGames * kTCap))
+#ifndef RNAD_K3_BLOCKS_X
+#define RNAD_K3_BLOCKS_X 1024
+#endif
+__global__ void __launch_bounds__(kTbGames* kTCap, RNAD_K3_BLOCKS_X / (kTbGames * kTCap))
     learner_targets_tb_kernel(rnad_learner_io io, rnad_learner_params p, int T, int64_t B, float* partials,
                               unsigned int* ticket) {
     __shared__ float s_v[kTCap][kTbGames], s_reward[kTCap][kTbGames], s_cs[kTCap][kTbGames], s_ent[kTCap][kTbGames];
@@ -584,9 +587,9 @@ __global__ void __launch_bounds__(kTbGames* kTCap, 1024 / (kTbGames * kTCap))
         float acc = 0.f;
         for (int w = 0; w < (int)blockDim.y; ++w) acc += red[g][w];
         partials[blockIdx.x * 4 + g] = acc;
+        __threadfence();                  // (only the writers: a fence by all 256 threads costs a membar stall each)
     }
     // ---- the last block to arrive sums the partials of all blocks, in block order
-    __threadfence();
     __syncthreads();
     if (t == 0 && g == 0) s_last = atomicAdd(ticket, 1u) == gridDim.x - 1;
     __syncthreads();
