@@ -1,5 +1,5 @@
-// Declarations shared by the learner's backward kernels (learner_mlp.cu: the tf32 builds; learner_bwd_f16.cu: the
-// fp16-operand build): parameter layout, row loads, descriptor / tensor-memory helpers.
+// Declarations shared by the learner's backward kernels (learner_mlp.cu, learner_bwd_tc3.cu): parameter layout, row
+// loads, operand tiles, descriptor / tensor-memory helpers.
 #pragma once
 
 #include "tc_common.cuh"
@@ -41,6 +41,34 @@ __device__ __forceinline__ void load_row(const float* __restrict__ obs, int64_t 
     }
 }
 
+template <int KIN, int KP, bool kBiasInK>
+__device__ __forceinline__ void store_operand_row(uint8_t* tile, int lane, const float (&x)[KIN]) {
+#pragma unroll
+    for (int q = 0; q < KP / 4; ++q) {
+        float v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int k = 4 * q + u;
+            v[u] = k < KIN ? to_tf32_fast(x[k < KIN ? k : 0]) : ((kBiasInK && k == KIN) ? 1.f : 0.f);
+        }
+        *reinterpret_cast<float4*>(tile + operand_offset<KP>(lane, 4 * q)) = make_float4(v[0], v[1], v[2], v[3]);
+    }
+}
+
+__host__ __device__ constexpr uint32_t idesc_tf32(int n) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
+}
+
+__device__ __forceinline__ void mma_ss_n(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, bool acc) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+        "}\n" ::"r"(d_tmem),
+        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"((uint32_t)acc)
+        : "memory");
+}
 __device__ __forceinline__ uint64_t desc_lbo_sbo(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
     uint64_t d = 0;
     d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
@@ -61,13 +89,13 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
 }
 
 
-// The pipelined backward with fp16 operands (learner_bwd_f16.cu).  `image`: the backward's share of the workspace
-// (at least the tf32 image's size); mode: 0 = pack the weight image, then run; 1 = prepacked; 2 = pack only.
-// Leaves `blocks` per-CTA partial gradients in `partials` (split mode: pairs of CTAs alternate between the players).
-int learner_backward_f16(int A, const float* obs, int64_t N, int T_split, int64_t B_split, const rnad_mlp_weights& w,
-                         const float* d_logit, const float* d_v, uint8_t* image, float* partials, int blocks,
-                         cudaStream_t st, int mode);
-int64_t learner_backward_f16_image_bytes(int A);
+// The "mask" formulation of the pipelined backward (learner_bwd_tc3.cu), the default where its accumulators fit
+// tensor memory (max_actions <= 3).  `image`: the image of pack_bwd_tc_image_kernel (first layers + biases are read);
+// leaves `blocks` per-CTA partial gradients in `partials` (split mode: CTAs of even / odd index serve player 0 / 1).
+bool learner_backward_tc3_supported(int A);
+int learner_backward_tc3(int A, const float* obs, int64_t N, int T_split, int64_t B_split, const rnad_mlp_weights& w,
+                         const float* d_logit, const float* d_v, const uint8_t* image, float* partials, int blocks,
+                         cudaStream_t st);
 
 }  // namespace tc
 }  // namespace rnad

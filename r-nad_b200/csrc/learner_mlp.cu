@@ -112,20 +112,6 @@ __global__ void pack_fwd_image_kernel(FwdNets w, uint8_t* __restrict__ image) {
     }
 }
 
-template <int KIN, int KP, bool kBiasInK>
-__device__ __forceinline__ void store_operand_row(uint8_t* tile, int lane, const float (&x)[KIN]) {
-#pragma unroll
-    for (int q = 0; q < KP / 4; ++q) {
-        float v[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const int k = 4 * q + u;
-            v[u] = k < KIN ? to_tf32_fast(x[k < KIN ? k : 0]) : ((kBiasInK && k == KIN) ? 1.f : 0.f);
-        }
-        *reinterpret_cast<float4*>(tile + operand_offset<KP>(lane, 4 * q)) = make_float4(v[0], v[1], v[2], v[3]);
-    }
-}
-
 template <int KP>
 __device__ __forceinline__ void issue_trunk_mma(uint32_t a_base, uint32_t b_trunk, uint32_t d_tmem, uint32_t mbar) {
 #pragma unroll
@@ -570,20 +556,6 @@ struct BwdTcPlan : Shape<A> {
     static_assert(kX % 16 == 0 && kBX % 16 == 0 && kBG % 16 == 0 && kG % 16 == 0 && kBar % 8 == 0, "alignment");
 };
 
-__host__ __device__ constexpr uint32_t idesc_tf32(int n) {
-    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
-}
-
-__device__ __forceinline__ void mma_ss_n(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, bool acc) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
-        "}\n" ::"r"(d_tmem),
-        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"((uint32_t)acc)
-        : "memory");
-}
 template <int A>
 __global__ void pack_bwd_tc_image_kernel(rnad_mlp_weights w, uint8_t* __restrict__ image) {
     using P = BwdTcPlan<A>;
@@ -1291,7 +1263,17 @@ int launch_backward(const float* obs, int64_t N, int T_split, int64_t B_split, c
             RNAD_CHECK_LAUNCH("pack_bwd_tc_image_kernel");
             if (mode == 2) return RNAD_OK;
         }
-        static const bool two_ctas = getenv("RNAD_LEARNER_BWD_V1") != nullptr;   // the previous kernel (two CTAs per SM), for A/B runs
+        static const bool two_ctas = getenv("RNAD_LEARNER_BWD_V1") != nullptr;   // the first kernel (two CTAs per SM), for A/B runs
+        static const bool v2 = getenv("RNAD_LEARNER_BWD_V2") != nullptr;         // the S^T formulation where the mask one fits, for A/B runs
+        static_assert(PT::kB == 0 && PT::kB1 == 2 * PT::kTrunkBytes, "learner_bwd_tc3.cu reads the head of this image");
+        if (!two_ctas && !v2 && learner_backward_tc3_supported(A)) {
+            int rc = learner_backward_tc3(A, obs, N, T_split, B_split, w, d_logit, d_v, image, partials, (int)blocks, st);
+            if (rc) return rc;
+            reduce_partials_kernel<<<dim3((P::kParams * 8 + 255) / 256, T_split > 0 ? 2 : 1), 256, 0, st>>>(
+                partials, (int)blocks, P::kParams, flat_grad);
+            RNAD_CHECK_LAUNCH("reduce_partials_kernel");
+            return RNAD_OK;
+        }
         if (!two_ctas) {
             using P2 = BwdTc2Plan<A>;
             // one CTA per SM (all 512 tensor-memory columns): more than half of the shared memory keeps a second one out
