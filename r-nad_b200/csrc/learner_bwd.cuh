@@ -97,5 +97,14 @@ int learner_backward_tc3(int A, const float* obs, int64_t N, int T_split, int64_
                          const float* d_logit, const float* d_v, const uint8_t* image, float* partials, int blocks,
                          cudaStream_t st);
 
+// The fp16-operand engine (learner_bwd_f16.cu), for UNNORMALISED gradients (split mode).  `image`: its own share of
+// the workspace, learner_backward_f16_image_bytes(A) bytes; mode: 0 = pack the weight image, then run; 1 = prepacked;
+// 2 = pack only.
+bool learner_backward_f16_supported(int A);
+int64_t learner_backward_f16_image_bytes(int A);
+int learner_backward_f16(int A, const float* obs, int64_t N, int T_split, int64_t B_split, const rnad_mlp_weights& w,
+                         const float* d_logit, const float* d_v, uint8_t* image, float* partials, int blocks,
+                         cudaStream_t st, int mode);
+
 }  // namespace tc
 }  // namespace rnad

@@ -23,6 +23,11 @@ namespace {
 
 constexpr int kConsumers = 512, kProducers = 128, kIssuers = 64;
 constexpr int kThreads3 = kConsumers + kProducers + kIssuers;
+#ifndef RNAD_BWD3_GROUPS
+#define RNAD_BWD3_GROUPS 2
+#endif
+constexpr int kGroups = RNAD_BWD3_GROUPS;   // consumer groups: 2 = one per stage buffer, 1 = all sixteen warps on every stage
+static_assert(kGroups == 1 || kGroups == 2, "one or two consumer groups");
 
 template <int A>
 struct Plan3 : Shape<A> {
@@ -79,7 +84,7 @@ __global__ void __launch_bounds__(kThreads3, 1) learner_bwd_tc3_kernel(const flo
         mbar_init(bar_img, 1);
         for (int b = 0; b < 2; ++b) {
             mbar_init(bar_r(b), 1);
-            mbar_init(bar_c(b), kConsumers / 32);
+            mbar_init(bar_c(b), kConsumers / 32 / kGroups);
             mbar_init(bar_full(b), kProducers / 32);
             mbar_init(bar_empty(b), 2);                              // one commit per issuer
         }
@@ -235,8 +240,14 @@ __global__ void __launch_bounds__(kThreads3, 1) learner_bwd_tc3_kernel(const flo
             if (lane32 == 0) s_red[pw * 8 + a] = v;
         }
     } else {
-        // ------------------------------------------------------------ consumers: thread = hidden unit x 16 rows of a stage
-        const int quad = warp & 3, cpart = warp >> 2;             // TMEM lane quadrant (hidden unit), 16-column (row) part of a stage
+        // ------------------------------------------------------------ consumers: thread = hidden unit x 16 * kGroups rows of a stage
+        // Two GROUPS of eight warps, one per stage buffer (group b takes the stages with s & 1 == b): a stage's
+        // round trip - barrier wake-up, tcgen05.ld, arithmetic, tcgen05.st, arrival - is mostly latency, and with all
+        // sixteen warps on the same stage nothing hid it (the consumers, not the tensor core, bounded the kernel).
+        const int quad = warp & 3, cpart = warp >> 2;             // TMEM lane quadrant (hidden unit); (trunk, half) of the final read-out
+        const int group = kGroups == 2 ? warp >> 3 : 0;
+        const int cw = kGroups == 2 ? cpart & 1 : cpart;           // which kColsW columns (rows of the tile) of a 64-column stage
+        constexpr int kColsW = 16 * kGroups;
         const int j_local = quad * 32 + lane32;
         const uint32_t tmem_lane = tmem_base + ((uint32_t)(quad * 32) << 16);
         tcp::mbar_wait_c(bar_img, 0);
@@ -245,43 +256,54 @@ __global__ void __launch_bounds__(kThreads3, 1) learner_bwd_tc3_kernel(const flo
 #pragma unroll
         for (int c = 0; c < 4; ++c) bias_j[c] = P::kBiasInK ? 0.f : b1[(c >> 1) * kHidden + (c & 1) * 128 + j_local];
 #pragma unroll 1
-        for (int64_t s = 0; s < n_stages; ++s) {
+        for (int64_t s = group; s < n_stages; s += kGroups) {
             const int b = (int)(s & 1), trunk = (int)(s >> 1) & 1;
             tcp::mbar_wait_c(bar_r(b), (uint32_t)(s >> 1) & 1u);
             tc_fence_after();
-            // ---- this thread's 16 rows of its hidden unit: relu^T in place of H^T, the 0/1 mask next to it
-            uint32_t hr[16], mk[16];
-            const uint32_t th = tmem_lane + b * 128 + cpart * 16;
-            tmem_ld16(th, hr);
+            // ---- this thread's rows of its hidden unit: relu^T in place of H^T, the 0/1 mask next to it
+            uint32_t hr[kColsW];
+            const uint32_t th = tmem_lane + b * 128 + cw * kColsW;
+#pragma unroll
+            for (int q = 0; q < kGroups; ++q) tmem_ld16(th + q * 16, hr + q * 16);
             tmem_ld_wait();
             if (!P::kBiasInK) {
                 const float bias = bias_j[trunk * 2 + b];
 #pragma unroll
-                for (int i = 0; i < 16; ++i) hr[i] = __float_as_uint(__uint_as_float(hr[i]) + bias);
+                for (int i = 0; i < kColsW; ++i) hr[i] = __float_as_uint(__uint_as_float(hr[i]) + bias);
             }
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
-                const float h = __uint_as_float(hr[i]);
-                mk[i] = __float_as_uint(__saturatef(h * 1.7014118346046923e38f));   // 2^127: 1 for every normal h > 0, else 0
-                hr[i] = __float_as_uint(fmaxf(h, 0.f));
+            for (int q = 0; q < kGroups; ++q) {
+                uint32_t mk[16];
+                uint32_t* h16 = hr + q * 16;
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    const float h = __uint_as_float(h16[i]);
+                    mk[i] = __float_as_uint(__saturatef(h * 1.7014118346046923e38f));   // 2^127: 1 for every normal h > 0, else 0
+                    h16[i] = __float_as_uint(fmaxf(h, 0.f));
+                }
+                asm volatile(
+                    "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(th + q * 16),
+                    "r"(h16[0]), "r"(h16[1]), "r"(h16[2]), "r"(h16[3]), "r"(h16[4]), "r"(h16[5]), "r"(h16[6]), "r"(h16[7]), "r"(h16[8]),
+                    "r"(h16[9]), "r"(h16[10]), "r"(h16[11]), "r"(h16[12]), "r"(h16[13]), "r"(h16[14]), "r"(h16[15])
+                    : "memory");
+                asm volatile(
+                    "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(th + 64 + q * 16),
+                    "r"(mk[0]), "r"(mk[1]), "r"(mk[2]), "r"(mk[3]), "r"(mk[4]), "r"(mk[5]), "r"(mk[6]), "r"(mk[7]), "r"(mk[8]),
+                    "r"(mk[9]), "r"(mk[10]), "r"(mk[11]), "r"(mk[12]), "r"(mk[13]), "r"(mk[14]), "r"(mk[15])
+                    : "memory");
             }
-            asm volatile(
-                "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(th),
-                "r"(hr[0]), "r"(hr[1]), "r"(hr[2]), "r"(hr[3]), "r"(hr[4]), "r"(hr[5]), "r"(hr[6]), "r"(hr[7]), "r"(hr[8]),
-                "r"(hr[9]), "r"(hr[10]), "r"(hr[11]), "r"(hr[12]), "r"(hr[13]), "r"(hr[14]), "r"(hr[15])
-                : "memory");
-            asm volatile(
-                "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(th + 64),
-                "r"(mk[0]), "r"(mk[1]), "r"(mk[2]), "r"(mk[3]), "r"(mk[4]), "r"(mk[5]), "r"(mk[6]), "r"(mk[7]), "r"(mk[8]),
-                "r"(mk[9]), "r"(mk[10]), "r"(mk[11]), "r"(mk[12]), "r"(mk[13]), "r"(mk[14]), "r"(mk[15])
-                : "memory");
             tcp::tmem_st_wait();
             tc_fence_before();
             __syncwarp();
             if (lane32 == 0) tcp::mbar_arrive(bar_c(b));
         }
-        // every gradient MMA complete: the last commit of each issuer
-        if (n_stages >= 2) {
+        // every gradient MMA complete: the last commit of each issuer (a group has followed its own buffer's barrier
+        // only, so it waits there and the groups meet at a named barrier)
+        if (kGroups == 2) {
+            if (n_stages >= 2) tcp::mbar_wait_c(bar_r(group), (uint32_t)(n_stages >> 1) & 1u);
+            tc_fence_before();
+            asm volatile("bar.sync 1, %0;" ::"n"(kConsumers) : "memory");
+        } else if (n_stages >= 2) {
             tcp::mbar_wait_c(bar_r(0), (uint32_t)(n_stages >> 1) & 1u);
             tcp::mbar_wait_c(bar_r(1), (uint32_t)(n_stages >> 1) & 1u);
         }

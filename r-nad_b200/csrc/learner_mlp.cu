@@ -1200,9 +1200,15 @@ int64_t fwd_image_reserve() {
     return round_up((int)(v1 > v2 ? v1 : v2), 256);
 }
 
+// then the backward's images: the tf32 one (pack_bwd_tc_image_kernel) and, where that engine exists, the fp16 one
+template <int A>
+int64_t bwd_image_reserve() {
+    return round_up(BwdTcPlan<A>::kImageBytes, 256) + round_up((int)learner_backward_f16_image_bytes(A), 256);
+}
+
 template <int A>
 int64_t workspace_bytes() {
-    return fwd_image_reserve<A>() + round_up(BwdTcPlan<A>::kImageBytes, 256) + (int64_t)kMaxBwdCtas * Shape<A>::kParams * 4;
+    return fwd_image_reserve<A>() + bwd_image_reserve<A>() + (int64_t)kMaxBwdCtas * Shape<A>::kParams * 4;
 }
 
 template <int A, typename Kernel>
@@ -1239,7 +1245,8 @@ int launch_backward(const float* obs, int64_t N, int T_split, int64_t B_split, c
     using PT = BwdTcPlan<A>;
     static_assert(PT::kImageBytes >= P::kImageBytes, "the workspace reserves the larger image");
     uint8_t* image = workspace + fwd_image_reserve<A>();
-    float* partials = reinterpret_cast<float*>(image + round_up(PT::kImageBytes, 256));
+    uint8_t* image_f16 = image + round_up(PT::kImageBytes, 256);
+    float* partials = reinterpret_cast<float*>(image + bwd_image_reserve<A>());
     int64_t blocks = (N + kTileM - 1) / kTileM;
     const int cap = sm_count() < kMaxBwdCtas ? sm_count() : kMaxBwdCtas;
     if (T_split > 0) {
@@ -1258,6 +1265,20 @@ int launch_backward(const float* obs, int64_t N, int T_split, int64_t B_split, c
         learner_bwd_kernel<A><<<(int)blocks, kLearnThreads, P::kBytes, st>>>(obs, N, image, w, d_logit, d_v, partials);
         RNAD_CHECK_LAUNCH("learner_bwd_kernel");
     } else {
+        // split mode (one UNNORMALISED gradient per player: the learner step) runs on the fp16-operand engine
+        // (learner_bwd_f16.cu) where it exists; RNAD_LEARNER_BWD_TF32 keeps the tf32 kernels there too, for A/B runs
+        static const bool tf32_only = getenv("RNAD_LEARNER_BWD_TF32") != nullptr || getenv("RNAD_LEARNER_BWD_V1") != nullptr ||
+                                      getenv("RNAD_LEARNER_BWD_V2") != nullptr;
+        const bool f16_engine = !tf32_only && learner_backward_f16_supported(A);
+        if (f16_engine && (T_split > 0 || mode == 2)) {
+            int rc = learner_backward_f16(A, obs, N, T_split, B_split, w, d_logit, d_v, image_f16, partials, (int)blocks, st, mode);
+            if (rc) return rc;
+            if (mode != 2) {
+                reduce_partials_kernel<<<dim3((P::kParams * 8 + 255) / 256, 2), 256, 0, st>>>(partials, (int)blocks, P::kParams, flat_grad);
+                RNAD_CHECK_LAUNCH("reduce_partials_kernel");
+                return RNAD_OK;
+            }
+        }
         if (mode != 1) {      // (mode as in learner_fwd_tc2.cu: 0 pack + run, 1 prepacked, 2 pack only)
             pack_bwd_tc_image_kernel<A><<<32, 256, 0, st>>>(w, image);
             RNAD_CHECK_LAUNCH("pack_bwd_tc_image_kernel");

@@ -70,7 +70,10 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
 
 // mbarrier wait with a small code footprint (the hot loops of three warp roles share the instruction cache);
 // try_wait suspends the warp for a hardware time slice per probe, the spin bound turns a lost arrival into a trap
-constexpr uint32_t kSuspendHintNs = 20000;   // let the hardware park a waiting warp instead of polling
+#ifndef RNAD_SUSPEND_HINT_NS
+#define RNAD_SUSPEND_HINT_NS 20000
+#endif
+constexpr uint32_t kSuspendHintNs = RNAD_SUSPEND_HINT_NS;   // let the hardware park a waiting warp instead of polling
 __device__ __forceinline__ void mbar_wait_c(uint32_t mbar, uint32_t parity) {
     uint32_t done = 0;
 #pragma unroll 1

@@ -87,6 +87,22 @@ class FusedLearner:
         return self.flat_grad
 
 
+    def backward_split(self, observations, net, d_logit, d_v):
+        """
+        One UNNORMALISED gradient per player (rows of even t: player 0, odd t: player 1) -> (2, P) tensor
+        (`rnad_learner_backward_split`, the learner step's backward: fp16-operand engine where it exists).
+        """
+        t, b = observations.shape[:2]
+        obs = observations.detach().contiguous()
+        out = torch.empty(2, self.flat_grad.numel(), dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            w = _b200.mlp_weights(net, self.device)
+            _b200.lib().rnad_learner_backward_split(_b200.ptr(obs, torch.float32), t, b, self.a, ctypes.byref(w),
+                                                    _b200.ptr(d_logit, torch.float32), _b200.ptr(d_v, torch.float32),
+                                                    _b200.ptr(out), _b200.ptr(self.workspace), _b200.stream())
+        return out
+
+
 class LearnerStep:
     """
     One iteration of the reference's learner loop (rnad.py:495-526: rollout, __learn, Adam, target-net average) as a

@@ -21,3 +21,5 @@ def timeit(fn, n=20):
     return s.elapsed_time(e) / n * 1e3
 print("forward  %.1f us" % timeit(lambda: fl.forward(obs, *nets)))
 print("backward %.1f us" % timeit(lambda: fl.backward(obs, nets[0], d_logit, d_v)))
+d_logit_u = torch.randn(T, B, a, device=dev); d_v_u = torch.randn(T, B, device=dev)
+print("backward_split %.1f us" % timeit(lambda: fl.backward_split(obs, nets[0], d_logit_u, d_v_u)))

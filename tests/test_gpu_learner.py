@@ -392,6 +392,61 @@ def test_fused_learner_backward_vs_autograd(a, T, B):
         assert torch.equal(again, first)
 
 
+@pytest.mark.parametrize("a,T,B", [(2, 4, 300), (3, 8, 4099), (3, 3, 130), (4, 5, 2048)])
+def test_fused_learner_backward_split_vs_autograd(a, T, B):
+    """
+    The learner step's backward (`rnad_learner_backward_split`): one UNNORMALISED gradient per player, rows of even t
+    player 0's, odd t player 1's.  max_actions <= 3 runs on the fp16-operand engine (csrc/learner_bwd_f16.cu),
+    max_actions = 4 on the tf32 one; the reference is float64 autograd through the engine's own first-layer numerics
+    (operands rounded like the engine's, straight-through), per player.
+    """
+    import learn.fused as fused
+    from nn.net import MLP
+
+    nets, weights = _four_nets(a, 5 + a)
+    obs = _random_observations(a, T, B, 29)
+    gen = torch.Generator().manual_seed(11)
+    d_logit = torch.randn(T, B, a, generator=gen)          # unnormalised: O(1), as rnad_learner_targets leaves them
+    d_v = torch.randn(T, B, generator=gen)
+    d_logit[:, ::3] = 0                                    # invalid steps carry exact zeros
+    d_v[:, ::3] = 0
+    f16 = a <= 3
+    rnd = orc.f16_rn if f16 else orc.tf32_rna
+    bias_k = orc.tc_bias_in_k(a, 16 if f16 else 8)
+    x = rnd(obs.reshape(T, B, -1)).double()
+    fl = fused.FusedLearner(nets[0])
+    got = cpu(fl.backward_split(obs.to(DEV), nets[0], d_logit.to(DEV), d_v.to(DEV))).double()
+    names = [n for n, _ in MLP(a, 256).named_parameters()]
+    for player in range(2):
+        w64 = {k: v.double().requires_grad_(True) for k, v in weights[0].items()}
+
+        def trunk(name):
+            w0 = w64[name + "_fc0.weight"]
+            w0r = w0 + (rnd(weights[0][name + "_fc0.weight"]).double() - w0).detach()
+            b0 = w64[name + "_fc0.bias"]
+            b0r = b0 + (rnd(weights[0][name + "_fc0.bias"]).double() - b0).detach() if bias_k else b0
+            h = torch.relu(x[player::2] @ w0r.T + b0r)
+            return h @ w64[name + "_fc1.weight"].T + w64[name + "_fc1.bias"]
+
+        v64, logit64 = trunk("value"), trunk("policy")
+        torch.autograd.backward([logit64, v64], [d_logit[player::2].double(), d_v[player::2].unsqueeze(-1).double()])
+        offset = 0
+        for name in names:
+            want = w64[name].grad
+            mine = got[player, offset: offset + want.numel()].view_as(want)
+            offset += want.numel()
+            rel = (mine - want).norm() / want.norm().clamp_min(1e-30)
+            # fp16 / tf32 operands carry 11 bits: 2.4e-4 per rounded factor; the relu masks agree by construction
+            assert rel < 2e-3, f"player {player} {name}: relative gradient error vs the engine-aware reference {rel:.2e}"
+    first = fl.backward_split(obs.to(DEV), nets[0], d_logit.to(DEV), d_v.to(DEV)).clone()
+    for _ in range(25):      # deterministic, and no ordering race between the warp roles
+        assert torch.equal(fl.backward_split(obs.to(DEV), nets[0], d_logit.to(DEV), d_v.to(DEV)), first)
+    # large signals saturate at fp16's largest finite value instead of turning into Inf / NaN
+    if f16:
+        big = fl.backward_split(obs.to(DEV), nets[0], (d_logit * 1e6).to(DEV), (d_v * 1e6).to(DEV))
+        assert bool(torch.isfinite(big).all())
+
+
 def test_rnad_learn_fused_engine_tracks_reference(golden):
     """Default (fused, tf32) engine on the reference's episodes: gradients within tf32 noise of the reference's."""
     from learn.rnad import RNaD

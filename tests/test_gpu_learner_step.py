@@ -205,7 +205,13 @@ def test_graph_replay_equals_eager_equals_stepwise_path():
         assert (p_g - p_s).norm() < 0.03 * moved, ((p_g - p_s).norm().item(), moved.item())
         assert_params_track(p_g, p_s, steps=i + 1)
         close(t_g, t_s, rtol=0, atol=3e-5 + 2e-5 * (i + 1))    # (the target net averages 1 % of the parameters in per step)
-        close(l_g, l_s, rtol=3e-3, atol=1e-3)      # (the NeuRD loss is a small difference of O(1) terms: -0.01 .. -0.08 here)
+        # losses: the same games -> the same sums to rounding; once the nets differ by tf32 / fp16 noise a uniform falls
+        # on the other side of a cumulative probability somewhere, the batches are different samples of 4,096 games,
+        # and the losses agree to sampling noise only (the NeuRD loss is a small difference of O(1) terms: -0.01 .. -0.08)
+        if torch.equal(idx_s, idx_g):
+            close(l_g, l_s, rtol=3e-3, atol=1e-3)
+        else:
+            close(l_g, l_s, rtol=0, atol=3e-2)
     # Adam's step count lives on the device; a checkpoint sees it
     trials["graph"]._step.sync_optimizer(trials["graph"])
     assert float(trials["graph"].optimizer.state[next(trials["graph"].net.parameters())]["step"]) == 5.0
