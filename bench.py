@@ -383,7 +383,7 @@ def run_native(args):
         sustained = {"launches": n_sus, "seconds": sus_ms / 1e3, "ms_per_step": sus_ms / n_sus, "clocks": sus_sampler.stop()}
 
     # ---- e2e: the public API with host buffers: every step the actor's weights arrive from pinned HOST memory and the
-    # per-game returns go back to pinned host memory; environment.episode.SelfPlay replays copy -> rollout -> copy as
+    # per-game returns go back to pinned host memory; environment.episode.SelfPlay replays copy -> rollout [-> copy] as
     # one CUDA graph (timed region = control launch + replay + stream synchronize)
     flat_host = torch.cat([v.flatten() for v in weights_cpu.values()]).pin_memory()
     returns_host = torch.empty(batch, dtype=torch.float32).pin_memory()
@@ -513,8 +513,8 @@ def run_native(args):
                     "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
                     "ms_per_step": e2e_ms / args.steps,
                     "what": "environment.episode.SelfPlay.play(): net weights copied from pinned host memory, rollout, "
-                            "per-game returns copied back to pinned host memory - one CUDA graph per batch - then a "
-                            "stream synchronize"},
+                            "per-game returns " + ("written by the kernel straight into" if play.direct_returns else "copied back to") +
+                            " pinned host memory - one CUDA graph per batch - then a stream synchronize"},
             "gpu_launches": args.steps * runner.launches_per_step,
             "roofline": {"bound": "hbm", "achieved": achieved_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                          "frac": achieved_gbs / peaks["hbm_gbs"],

@@ -309,6 +309,11 @@ RNAD_API int rnad_step_control(rnad_step_ctrl* ctrl, uint64_t seed, float alpha,
 /* the next rollout seed WITHOUT the host: state += 0x9E3779B97F4A7C15, seed = splitmix64's mix of the state >> 2 (a
  * one-thread kernel; inside a captured graph every replay plays a new, host-predictable seed) */
 RNAD_API int rnad_step_advance(rnad_step_ctrl* ctrl, void* stream);
+/* rnad_step_advance and, in the same kernel, the step's fresh inputs: n floats from src to dst (both 16-byte aligned).
+ * src may be PINNED HOST memory (device-readable at the same address under unified addressing): the actor weights of a
+ * self-play batch then arrive with one round trip over PCIe and without a copy node of their own
+ * (environment.episode.SelfPlay; the reference's analogue is net.to(device) before Episodes.generate, rnad.py:502). */
+RNAD_API int rnad_step_advance_fetch(rnad_step_ctrl* ctrl, const float* src, float* dst, int64_t n, void* stream);
 
 /* rnad_learner_tail: [sum over ranks of (G_0 | G_1 | N_0, N_1 | loss numerators) over NVLink peer memory] ->
  * g = G_0 / N_0 + G_1 / N_1 -> clip_grad_norm_(grad_clip) (rnad.py:456) -> Adam (torch.optim.Adam semantics without

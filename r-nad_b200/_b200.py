@@ -31,7 +31,7 @@ EXPORTS = (
     "rnad_learner_targets", "rnad_learner_mlp_supported", "rnad_learner_mlp_workspace_bytes",
     "rnad_learner_param_count", "rnad_learner_forward", "rnad_learner_backward", "rnad_learner_backward_split",
     "rnad_learner_pack", "rnad_learner_forward_prepacked", "rnad_learner_backward_split_prepacked",
-    "rnad_step_control", "rnad_step_advance", "rnad_learner_tail", "rnad_xchg_bytes", "rnad_xchg_create", "rnad_xchg_open", "rnad_xchg_close",
+    "rnad_step_control", "rnad_step_advance", "rnad_step_advance_fetch", "rnad_learner_tail", "rnad_xchg_bytes", "rnad_xchg_create", "rnad_xchg_open", "rnad_xchg_close",
     "rnad_xchg_destroy",
 )
 MAX_PEERS = 16
@@ -140,6 +140,7 @@ def lib():
     L.rnad_learner_pack.argtypes = [c_int] + [POINTER(MlpWeights)] * 4 + [c_int, c_void_p, c_void_p]
     L.rnad_step_control.argtypes = [c_void_p, c_uint64, c_float, c_void_p]
     L.rnad_step_advance.argtypes = [c_void_p, c_void_p]
+    L.rnad_step_advance_fetch.argtypes = [c_void_p, c_void_p, c_void_p, c_int64, c_void_p]
     L.rnad_learner_tail.argtypes = [POINTER(TailArgs), c_void_p]
     L.rnad_xchg_bytes.restype = c_int64
     L.rnad_xchg_bytes.argtypes = [c_int, c_int]

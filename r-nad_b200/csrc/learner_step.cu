@@ -68,6 +68,27 @@ __global__ void step_advance_kernel(rnad_step_ctrl* ctrl) {
     ctrl->seed = (z ^ (z >> 31)) >> 2;
 }
 
+// The same, and the step's inputs with it: n floats from `src` - pinned host memory, which unified addressing makes
+// device-readable at the same address - to `dst`, one 16-byte load per thread (a single round trip over PCIe instead
+// of a copy node of its own in front of a one-thread kernel).
+__global__ void step_advance_fetch_kernel(rnad_step_ctrl* ctrl, const float* __restrict__ src, float* __restrict__ dst, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (4 * i + 3 < n) {
+        reinterpret_cast<float4*>(dst)[i] = __ldcv(reinterpret_cast<const float4*>(src) + i);
+    } else {
+        for (int k = 4 * i; k < n; ++k) dst[k] = __ldcv(src + k);
+    }
+    if (i == 0) {
+        uint64_t state = ((uint64_t)ctrl->seed_state[1] << 32 | ctrl->seed_state[0]) + 0x9E3779B97F4A7C15ull;
+        ctrl->seed_state[0] = (uint32_t)state;
+        ctrl->seed_state[1] = (uint32_t)(state >> 32);
+        uint64_t z = state;
+        z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+        z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+        ctrl->seed = (z ^ (z >> 31)) >> 2;
+    }
+}
+
 // The tail runs as ONE thread-block cluster of kTailCtas CTAs (8192 threads: one or two parameters per thread, so
 // every pass is a single round of independent loads instead of a latency-bound loop) synchronised by the hardware
 // cluster barrier; the squared gradient norm is reduced per CTA and the CTAs' partial sums are read by every CTA
@@ -242,6 +263,17 @@ int rnad_step_advance(rnad_step_ctrl* ctrl, void* stream) {
     RNAD_REQUIRE(ctrl != nullptr, "rnad_step_advance: null pointer");
     step_advance_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(ctrl);
     RNAD_CHECK_LAUNCH("step_advance_kernel");
+    return RNAD_OK;
+}
+
+int rnad_step_advance_fetch(rnad_step_ctrl* ctrl, const float* src, float* dst, int64_t n, void* stream) {
+    RNAD_REQUIRE(ctrl != nullptr && src != nullptr && dst != nullptr, "rnad_step_advance_fetch: null pointer");
+    RNAD_REQUIRE(n >= 1 && n <= (1 << 30), "rnad_step_advance_fetch: %lld floats", (long long)n);
+    RNAD_REQUIRE(((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15) == 0,
+                 "rnad_step_advance_fetch: src and dst must be 16-byte aligned");
+    const int threads = 256, quads = (int)((n + 3) / 4);
+    step_advance_fetch_kernel<<<(quads + threads - 1) / threads, threads, 0, (cudaStream_t)stream>>>(ctrl, src, dst, (int)n);
+    RNAD_CHECK_LAUNCH("step_advance_fetch_kernel");
     return RNAD_OK;
 }
 

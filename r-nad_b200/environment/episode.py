@@ -451,14 +451,14 @@ class SelfPlay:
     Repeated self-play with one actor net as a replayable unit: the trajectory lives in one static arena, the rollout
     seed in device memory, and - after one eager call - every `play()` is ONE CUDA-graph replay of
 
-        [weights_host -> the actor's flat parameter buffer]  ->  next seed  ->  rnad_rollout  ->  [returns -> returns_host]
+        [weights_host -> the actor's flat parameter buffer, next seed]  ->  rnad_rollout [-> returns_host]
 
     The seeds are a splitmix64 sequence started from one draw of torch's generator at construction and advanced on the
     device (`rnad_step_advance`); the host mirrors it, so `episodes.states.seed` names every batch's seed.
 
     `weights_host` (optional, pinned fp32, state_dict order, `sum(p.numel())` floats): fresh actor weights arrive from
     host memory before every batch (a learner elsewhere, a checkpoint).  `returns_host` (optional, pinned fp32, B
-    floats): every game's payoff for the row player is copied back after the batch.  `play()` does not synchronise;
+    floats): every game's payoff for the row player, written by the rollout kernel itself.  `play()` does not synchronise;
     the returned `Episodes` holds views of the arena, valid until the next `play()`.  (Reference: the loop around
     `Episodes.generate`, rnad.py:502-505 / episode.py:175-230.)
     """
@@ -498,15 +498,23 @@ class SelfPlay:
                     offset += p.numel()
             ws = int(L.rnad_rollout_workspace_bytes(packed.A, net.width, _b200.PRECISIONS[precision]))
             self.workspace = torch.empty(ws, dtype=torch.uint8, device=dev) if ws else None
-            self.returns = torch.empty(self.batch_size, dtype=torch.float32, device=dev) if returns_host is not None else None
+            # returns_host is pinned, i.e. (unified addressing) device-accessible at the same address: the kernel writes
+            # each game's return straight into it - 128-byte posted writes that ride under the rollout - instead of
+            # a device buffer plus a copy node behind the kernel (RNAD_SELFPLAY_COPY_RETURNS=1 keeps the copy, for A/B runs)
+            self.direct_returns = returns_host is not None and os.environ.get("RNAD_SELFPLAY_COPY_RETURNS") is None
+            # likewise the weights: read from pinned host memory by the kernel that advances the seed
+            # (RNAD_SELFPLAY_COPY_WEIGHTS=1: a copy node in front of it instead)
+            self.direct_weights = os.environ.get("RNAD_SELFPLAY_COPY_WEIGHTS") is None
+            self.returns = (torch.empty(self.batch_size, dtype=torch.float32, device=dev)
+                            if returns_host is not None and not self.direct_returns else None)
         if weights_host is not None and (not weights_host.is_pinned() or weights_host.numel() != n):
             raise _b200.RnadError(f"weights_host must be a pinned fp32 tensor of {n} elements")
         if returns_host is not None and (not returns_host.is_pinned() or returns_host.numel() != self.batch_size):
             raise _b200.RnadError(f"returns_host must be a pinned fp32 tensor of {self.batch_size} elements")
         self._w = _b200.mlp_weights(net, dev)
         self._traj = _b200.Trajectory(*self.arena.pointers())
-        if self.returns is not None:
-            self._traj.returns = self.returns.data_ptr()     # the kernel sums each game's rewards itself
+        if returns_host is not None:                           # the kernel sums each game's rewards itself
+            self._traj.returns = returns_host.data_ptr() if self.direct_returns else self.returns.data_ptr()
         self.episodes = Episodes(tree, self.batch_size)
         self.episodes.finished = True
         self.episodes.precision = precision
@@ -514,14 +522,18 @@ class SelfPlay:
 
     def _enqueue(self):
         L, p = _b200.lib(), self.packed
-        if self.weights_host is not None:
-            self.flat.copy_(self.weights_host, non_blocking=True)
-        L.rnad_step_advance(self.ctrl.data_ptr(), _b200.stream())
+        if self.weights_host is not None and self.direct_weights:
+            L.rnad_step_advance_fetch(self.ctrl.data_ptr(), self.weights_host.data_ptr(), self.flat.data_ptr(),
+                                      self.flat.numel(), _b200.stream())
+        else:
+            if self.weights_host is not None:
+                self.flat.copy_(self.weights_host, non_blocking=True)
+            L.rnad_step_advance(self.ctrl.data_ptr(), _b200.stream())
         L.rnad_rollout(_b200.ptr(p.ev_tab), _b200.ptr(p.tr_tab), p.A, p.C, ctypes.byref(self._w), self.batch_size,
                        self.t_max, 0, self.ctrl.data_ptr() + _b200.StepCtrl.seed.offset, self.episodes.states.game_offset,
                        None, _b200.PRECISIONS[self.precision], ctypes.byref(self._traj), self.arena.stats.data_ptr(),
                        _b200.ptr(self.workspace), _b200.stream())
-        if self.returns_host is not None:
+        if self.returns is not None:
             self.returns_host.copy_(self.returns, non_blocking=True)
 
     def _next_seed(self) -> int:
