@@ -415,8 +415,8 @@ def run_native(args):
     def learner_step():
         trial.learner_step(alpha=0.5)
         trial.total_steps += 1
-        loss_host.copy_(trial.last_losses, non_blocking=True)
         torch.cuda.current_stream().synchronize()
+        loss_host.copy_(trial.last_losses_host[:2])       # (pinned host memory the tail kernel wrote: a host-side read)
 
     learner_steps = max(args.learner_steps, args.steps)
     learner_ms, _ = timed_steps(learner_step, learner_steps, max(3, args.warmup), flush, barrier)

@@ -338,6 +338,9 @@ typedef struct rnad_tail_args {
     float lr, beta1, beta2, eps, grad_clip, gamma_averaging, one_minus_gamma_averaging;
     int world, rank;
     float* xchg[RNAD_MAX_PEERS];
+    float* losses_host;           /* optional: the same four floats once more, e.g. into PINNED HOST memory (device-
+                                   * writable at the same address under unified addressing) - a host that wants the
+                                   * losses every step then needs a stream synchronize and no copy */
 } rnad_tail_args;
 
 RNAD_API int rnad_learner_tail(const rnad_tail_args* args /* host struct */, void* stream);

@@ -84,7 +84,7 @@ class TailArgs(Structure):
                                            "exp_avg_sq", "flat_grad", "losses", "ctrl")]
                 + [(n, c_float) for n in ("lr", "beta1", "beta2", "eps", "grad_clip", "gamma_averaging",
                                           "one_minus_gamma_averaging")]
-                + [("world", c_int), ("rank", c_int), ("xchg", c_void_p * MAX_PEERS)])
+                + [("world", c_int), ("rank", c_int), ("xchg", c_void_p * MAX_PEERS), ("losses_host", c_void_p)])
 
 
 _lib = None

@@ -240,6 +240,12 @@ __global__ void __cluster_dims__(kTailCtas, 1, 1) __launch_bounds__(kTailThreads
         a.losses[1] = -(s_stats[6] / n0 + s_stats[7] / n1);
         a.losses[2] = norm;
         a.losses[3] = (float)a.ctrl->error;
+        if (a.losses_host != nullptr) {
+            a.losses_host[0] = a.losses[0];
+            a.losses_host[1] = a.losses[1];
+            a.losses_host[2] = norm;
+            a.losses_host[3] = a.losses[3];
+        }
         a.ctrl->seq = seq + 1u;
         a.ctrl->adam_step = s_adam[2];
     }

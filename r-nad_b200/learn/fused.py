@@ -155,6 +155,9 @@ class LearnerStep:
             self.d_v = torch.empty((self.t, self.b), dtype=torch.float32, device=dev)
             self.loss_sums = torch.zeros(4, dtype=torch.float32, device=dev)
             self.losses = torch.zeros(4, dtype=torch.float32, device=dev)      # loss_v, loss_nerd, |grad|, error word
+            # the same four floats in pinned host memory, written by the tail kernel itself: current after a stream
+            # synchronize, no copy (RNaD.last_losses_host)
+            self.losses_host = torch.zeros(4, dtype=torch.float32).pin_memory()
             self.player_grads = torch.zeros(2 * n, dtype=torch.float32, device=dev)
             self.flat_grad = torch.zeros(n, dtype=torch.float32, device=dev)
             self.flat = {k: torch.zeros(n, dtype=torch.float32, device=dev)
@@ -186,6 +189,27 @@ class LearnerStep:
                 float(trial.grad_clip), float(trial.gamma_averaging), float(trial.eta), float(trial.c_bar),
                 float(trial.roh_bar), float(trial.vtrace_gamma), float(trial.epsilon_threshold), int(trial.n_discrete),
                 float(trial.neurd_clip), float(trial.beta), float(trial.value_weight), float(trial.neurd_weight))
+
+    @staticmethod
+    def quick_key_of(trial):
+        """
+        A cheap fingerprint of the same things (object identities, scalars, one parameter address per net) that
+        does not walk the modules: RNaD compares it every step and runs `applicable` / `key_of` only when it changed.
+        """
+        opt = trial.optimizer
+        group = opt.param_groups[0] if getattr(opt, "param_groups", None) else {}
+        nets = (trial.net, trial.net_target, trial.net_reg, trial.net_reg_)
+        first = tuple(getattr(getattr(x, "value_fc0", None), "weight", None) for x in nets)
+        return (id(opt), type(opt), len(getattr(opt, "param_groups", ())), tuple(id(x) for x in nets),
+                tuple((id(w), w.data_ptr()) if w is not None else None for w in first),
+                id(trial.tree), id(getattr(trial.tree, "_packed", None)), trial.tree.index_tensor.data_ptr(),
+                int(trial.batch_size), trial.step_engine, trial.learner_engine,
+                os.environ.get("RNAD_LEARNER_ENGINE"), trial.n_batches_per_buffer, trial.buffer_mod,
+                group.get("lr"), group.get("betas"), group.get("eps"), group.get("amsgrad"), group.get("weight_decay"),
+                group.get("maximize"), group.get("capturable"), group.get("fused"), len(group.get("params", ())),
+                trial.grad_clip, trial.gamma_averaging, trial.eta, trial.c_bar, trial.roh_bar, trial.vtrace_gamma,
+                trial.epsilon_threshold, trial.n_discrete, trial.neurd_clip, trial.beta, trial.value_weight,
+                trial.neurd_weight)
 
     @staticmethod
     def applicable(trial) -> bool:
@@ -281,6 +305,7 @@ class LearnerStep:
         tail.params, tail.target_params = self.flat["params"].data_ptr(), self.flat["target"].data_ptr()
         tail.exp_avg, tail.exp_avg_sq = self.flat["exp_avg"].data_ptr(), self.flat["exp_avg_sq"].data_ptr()
         tail.flat_grad, tail.losses, tail.ctrl = self.flat_grad.data_ptr(), self.losses.data_ptr(), ctrl
+        tail.losses_host = self.losses_host.data_ptr()
         tail.lr, (tail.beta1, tail.beta2), tail.eps = float(group["lr"]), (float(b) for b in group["betas"]), float(group["eps"])
         tail.grad_clip, tail.gamma_averaging = float(trial.grad_clip), float(trial.gamma_averaging)
         tail.one_minus_gamma_averaging = 1 - trial.gamma_averaging      # the reference's python-float (1 - gamma)

@@ -168,6 +168,7 @@ class RNaD:
         self.net_reg_: nn.Module = None
         self.optimizer = None
         self.last_losses = None      # device tensor [loss_v, loss_nerd] of the latest step
+        self.last_losses_host = None # (step engine) pinned host tensor [loss_v, loss_nerd, |grad|, error word], current after a synchronize
         self.nashconv_history = []   # (total_steps, NashConv of the target net)
         self.learner_engine = None   # None = auto: "fused" tensor-core kernels where supported, else "torch"
         self._fused = None
@@ -357,6 +358,7 @@ class RNaD:
             beta=self.beta, value_weight=self.value_weight, neurd_weight=self.neurd_weight,
             global_counts=global_counts)
         self.last_losses = out.losses
+        self.last_losses_host = None
         if engine == "fused":
             flat = self._fused.backward(observations, self.net, out.d_logit, out.d_v)
             dp.all_reduce_flat(flat)                      # the params' .grad are views of this buffer
@@ -413,6 +415,11 @@ class RNaD:
         """The LearnerStep serving the current nets / optimizer / hyper-parameters, or None if it does not apply."""
         if self.step_engine in ("0", "off", "none") or self.learner_engine == "torch":
             return None
+        # fast path (every step of a run): the same objects and scalars as at the last full check, and the nets'
+        # first parameters still where the engine's flat buffers put them - without walking the modules
+        quick = fused.LearnerStep.quick_key_of(self)
+        if self._step is not None and quick == self.__dict__.get("_step_quick_key"):
+            return self._step
         if os.environ.get("RNAD_LEARNER_ENGINE") == "torch" or not fused.LearnerStep.applicable(self):
             return None
         if self._step is not None and self._step.trial_key != fused.LearnerStep.key_of(self):
@@ -427,6 +434,7 @@ class RNaD:
                 self.step_engine = "off"
                 return None
             self._tail = None
+        self._step_quick_key = fused.LearnerStep.quick_key_of(self)      # (after the engine adopted the parameters)
         return self._step
 
     def learner_step(self, alpha: float, buffer: "episode.Buffer" = None, log: dict = None):
@@ -439,6 +447,7 @@ class RNaD:
             episodes = step.run(alpha)
             buffer.append(episodes)
             self.last_losses = step.losses[:2]
+            self.last_losses_host = step.losses_host          # pinned; current after a stream synchronize
             return episodes
         if self._step is not None:
             self._step.sync_optimizer(self)          # this step runs torch's optimizer on the shared flat state

@@ -191,6 +191,8 @@ def test_graph_replay_equals_eager_equals_stepwise_path():
             hist[e].append((flat(trial.net).clone(), flat(trial.net_target).clone(), trial.last_losses.clone(),
                             ep.full("indices").clone(), ep.full("policy").clone()))
     assert trials["graph"]._step.graph is not None and trials["eager"]._step.graph is None and trials["off"]._step is None
+    torch.cuda.synchronize()         # the tail kernel also writes the losses into pinned host memory
+    assert torch.equal(trials["graph"].last_losses_host[:2], trials["graph"].last_losses.cpu())
     for i in range(5):
         for x, y in zip(hist["graph"][i], hist["eager"][i]):
             assert torch.equal(x, y), f"step {i}: graph replay and eager launch differ"
