@@ -348,23 +348,37 @@ __global__ void __launch_bounds__(kThreads, 1) learner_fwd_tc2_kernel(const floa
         }
         uint32_t mask_prev = 0;
         int64_t row_prev = -1;
+        // The observation row of tile k + 1 is fetched while tile k's row is packed and tile k - 1's heads are computed:
+        // the row warps' loop used to be [HBM round trip of tile k] -> [heads of tile k - 1], ~2,400 cycles per tile that
+        // the six items of a three-trunk launch (~2,300 cycles of tensor-core work) could not hide.
+        float xn[KIN];
+        bool active_n = false;
+        int64_t rown = 0;
+        auto fetch = [&](int64_t k) {
+            const int64_t tile = (int64_t)blockIdx.x + k * gridDim.x;
+            rown = tile * kTileM + tid;
+            active_n = rown < N;
+            const float2* src = reinterpret_cast<const float2*>(obs + rown * KIN);
+#pragma unroll
+            for (int q = 0; q < KIN / 2; ++q) {
+                const float2 v = active_n ? __ldg(src + q) : make_float2(0.f, 0.f);
+                xn[2 * q] = v.x;
+                xn[2 * q + 1] = v.y;
+            }
+        };
+        if (my_tiles > 0) fetch(0);
 #pragma unroll 1
         for (int64_t k = 0; k <= my_tiles; ++k) {
             uint32_t mask_now = 0;
             int64_t row_now = -1;
             if (k < my_tiles) {
                 // ---- this tile's observation row -> tensor memory (its buffer is free: the heads of tile k - 2 are out)
-                const int64_t tile = (int64_t)blockIdx.x + k * gridDim.x;
-                const int64_t row = tile * kTileM + tid;
-                const bool active = row < N;
+                const int64_t row = rown;
+                const bool active = active_n;
                 float x[KIN];
-                const float2* src = reinterpret_cast<const float2*>(obs + row * KIN);
 #pragma unroll
-                for (int q = 0; q < KIN / 2; ++q) {
-                    const float2 v = active ? __ldg(src + q) : make_float2(0.f, 0.f);
-                    x[2 * q] = v.x;
-                    x[2 * q + 1] = v.y;
-                }
+                for (int q = 0; q < KIN; ++q) x[q] = xn[q];
+                if (k + 1 < my_tiles) fetch(k + 1);
 #pragma unroll
                 for (int a = 0; a < A; ++a) mask_now |= (x[A * A + a * A] != 0.f ? 1u : 0u) << a;   // obs[:, 1, :, 0]
                 row_now = active ? row : -1;
