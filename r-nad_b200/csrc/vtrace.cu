@@ -342,7 +342,7 @@ __global__ void __launch_bounds__(kLearnerBlock) learner_targets_kernel(rnad_lea
                     // critic (vtrace.py:377-393)
                     const float dv = sub(io.v[i], vt);
                     lv[pl] = add(lv[pl], mul(dv, dv));
-                    d_v = p.value_weight * 2.f * dv / N[pl];
+                    d_v = io.unnormalised ? p.value_weight * 2.f * dv : p.value_weight * 2.f * dv / N[pl];   // (x / 1 == x: no division)
                     // NeuRD (vtrace.py:355-367, 396-431) with importance_sampling_correction == 1
                     float pq[A], ll[A];
 #pragma unroll
@@ -544,14 +544,16 @@ __global__ void __launch_bounds__(kTbGames* kTCap, RNAD_K3_BLOCKS_X / (kTbGames 
                     const float lc = sub(logit[a], mean_logit);
                     const float force = add(lc > -p.beta ? fminf(adv, 0.f) : 0.f, lc < p.beta ? fmaxf(adv, 0.f) : 0.f);
                     term[a] = mul(mask[a], mul(lc, force));
-                    gg[a] = -mask[a] * force / N[pl];
+                    gg[a] = io.unnormalised ? -mask[a] * force : -mask[a] * force / N[pl];
                 }
                 ln[pl] = add(ln[pl], sum_lanes<A>(term));
                 float gsum = 0.f;
 #pragma unroll
                 for (int a = 0; a < A; ++a) gsum += gg[a];
 #pragma unroll
-                for (int a = 0; a < A; ++a) d_logit[a] = p.neurd_weight * (gg[a] - mask[a] * gsum / (float)A);
+                const float gmean = gsum / (float)A;      // mask is 0 or 1: (mask * gsum) / A == mask * (gsum / A), one division
+#pragma unroll
+                for (int a = 0; a < A; ++a) d_logit[a] = p.neurd_weight * (gg[a] - mask[a] * gmean);
             }
             if (active) {
                 if (io.v_target[pl]) io.v_target[pl][i] = vt;
@@ -687,11 +689,17 @@ int launch_learner(const rnad_learner_io& io, const rnad_learner_params& p, int 
     static const bool per_game = getenv("RNAD_TARGETS_PER_GAME") != nullptr;   // the previous kernel, for A/B runs
     int blocks;
     if (T <= kTbMaxT && !per_game) {
-        // one thread per (t, b) slot, one 32-game tile per block while the partial-sum buffer allows: blocks of one SM
-        // are then in different phases (loads / scan / stores) and hide each other's latencies
+        // one thread per (t, b) slot, a block = one 32-game tile at a time: the blocks of one SM are in different phases
+        // (loads / scan / stores) and hide each other's latencies
         const dim3 block(kTbGames, T);
         const int64_t n_tiles = (B + kTbGames - 1) / kTbGames;
-        blocks = (int)(n_tiles < kMaxLearnerBlocks ? n_tiles : kMaxLearnerBlocks);
+        // four resident blocks per SM walk the tiles: the per-block work (parameters, the loss partials' reduction and
+        // ticket) is paid once per ~3 tiles instead of once per tile (37.5 -> 33.8 us at cfg2; RNAD_K3_BLOCKS overrides)
+        const int64_t resident = 4 * (int64_t)sm_count();
+        blocks = (int)(n_tiles < resident ? n_tiles : resident);
+        static const char* blocks_env = getenv("RNAD_K3_BLOCKS");
+        if (blocks_env != nullptr && atoi(blocks_env) > 0)
+            blocks = (int)(n_tiles < atoi(blocks_env) ? n_tiles : (atoi(blocks_env) < kMaxLearnerBlocks ? atoi(blocks_env) : kMaxLearnerBlocks));
         unsigned int* ticket = reinterpret_cast<unsigned int*>(partials + (size_t)kMaxLearnerBlocks * 4);
         if (T <= 8) learner_targets_tb_kernel<A, 8><<<blocks, block, 0, st>>>(io, p, T, B, partials, ticket);
         else if (T <= 16) learner_targets_tb_kernel<A, 16><<<blocks, block, 0, st>>>(io, p, T, B, partials, ticket);
