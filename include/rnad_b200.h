@@ -262,7 +262,11 @@ RNAD_API int rnad_learner_backward(const float* observations, int64_t N, int A, 
                           void* workspace, void* stream);
 /* The same for a (T,B,...) trajectory, one gradient per PLAYER: rows of even t are player 0's steps, rows of odd t
  * player 1's (every row has exactly one owner and d_logit / d_v are zero elsewhere), and player_grads receives
- * 2 x rnad_learner_param_count() floats - player 0's gradient, then player 1's.  With d_logit / d_v from
+ * 2 x rnad_learner_param_count() floats - player 0's gradient, then player 1's.  For max_actions <= 3 this call
+ * runs on the fp16-operand engine (csrc/learner_bwd_f16.cu; fp32 accumulation): d_logit / d_v - and their products
+ * with the observations - are rounded to fp16 (11-bit significand like tf32; saturating at +-65504, subnormal below
+ * 6e-5), which suits UNNORMALISED gradients; pass gradients that were already divided by large step counts to
+ * rnad_learner_backward instead (tf32 operands).  With d_logit / d_v from
  * rnad_learner_targets in unnormalised mode these are the numerators G_p of
  *     d loss / d params = G_0 / N_0 + G_1 / N_1        (vtrace.py:370-374, 387-389; N_p = the players' step counts)
  * which is what data-parallel ranks exchange: the division by the GLOBAL counts happens once, after the sum over

@@ -3,19 +3,26 @@
 //   rnad_learner_forward   the four forward_batch calls of rnad.py:373-380 in ONE pass
 //                          over the trajectory: learner (logit, pi, log_pi, v), target
 //                          net (v only), regularisation nets (log_pi only) = five trunk
-//                          evaluations per step instead of eight, first layers on
-//                          tcgen05 (kind::tf32, fp32 accumulate in TMEM), the hidden
-//                          activations never leave the SM.
+//                          evaluations per step instead of eight.  The engine in use is
+//                          learner_fwd_tc2.cu (both layers on tcgen05, fp16 operands); the
+//                          kernel in THIS file (first layers tcgen05 kind::tf32, second
+//                          layers on the CUDA cores) is the first build, kept for A/B runs
+//                          (RNAD_LEARNER_FWD_V1).
 //   rnad_learner_backward  parameter gradients of the learner net given d loss/d logit
-//   (_split)               and d loss/d v (from rnad_learner_targets): recomputes the two
-//                          learner trunks TRANSPOSED on the tensor core and forms
+//   (_split)               and d loss/d v (from rnad_learner_targets).  Dispatch, newest
+//                          first:  split mode, max_actions <= 3 -> learner_bwd_f16.cu (fp16
+//                          operands, mask formulation, decoupled tensor-memory regions);
+//                          flat mode, max_actions <= 3 -> learner_bwd_tc3.cu (tf32, mask
+//                          formulation);  max_actions = 4 -> learner_bwd_tc2_kernel here:
+//                          the two trunks recomputed TRANSPOSED on the tensor core,
 //                              dW2 = g^T relu(h),  dh = (g W2) * [h > 0],  dW1 = dh^T x
-//                          with tcgen05 MMAs whose A operands (relu^T, dh^T) sit in tensor
-//                          memory and whose accumulators stay there across all tiles of a
-//                          CTA (learner_bwd_tc_kernel); a second kernel adds the per-CTA
-//                          partials in a fixed order (deterministic), per player in split
-//                          mode.  learner_bwd_kernel (reduction on the CUDA cores) is the
-//                          previous build, kept for A/B runs (RNAD_LEARNER_BWD_CUDA_CORES).
+//                          with MMAs whose A operands (relu^T, dh^T) sit in tensor memory
+//                          and whose accumulators stay there across all tiles of a CTA.
+//                          A second kernel adds the per-CTA partials in a fixed order
+//                          (deterministic), per player in split mode.  learner_bwd_tc_kernel
+//                          (two CTAs per SM) and learner_bwd_kernel (reduction on the CUDA
+//                          cores) are earlier builds kept for A/B runs (RNAD_LEARNER_BWD_V1,
+//                          RNAD_LEARNER_BWD_CUDA_CORES).
 //
 // Reference: nn/net.py:64-85 (forward_batch), learn/rnad.py:373-380, 424-425.
 // In the reference these are 8 x T small GEMMs + ~40 elementwise launches forward and
@@ -1276,8 +1283,8 @@ int launch_backward(const float* obs, int64_t N, int T_split, int64_t B_split, c
             if (mode != 2) {
                 reduce_partials_kernel<<<dim3((P::kParams * 8 + 255) / 256, 2), 256, 0, st>>>(partials, (int)blocks, P::kParams, flat_grad);
                 RNAD_CHECK_LAUNCH("reduce_partials_kernel");
-                return RNAD_OK;
             }
+            return RNAD_OK;      // (pack only: the prepacked entry point is the split one, which this engine serves)
         }
         if (mode != 1) {      // (mode as in learner_fwd_tc2.cu: 0 pack + run, 1 prepacked, 2 pack only)
             pack_bwd_tc_image_kernel<A><<<32, 256, 0, st>>>(w, image);

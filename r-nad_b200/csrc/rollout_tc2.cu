@@ -1,4 +1,5 @@
-// K2, tensor-core build with BOTH layers of the net on tcgen05 (RNAD_PREC_TF32X2):
+// K2, tensor-core build with BOTH layers of the net on tcgen05 (RNAD_PREC_F16X2, the default: fp16 operands,
+// kind::f16; RNAD_PREC_TF32X2: the same kernel with tf32 operands, kind::tf32 - see Plan<A, F16>):
 // Episodes.generate fused with MLP.forward as a persistent, warp-specialised kernel.
 //
 // One CTA per SM owns all 512 TMEM columns and keeps TWO tiles of 128 games ("sides")
@@ -11,7 +12,7 @@
 //                           (one elected lane each; warp 16 + c issues the chunks with index c: several issuers
 //                           keep the tensor core's queue fed).  A chunk is 128 hidden units of
 //                           [policy trunk | value trunk]:
-//                             MMA1  D[128 x 128]  = obs[128 x KP] (TMEM) x W1_c^T (smem)      kind::tf32, 3 slots
+//                             MMA1  D[128 x 128]  = obs[128 x KP] (TMEM) x W1_c^T (smem)      3 slots
 //                             MMA2  D2[128 x 16] += relu(D)[128 x 128] (TMEM) x W2_c^T (smem)
 //                           both with the A operand in tensor memory.  The policy trunk's chunks come
 //                           first and have their own accumulator (logits in columns 1..A): the heads
@@ -23,7 +24,7 @@
 //                           FMNMX per hidden unit is all the CUDA cores do for the net.
 //   warps 0..3 / 4..7       heads of side 0 / 1, one thread per game: read D2, masked
 //                           softmax, Philox inverse-CDF action draw, next observation ->
-//                           tensor memory (tf32).  Off the critical path (the tensor core is
+//                           tensor memory (operand format).  Off the critical path (the tensor core is
 //                           busy with the other side): trajectory record, fp32 observations
 //                           (staged per warp, stored as coalesced 16-byte words), the next
 //                           uniforms, and on row half-moves the chance draw + child gather

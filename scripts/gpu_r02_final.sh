@@ -14,7 +14,7 @@ tail -c 600 gpurun_out/bench_${TAG}_reference.json
 LIGHT="--steps 3 --warmup 3 --cpu-budget 0 --learner-steps 6 --fp32-steps 0 --sustained-s 0"
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 900 --csv \
     --log-file gpurun_out/launches_${TAG}.csv python bench.py $LIGHT > gpurun_out/ncu_bench_${TAG}.log 2>&1
-for spec in rollout_tc2:rollout learner_fwd_tc2:fwd learner_bwd_tc2:bwd learner_targets:targets learner_tail:tail; do
+for spec in rollout_tc2:rollout learner_fwd_tc2:fwd learner_bwd_f16:bwd learner_targets:targets learner_tail:tail; do
   K=${spec%%:*}; N=${spec##*:}
   timeout 400 ncu --set full --clock-control none --import-source on -k regex:$K -s 4 -c 1 \
       -o gpurun_out/prof_${N}_${TAG} -f python bench.py $LIGHT > gpurun_out/ncu_${N}_${TAG}.log 2>&1

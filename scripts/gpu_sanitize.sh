@@ -10,6 +10,6 @@ mkdir -p gpurun_out
 for tool in memcheck synccheck racecheck; do
   timeout 900 compute-sanitizer --tool $tool --error-exitcode 1 \
       python -m pytest tests/test_gpu_env_rollout.py tests/test_gpu_learner.py -m gpu -x -q \
-      -k "(width256 and 128) or (fused_learner and 300)" > gpurun_out/sanitize_${TAG}_${tool}.log 2>&1
+      -k "(width256 and 128) or (fused_learner and (300 or 130))" > gpurun_out/sanitize_${TAG}_${tool}.log 2>&1
   echo "$tool: exit $?"; tail -5 gpurun_out/sanitize_${TAG}_${tool}.log
 done
