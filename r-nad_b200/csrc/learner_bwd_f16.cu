@@ -31,7 +31,15 @@ namespace tc {
 
 namespace {
 
-constexpr int kConsumers = 512, kProducers = 128, kIssuers = 64;
+#ifndef RNAD_BWDH_SELF_ISSUE
+#define RNAD_BWDH_SELF_ISSUE 0
+#endif
+// 0: two issuer warps issue the MMAs (the default);
+// 1: the first warp of each consumer group issues the group's MMAs itself, right behind a named barrier of the group's
+//    256 threads, and the issuer warps are not launched: two mbarrier hops per stage fall off the chain, but the
+//    leader warp's own stage work now waits for its issue sequences - measured 101 vs 87 us at cfg2, not adopted
+constexpr bool kSelfIssue = RNAD_BWDH_SELF_ISSUE != 0;
+constexpr int kConsumers = 512, kProducers = 128, kIssuers = kSelfIssue ? 0 : 64;
 constexpr int kThreadsH = kConsumers + kProducers + kIssuers;
 
 template <int A>
@@ -214,44 +222,46 @@ __global__ void __launch_bounds__(kThreadsH, 1) learner_bwd_f16_kernel(const flo
     const int64_t n_stages = my_tiles * 8;
     float* dst = partials + (int64_t)cta * S::kParams;
 
+    // region / hidden half / stage parity this warp serves: issuer warp b, consumer group b (producers: unused)
+    const int b = tid >= kConsumers + kProducers ? warp - (kConsumers + kProducers) / 32 : (warp >> 3) & 1;
+    // MMA issue (the issuer warps, or with kSelfIssue the first warp of each consumer group), for region / hidden half b.
+    // Everything an MMA takes is computed BEFORE the barrier wait it follows and pinned there (pin()): after the wait
+    // only the register -> uniform-register moves and the tcgen05.mma themselves remain - the descriptor arithmetic
+    // (a dependent scalar chain of ~60 instructions) used to sit between the arrival and the first MMA of both groups.
+    const uint32_t n_st = (uint32_t)n_stages;
+    const uint32_t tile0 = smem_u32(smem + P::kTile);
+    const uint32_t d_h = tmem_base + P::kColH + (uint32_t)b * 64, rm = tmem_base + P::kColRM + (uint32_t)b * 64;
+    const uint64_t w1_desc = tcp::desc_sbo(smem_u32(smem) + b * (128 / 8) * P::kSbo1, P::kSbo1);
+    const uint64_t x_desc = tcp::desc_sbo(tile0 + P::kX, P::kSbo1);
+    const uint64_t g_desc = desc_lbo_sbo(tile0, P::kLboK, P::kSboN);
+    auto pin32 = [](uint32_t& v) { asm volatile("" : "+r"(v)::"memory"); };
+    auto pin64 = [](uint64_t& v) { asm volatile("" : "+l"(v)::"memory"); };
+    uint32_t seen_full = 0xffffffffu;
+    auto need_tile = [&](uint32_t k) {      // (whole warp) the producers have written tile k's operands
+        if (k != seen_full) {
+            tcp::mbar_wait_c(bar_full((int)(k & 1)), (k >> 1) & 1u);
+            seen_full = k;
+        }
+    };
+    // first-layer operands of stage s: A = W1 of (trunk, hidden half b), B = the stage's 64 observation rows
+    auto recompute_ops = [&](uint32_t s, uint64_t& a, uint64_t& bb) {
+        const uint32_t trunk = (s >> 1) & 1u, rh = (s >> 2) & 1u, kb = (s >> 3) & 1u;
+        a = w1_desc + (uint64_t)((trunk * P::kTrunkBytes) >> 4);
+        bb = x_desc + (uint64_t)((kb * P::kTileBytes + rh * (64 / 8) * P::kSbo1) >> 4);
+        pin64(a);
+        pin64(bb);
+    };
+    auto recompute = [&](uint64_t a, uint64_t bb) {     // H^T of a stage into H region b (elected lane)
+#pragma unroll
+        for (int ks = 0; ks < KP / 16; ++ks) mma_ss_f16(d_h, a + (uint64_t)(ks * 16), bb + (uint64_t)(ks * 16), idesc_f16(64), ks > 0);
+        mma_commit(bar_h(b));
+    };
     if (tid >= kConsumers + kProducers) {
         // ------------------------------------------------------------ issuers: warp b issues the stages with s & 1 == b
         // stage s: tile k = s >> 3, hidden half = s & 1 (== region == issuer == consumer group), trunk = (s >> 1) & 1,
         // row half = (s >> 2) & 1
-        // Everything an MMA takes is computed BEFORE the barrier wait it follows and pinned there (pin()): after the wait
-        // only the register -> uniform-register moves and the tcgen05.mma themselves remain - the descriptor arithmetic
-        // (a dependent scalar chain of ~60 instructions) used to sit between the arrival and the first MMA of both groups.
-        const int b = warp - (kConsumers + kProducers) / 32;
-        tcp::mbar_wait_c(bar_img, 0);
-        const uint32_t n_st = (uint32_t)n_stages;
-        const uint32_t tile0 = smem_u32(smem + P::kTile);
-        const uint32_t d_h = tmem_base + P::kColH + (uint32_t)b * 64, rm = tmem_base + P::kColRM + (uint32_t)b * 64;
-        const uint64_t w1_desc = tcp::desc_sbo(smem_u32(smem) + b * (128 / 8) * P::kSbo1, P::kSbo1);
-        const uint64_t x_desc = tcp::desc_sbo(tile0 + P::kX, P::kSbo1);
-        const uint64_t g_desc = desc_lbo_sbo(tile0, P::kLboK, P::kSboN);
-        auto pin32 = [](uint32_t& v) { asm volatile("" : "+r"(v)::"memory"); };
-        auto pin64 = [](uint64_t& v) { asm volatile("" : "+l"(v)::"memory"); };
-        uint32_t seen_full = 0xffffffffu;
-        auto need_tile = [&](uint32_t k) {      // (whole warp) the producers have written tile k's operands
-            if (k != seen_full) {
-                tcp::mbar_wait_c(bar_full((int)(k & 1)), (k >> 1) & 1u);
-                seen_full = k;
-            }
-        };
-        // first-layer operands of stage s: A = W1 of (trunk, hidden half b), B = the stage's 64 observation rows
-        auto recompute_ops = [&](uint32_t s, uint64_t& a, uint64_t& bb) {
-            const uint32_t trunk = (s >> 1) & 1u, rh = (s >> 2) & 1u, kb = (s >> 3) & 1u;
-            a = w1_desc + (uint64_t)((trunk * P::kTrunkBytes) >> 4);
-            bb = x_desc + (uint64_t)((kb * P::kTileBytes + rh * (64 / 8) * P::kSbo1) >> 4);
-            pin64(a);
-            pin64(bb);
-        };
-        auto recompute = [&](uint64_t a, uint64_t bb) {     // H^T of a stage into H region b (elected lane)
-#pragma unroll
-            for (int ks = 0; ks < KP / 16; ++ks) mma_ss_f16(d_h, a + (uint64_t)(ks * 16), bb + (uint64_t)(ks * 16), idesc_f16(64), ks > 0);
-            mma_commit(bar_h(b));
-        };
-        if ((uint32_t)b < n_st) {               // fill the pipeline: stage b
+        if (!kSelfIssue) tcp::mbar_wait_c(bar_img, 0);
+        if (!kSelfIssue && (uint32_t)b < n_st) {               // fill the pipeline: stage b
             uint64_t a, bb;
             recompute_ops((uint32_t)b, a, bb);
             need_tile(0);
@@ -260,7 +270,7 @@ __global__ void __launch_bounds__(kThreadsH, 1) learner_bwd_f16_kernel(const flo
             __syncwarp();
         }
 #pragma unroll 1
-        for (uint32_t s = (uint32_t)b; s < n_st; s += 2) {
+        for (uint32_t s = (uint32_t)b; !kSelfIssue && s < n_st; s += 2) {
             const uint32_t trunk = (s >> 1) & 1u, rh = (s >> 2) & 1u, kb = (s >> 3) & 1u;
             const uint32_t par = (s >> 1) & 1u;
             const bool more = s + 2 < n_st;
@@ -395,7 +405,18 @@ __global__ void __launch_bounds__(kThreadsH, 1) learner_bwd_f16_kernel(const flo
     } else {
         // ------------------------------------------------------------ consumers: thread = hidden unit x 32 rows of a stage
         const int quad = warp & 3, cpart = warp >> 2;             // TMEM lane quadrant (hidden unit); (trunk, half) of the final read-out
-        const int b = warp >> 3;                                   // group == region == stage parity
+        // (b = warp >> 3: group == region == stage parity)
+        const bool leader = kSelfIssue && (warp & 7) == 0;          // issues the group's MMAs
+        auto group_sync = [&]() { asm volatile("bar.sync %0, %1;" ::"r"(1 + b), "n"(kConsumers / 2) : "memory"); };
+        tcp::mbar_wait_c(bar_img, 0);
+        if (leader && (uint32_t)b < n_st) {                        // fill the pipeline: stage b
+            uint64_t a, bb;
+            recompute_ops((uint32_t)b, a, bb);
+            need_tile(0);
+            tc_fence_after();
+            if (tcp::elect_one()) recompute(a, bb);
+            __syncwarp();
+        }
         const int cw = cpart & 1;                                  // which 32 of the stage's 64 rows
         const int j_local = quad * 32 + lane32;
         const uint32_t tmem_lane = tmem_base + ((uint32_t)(quad * 32) << 16);
@@ -403,11 +424,31 @@ __global__ void __launch_bounds__(kThreadsH, 1) learner_bwd_f16_kernel(const flo
         const uint32_t trm = tmem_lane + P::kColRM + b * 64 + cw * 16;
         const __half2 zero2 = __float2half2_rn(0.f);
 #pragma unroll 1
-        for (int64_t s = b; s < n_stages; s += 2) {
-            const int64_t i = s >> 1;
+        for (uint32_t s = (uint32_t)b; s < n_st; s += 2) {
+            const uint32_t i = s >> 1;
             const bool tr = (warp & 7) == 0;
+            const bool more = s + 2 < n_st;
+            // (leader) operands of grad(s) and recompute(s + 2), ahead of the waits
+            const uint32_t trunk = (s >> 1) & 1u, rh = (s >> 2) & 1u, kb = (s >> 3) & 1u;
+            const uint32_t t_off = kb * P::kTileBytes + rh * 8 * P::kLboK;
+            uint64_t bx = g_desc + (uint64_t)((t_off + (trunk == 0 ? P::kBXV : P::kBXP)) >> 4);
+            uint64_t bg = g_desc + (uint64_t)((t_off + P::kBG) >> 4);
+            const uint32_t nx = trunk == 0 ? P::kNXV : P::kNXP;
+            uint32_t acc1 = tmem_base + (trunk == 0 ? P::kAccV : P::kAccP) + (uint32_t)b * nx;
+            uint32_t acc2 = tmem_base + (trunk == 0 ? P::kAccV : P::kAccP) + 2 * nx + (uint32_t)b * P::kNG;
+            uint32_t idx = trunk == 0 ? idesc_f16(P::kNXV, true) : idesc_f16(P::kNXP, true);
+            const uint32_t empty_bar = bar_empty((int)kb);
+            uint64_t a2 = 0, b2 = 0;
+            if (leader) {
+                pin64(bx);
+                pin64(bg);
+                pin32(acc1);
+                pin32(acc2);
+                pin32(idx);
+                if (more) recompute_ops(s + 2, a2, b2);
+            }
             if (tr) HTR(b, s, 0);
-            tcp::mbar_wait_c(bar_h(b), (uint32_t)i & 1u);
+            tcp::mbar_wait_c(bar_h(b), i & 1u);
             tc_fence_after();
             if (tr) HTR(b, s, 1);
             uint32_t hr[32];
@@ -416,8 +457,18 @@ __global__ void __launch_bounds__(kThreadsH, 1) learner_bwd_f16_kernel(const flo
             tmem_ld_wait();
             if (tr) HTR(b, s, 2);
             tc_fence_before();
-            __syncwarp();
-            if (lane32 == 0) tcp::mbar_arrive(bar_hl(b));           // the issuer may recompute stage s + 2 into the region
+            if (kSelfIssue) {
+                group_sync();                                       // H^T of stage s is in the group's registers
+                if (leader && more) {
+                    need_tile((s + 2) >> 3);
+                    tc_fence_after();
+                    if (tcp::elect_one()) recompute(a2, b2);
+                    __syncwarp();
+                }
+            } else {
+                __syncwarp();
+                if (lane32 == 0) tcp::mbar_arrive(bar_hl(b));       // the issuer may recompute stage s + 2 into the region
+            }
             // ---- rows (2c, 2c + 1) -> one packed column: relu^T, and next to it the 0/1 mask (of the ROUNDED value: a
             // hidden unit whose positive pre-activation rounds to zero in fp16 counts as switched off in both)
             uint32_t re[16], mk[16];
@@ -428,7 +479,7 @@ __global__ void __launch_bounds__(kThreadsH, 1) learner_bwd_f16_kernel(const flo
                 mk[c] = *reinterpret_cast<const uint32_t*>(&m);
             }
             if (i >= 1) {                                           // grad(s - 2) has read the region
-                tcp::mbar_wait_c(bar_g(b), (uint32_t)(i - 1) & 1u);
+                tcp::mbar_wait_c(bar_g(b), (i - 1) & 1u);
                 tc_fence_after();
             }
             if (tr) HTR(b, s, 3);
@@ -437,14 +488,32 @@ __global__ void __launch_bounds__(kThreadsH, 1) learner_bwd_f16_kernel(const flo
             tcp::tmem_st_wait();
             if (tr) HTR(b, s, 4);
             tc_fence_before();
-            __syncwarp();
-            if (lane32 == 0) tcp::mbar_arrive(bar_c(b));
+            if (kSelfIssue) {
+                group_sync();                                       // relu^T | M^T of stage s are in RM region b
+                if (leader) {
+                    tc_fence_after();
+                    if (tcp::elect_one()) {
+#pragma unroll
+                        for (int ks = 0; ks < 4; ++ks)
+                            mma_ts_f16(acc2, rm + ks * 8, bg + (uint64_t)((ks * 2 * P::kLboK) >> 4), idesc_f16(P::kNG, true), true);
+#pragma unroll
+                        for (int ks = 0; ks < 4; ++ks)
+                            mma_ts_f16(acc1, rm + 32 + ks * 8, bx + (uint64_t)((ks * 2 * P::kLboK) >> 4), idx, true);
+                        if ((s & 7) >= 6) mma_commit(empty_bar);    // this group's last reads of the tile's shared-memory operands
+                        mma_commit(bar_g(b));
+                    }
+                    __syncwarp();
+                }
+            } else {
+                __syncwarp();
+                if (lane32 == 0) tcp::mbar_arrive(bar_c(b));
+            }
             if (tr) HTR(b, s, 5);
         }
         // every gradient MMA complete: the last commit of the group's issuer; then the groups meet
         if (n_stages >= 2) tcp::mbar_wait_c(bar_g(b), (uint32_t)((n_stages >> 1) - 1) & 1u);
         tc_fence_before();
-        asm volatile("bar.sync 1, %0;" ::"n"(kConsumers) : "memory");
+        asm volatile("bar.sync 3, %0;" ::"n"(kConsumers) : "memory");
         tc_fence_after();
 
         // ---- this CTA's partial gradient, flat in state_dict order: column part c reads (trunk, half) = (c >> 1, c & 1);

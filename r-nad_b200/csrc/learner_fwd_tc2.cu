@@ -33,6 +33,15 @@ using namespace rnad::tc;
 using namespace rnad::tcp;
 
 constexpr int kRowWarps = 4, kEpiWarps = 8, kMmaWarps = 4;   // epilogue: 4 lane quadrants x 2 halves of 64 columns
+#ifndef RNAD_FWD_EPI_GROUPS
+#define RNAD_FWD_EPI_GROUPS 2
+#endif
+// 1: all eight epilogue warps work on every stream item (a warp = a lane quadrant x 64 columns);
+// 2: two groups of four warps take alternate items (a warp = a lane quadrant x all 128 columns, in two passes) - an
+//    item's round trip (barrier wake-up, tcgen05.ld, pack, tcgen05.st, arrival) is mostly latency, and two items in
+//    the epilogue at a time hide it
+constexpr int kEpiGroups = RNAD_FWD_EPI_GROUPS;
+static_assert(kEpiGroups == 1 || kEpiGroups == 2, "one or two epilogue groups");
 constexpr int kKStep = 16, kEsz = 2;                         // K of one kind::f16 MMA, bytes per operand element
 constexpr int kMmaWarp = kRowWarps + kEpiWarps;
 constexpr int kThreads = (kMmaWarp + kMmaWarps) * 32;
@@ -197,7 +206,7 @@ __global__ void __launch_bounds__(kThreads, 1) learner_fwd_tc2_kernel(const floa
         }
         for (int k = 0; k < 2 * kSlots; ++k) {
             mbar_init(bar_d1(k), 1);
-            mbar_init(bar_relu(k), kEpiWarps);
+            mbar_init(bar_relu(k), kEpiWarps / kEpiGroups);
         }
         mbar_fence_init();
         tma_bulk_load(smem, image, P::kImageBytes, bar_img);
@@ -292,48 +301,46 @@ __global__ void __launch_bounds__(kThreads, 1) learner_fwd_tc2_kernel(const floa
     } else if (warp >= kRowWarps) {
         // ------------------------------------------------------------ relu epilogue
         const int e = warp - kRowWarps;
-        const int quad = e & 3, half = e >> 2;                 // lane quadrant, column part
-        constexpr int kCols = kChunk / (kEpiWarps / 4);
-        const uint32_t tmem_mine = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(half * kCols);
-        const float* b1 = reinterpret_cast<const float*>(smem + P::kB1) + half * kCols;
+        const int quad = e & 3;                                // lane quadrant
+        const int group = kEpiGroups == 2 ? e >> 2 : 0;        // which items (kEpiGroups == 2) ...
+        const int half0 = kEpiGroups == 2 ? 0 : e >> 2;        // ... or which 64-column half of every item
+        constexpr int kCols = 64, kPasses = kEpiGroups;        // a pass = 64 columns = one packed 32-column store
+        const uint32_t tmem_quad = tmem_base + ((uint32_t)(quad * 32) << 16);
+        const float* b1 = reinterpret_cast<const float*>(smem + P::kB1);
         if (!P::kBiasInK) mbar_wait_c(bar_img, 0);
-        int slot = 0, rb = 0, c = 0;
-        uint32_t par = 0;
 #pragma unroll 1
-        for (uint32_t i = 0; i < n_items; ++i) {
+        for (uint32_t i = (uint32_t)group; i < n_items; i += kEpiGroups) {
+            const uint32_t slot = i % kSlots, rb = i % (2 * kSlots), par = (i / (2 * kSlots)) & 1u, c = i % kItemsPerTile;
             mbar_wait_c(bar_d1(rb), par);
             tc_fence_after();
-            const uint32_t taddr = tmem_mine + slot * kChunk;
-            uint32_t r[kCols];
 #pragma unroll
-            for (int q = 0; q < kCols / 32; ++q) tmem_ld32p(taddr + q * 32, r + q * 32);
-            tmem_ld_wait();
-            if (!P::kBiasInK) {
-                const float4* bias = reinterpret_cast<const float4*>(b1 + c * kChunk);   // chunk c = trunk c/2, half c%2
+            for (int pass = 0; pass < kPasses; ++pass) {
+                const int half = half0 + pass;
+                const uint32_t taddr = tmem_quad + slot * kChunk + (uint32_t)(half * kCols);
+                uint32_t r[kCols];
 #pragma unroll
-                for (int k = 0; k < kCols / 4; ++k) {
-                    const float4 bb = bias[k];
-                    r[4 * k + 0] = __float_as_uint(__uint_as_float(r[4 * k + 0]) + bb.x);
-                    r[4 * k + 1] = __float_as_uint(__uint_as_float(r[4 * k + 1]) + bb.y);
-                    r[4 * k + 2] = __float_as_uint(__uint_as_float(r[4 * k + 2]) + bb.z);
-                    r[4 * k + 3] = __float_as_uint(__uint_as_float(r[4 * k + 3]) + bb.w);
+                for (int q = 0; q < kCols / 32; ++q) tmem_ld32p(taddr + q * 32, r + q * 32);
+                tmem_ld_wait();
+                if (!P::kBiasInK) {
+                    const float4* bias = reinterpret_cast<const float4*>(b1 + c * kChunk + half * kCols);   // chunk c = trunk c/2, half c%2
+#pragma unroll
+                    for (int k = 0; k < kCols / 4; ++k) {
+                        const float4 bb = bias[k];
+                        r[4 * k + 0] = __float_as_uint(__uint_as_float(r[4 * k + 0]) + bb.x);
+                        r[4 * k + 1] = __float_as_uint(__uint_as_float(r[4 * k + 1]) + bb.y);
+                        r[4 * k + 2] = __float_as_uint(__uint_as_float(r[4 * k + 2]) + bb.z);
+                        r[4 * k + 3] = __float_as_uint(__uint_as_float(r[4 * k + 3]) + bb.w);
+                    }
                 }
-            }
-            static_assert(kCols == 64, "one packed 32-column store per warp and item");
-            uint32_t pk[kCols / 2];              // relu, round to fp16, pack: one instruction per two hidden units
+                uint32_t pk[kCols / 2];          // relu, round to fp16, pack: one instruction per two hidden units
 #pragma unroll
-            for (int k = 0; k < kCols / 2; ++k) pk[k] = pack_relu_f16x2(__uint_as_float(r[2 * k]), __uint_as_float(r[2 * k + 1]));
-            tmem_st32(taddr, pk);
+                for (int k = 0; k < kCols / 2; ++k) pk[k] = pack_relu_f16x2(__uint_as_float(r[2 * k]), __uint_as_float(r[2 * k + 1]));
+                tmem_st32(taddr, pk);
+            }
             tmem_st_wait();
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_relu(rb));
-            slot = slot + 1 == kSlots ? 0 : slot + 1;
-            if (++rb == 2 * kSlots) {
-                rb = 0;
-                par ^= 1u;
-            }
-            if (++c == kItemsPerTile) c = 0;
         }
     } else {
         // ------------------------------------------------------------ rows: observations in, heads out
