@@ -39,6 +39,13 @@ namespace {
 //    256 threads, and the issuer warps are not launched: two mbarrier hops per stage fall off the chain, but the
 //    leader warp's own stage work now waits for its issue sequences - measured 101 vs 87 us at cfg2, not adopted
 constexpr bool kSelfIssue = RNAD_BWDH_SELF_ISSUE != 0;
+#ifndef RNAD_BWDH_NAMED_BARRIERS
+#define RNAD_BWDH_NAMED_BARRIERS 1
+#endif
+// consumers -> issuer hand-overs ("H^T loaded", "relu^T | M^T stored"): 1 = hardware named barriers shared by the group's
+// eight warps and its issuer warp (288 threads; the issuer is released ~40 cycles after the last consumer warp arrives),
+// 0 = mbarriers the issuer polls (an arrival reaches it after 150-250 cycles)
+constexpr bool kNamedBarriers = RNAD_BWDH_NAMED_BARRIERS != 0 && !kSelfIssue;
 constexpr int kConsumers = 512, kProducers = 128, kIssuers = kSelfIssue ? 0 : 64;
 constexpr int kThreadsH = kConsumers + kProducers + kIssuers;
 
@@ -234,6 +241,7 @@ __global__ void __launch_bounds__(kThreadsH, 1) learner_bwd_f16_kernel(const flo
     const uint64_t w1_desc = tcp::desc_sbo(smem_u32(smem) + b * (128 / 8) * P::kSbo1, P::kSbo1);
     const uint64_t x_desc = tcp::desc_sbo(tile0 + P::kX, P::kSbo1);
     const uint64_t g_desc = desc_lbo_sbo(tile0, P::kLboK, P::kSboN);
+    auto hand_over = [](int id) { asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(kConsumers / 2 + 32) : "memory"); };   // a consumer group + its issuer warp
     auto pin32 = [](uint32_t& v) { asm volatile("" : "+r"(v)::"memory"); };
     auto pin64 = [](uint64_t& v) { asm volatile("" : "+l"(v)::"memory"); };
     uint32_t seen_full = 0xffffffffu;
@@ -293,14 +301,20 @@ __global__ void __launch_bounds__(kThreadsH, 1) learner_bwd_f16_kernel(const flo
             HTR(2 + b, s, 0);
             if (more) {
                 need_tile((s + 2) >> 3);
-                tcp::mbar_wait_c(bar_hl(b), par);                        // H^T of stage s is in the consumers' registers
+                if (kNamedBarriers) hand_over(1 + b);
+                else tcp::mbar_wait_c(bar_hl(b), par);                   // H^T of stage s is in the consumers' registers
                 tc_fence_after();
                 HTR(2 + b, s, 1);
                 if (tcp::elect_one()) recompute(a2, b2);
                 __syncwarp();
                 HTR(2 + b, s, 2);
             }
-            tcp::mbar_wait_c(bar_c(b), par);                             // relu^T | M^T of stage s are in RM region b
+            if (kNamedBarriers) {
+                if (!more) hand_over(1 + b);                             // (every stage has both hand-overs, also the last ones)
+                hand_over(3 + b);
+            } else {
+                tcp::mbar_wait_c(bar_c(b), par);                         // relu^T | M^T of stage s are in RM region b
+            }
             tc_fence_after();
             HTR(2 + b, s, 3);
             if (tcp::elect_one()) {
@@ -465,9 +479,11 @@ __global__ void __launch_bounds__(kThreadsH, 1) learner_bwd_f16_kernel(const flo
                     if (tcp::elect_one()) recompute(a2, b2);
                     __syncwarp();
                 }
+            } else if (kNamedBarriers) {
+                hand_over(1 + b);                                   // the issuer may recompute stage s + 2 into the region
             } else {
                 __syncwarp();
-                if (lane32 == 0) tcp::mbar_arrive(bar_hl(b));       // the issuer may recompute stage s + 2 into the region
+                if (lane32 == 0) tcp::mbar_arrive(bar_hl(b));
             }
             // ---- rows (2c, 2c + 1) -> one packed column: relu^T, and next to it the 0/1 mask (of the ROUNDED value: a
             // hidden unit whose positive pre-activation rounds to zero in fp16 counts as switched off in both)
@@ -504,6 +520,8 @@ __global__ void __launch_bounds__(kThreadsH, 1) learner_bwd_f16_kernel(const flo
                     }
                     __syncwarp();
                 }
+            } else if (kNamedBarriers) {
+                hand_over(3 + b);                                   // relu^T | M^T of stage s are in RM region b
             } else {
                 __syncwarp();
                 if (lane32 == 0) tcp::mbar_arrive(bar_c(b));
@@ -513,7 +531,7 @@ __global__ void __launch_bounds__(kThreadsH, 1) learner_bwd_f16_kernel(const flo
         // every gradient MMA complete: the last commit of the group's issuer; then the groups meet
         if (n_stages >= 2) tcp::mbar_wait_c(bar_g(b), (uint32_t)((n_stages >> 1) - 1) & 1u);
         tc_fence_before();
-        asm volatile("bar.sync 3, %0;" ::"n"(kConsumers) : "memory");
+        asm volatile("bar.sync 5, %0;" ::"n"(kConsumers) : "memory");
         tc_fence_after();
 
         // ---- this CTA's partial gradient, flat in state_dict order: column part c reads (trunk, half) = (c >> 1, c & 1);
