@@ -10,17 +10,23 @@
 // gradients already divided by ~10^5 step counts (fp16 is subnormal below 6e-5), which is why the flat entry point
 // rnad_learner_backward keeps the tf32 kernels.
 //
-// What fp16 buys beyond K = 16 per MMA: relu^T and M^T of a 64-row stage are 32 + 32 packed columns, so tensor memory
-// holds H^T (fp32, written by the recompute MMA, read by the consumers) and relu^T | M^T (written by the consumers, read
-// by the gradient MMAs) in SEPARATE regions, two of each.  The issuer recomputes stage s + 2 as soon as the consumers
-// have LOADED stage s - before they have packed and stored it and before grad(s) has run - so the chain
-// "consumers -> gradient MMAs -> recompute -> consumers" of the tf32 kernels (one stage buffer serves all three) is cut:
-//     consumers (group b):  wait H(s) -> tcgen05.ld -> [H free] -> relu / mask, pack -> wait grad(s - 2) -> tcgen05.st -> [RM ready]
-//     issuer b:             wait [H free] -> recompute(s + 2) -> commit H;   wait [RM ready] -> grad(s) -> commit
-// ONE CTA per SM, 512 tensor-memory columns: H 2 x 64, relu^T | M^T 2 x 64, accumulators 256 (resident over all tiles
-// of the CTA; each touched by one issuing thread only: bit-reproducible).  Two consumer groups of eight warps (one per
-// hidden half == stage parity), two issuer warps, four producer warps that build the next tile's operands in the
-// other half of a double-buffered shared-memory region and prefetch the tile after it into registers.
+// What fp16 buys beyond K = 16 per MMA: a 64-row stage's relu^T and M^T are 32 + 32 packed columns - exactly the 64
+// columns its fp32 H^T took, so a stage lives IN PLACE in one 64-column region and tensor memory holds FOUR of them
+// next to 256 columns of accumulators.  The kernels are bound by the latency of the loop
+//     recompute(s) -> [commit] -> consumers: tcgen05.ld, relu / mask, pack, tcgen05.st -> [named barrier] -> issuer:
+//     grad(s), recompute(s + 4) -> ...
+// (~1,200 cycles of barrier hops and tensor-memory round trips, little of it work), so what counts is how many rows
+// are inside that loop at a time: four regions x 64 rows instead of the two stage buffers of the tf32 kernels.  Region
+// r = s & 3 = (trunk, hidden half) serves exactly one accumulator pair and has its own consumer group (four warps, one
+// per lane quadrant, two passes of 32 rows each: H^T columns [32p, 32p + 32) -> relu^T at [32p, 32p + 16), M^T at
+// [32p + 16, 32p + 32), so a pass only overwrites what it has loaded) and its own issuer warp (every accumulator is
+// touched by one issuing thread only, whose MMAs execute in issue order: bit-reproducible, and recompute(s + 4) may
+// follow grad(s) without a barrier).  ONE CTA per SM, 768 threads: 16 consumer warps, 4 issuer warps, 4 producer
+// warps that build the next tile's operands in the other half of a double-buffered shared-memory region and
+// prefetch the tile after it into registers.
+// [History at cfg2: tf32, S^T formulation 128 us -> tf32 mask formulation 106 -> fp16 with H^T and relu^T | M^T in
+//  separate regions, two stages in flight (recompute issued as soon as a stage is loaded) 87 -> named-barrier
+//  hand-overs 84.6 -> this cut.]
 // Reference: loss.backward() of rnad.py:425 through nn/net.py:37-51.
 #include <cuda_fp16.h>
 
@@ -31,23 +37,10 @@ namespace tc {
 
 namespace {
 
-#ifndef RNAD_BWDH_SELF_ISSUE
-#define RNAD_BWDH_SELF_ISSUE 0
-#endif
-// 0: two issuer warps issue the MMAs (the default);
-// 1: the first warp of each consumer group issues the group's MMAs itself, right behind a named barrier of the group's
-//    256 threads, and the issuer warps are not launched: two mbarrier hops per stage fall off the chain, but the
-//    leader warp's own stage work now waits for its issue sequences - measured 101 vs 87 us at cfg2, not adopted
-constexpr bool kSelfIssue = RNAD_BWDH_SELF_ISSUE != 0;
-#ifndef RNAD_BWDH_NAMED_BARRIERS
-#define RNAD_BWDH_NAMED_BARRIERS 1
-#endif
-// consumers -> issuer hand-overs ("H^T loaded", "relu^T | M^T stored"): 1 = hardware named barriers shared by the group's
-// eight warps and its issuer warp (288 threads; the issuer is released ~40 cycles after the last consumer warp arrives),
-// 0 = mbarriers the issuer polls (an arrival reaches it after 150-250 cycles)
-constexpr bool kNamedBarriers = RNAD_BWDH_NAMED_BARRIERS != 0 && !kSelfIssue;
-constexpr int kConsumers = 512, kProducers = 128, kIssuers = kSelfIssue ? 0 : 64;
+constexpr int kRegions = 4;                       // stages in flight = (trunk, hidden half) = accumulator pairs
+constexpr int kConsumers = 512, kProducers = 128, kIssuers = 32 * kRegions;
 constexpr int kThreadsH = kConsumers + kProducers + kIssuers;
+constexpr int kGroupThreads = kConsumers / kRegions + 32;   // a consumer group and its issuer warp (named barrier)
 
 template <int A>
 struct PlanH {
@@ -75,11 +68,11 @@ struct PlanH {
     static constexpr int kBG = kBXP + (kNXP / 8) * kSboN;                // [16 x 128]    d_v, d_logit[0..A)
     static constexpr int kTileBytes = round_up(kBG + (kNG / 8) * kSboN, 128);
     static constexpr int kRed = kTile + 2 * kTileBytes;
-    static constexpr int kBar = kRed + 4 * 32;                           // image, H[2], H free[2], RM ready[2], grad[2], full[2], empty[2]
-    static constexpr int kTmem = kBar + 8 * 13 + 8;
+    static constexpr int kBar = kRed + 4 * 32;                           // image, H[4], full[2], empty[2]
+    static constexpr int kTmem = kBar + 8 * 9 + 8;
     static constexpr int kBytes = kTmem + 16;
     // tensor memory
-    static constexpr int kColH = 0, kColRM = 128, kAccV = 256, kAccP = kAccV + 2 * kNXV + 2 * kNG;
+    static constexpr int kColStage = 0, kAccV = 256, kAccP = kAccV + 2 * kNXV + 2 * kNG;       // four 64-column stage regions, then the accumulators
     static constexpr bool kFits = kBiasInK && kAccP + 2 * kNXP + 2 * kNG <= 512 && kBytes <= 227 * 1024;
     __host__ __device__ static constexpr int acc(int trunk) { return trunk == 0 ? kAccV : kAccP; }
     __host__ __device__ static constexpr int nx(int trunk) { return trunk == 0 ? kNXV : kNXP; }
@@ -175,24 +168,18 @@ __global__ void __launch_bounds__(kThreadsH, 1) learner_bwd_f16_kernel(const flo
     const int tid = threadIdx.x, lane32 = tid & 31;
     const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);      // (tells the compiler that the warp index is warp-uniform)
     const uint32_t bar_img = smem_u32(smem + P::kBar);
-    auto bar_h = [&](int b) { return bar_img + 8 + 8 * b; };         // recompute into H region b complete
-    auto bar_hl = [&](int b) { return bar_img + 24 + 8 * b; };       // the consumers have loaded H region b
-    auto bar_c = [&](int b) { return bar_img + 40 + 8 * b; };        // relu^T | M^T of the stage are in RM region b
-    auto bar_g = [&](int b) { return bar_img + 56 + 8 * b; };        // the gradient MMAs reading RM region b complete
-    auto bar_full = [&](int b) { return bar_img + 72 + 8 * b; };     // tile operands of shared-memory buffer b written
-    auto bar_empty = [&](int b) { return bar_img + 88 + 8 * b; };    // every MMA reading shared-memory buffer b complete
+    auto bar_h = [&](int r) { return bar_img + 8 + 8 * r; };         // recompute into stage region r complete (and every MMA its issuer issued before)
+    auto bar_full = [&](int b) { return bar_img + 40 + 8 * b; };     // tile operands of shared-memory buffer b written
+    auto bar_empty = [&](int b) { return bar_img + 56 + 8 * b; };    // every MMA reading shared-memory buffer b complete
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + P::kTmem);
 
     if (warp == 0) tmem_alloc<512>(tmem_slot);
     if (tid == 0) {
         mbar_init(bar_img, 1);
+        for (int r = 0; r < kRegions; ++r) mbar_init(bar_h(r), 1);
         for (int b = 0; b < 2; ++b) {
-            mbar_init(bar_h(b), 1);
-            mbar_init(bar_hl(b), kConsumers / 64);
-            mbar_init(bar_c(b), kConsumers / 64);
-            mbar_init(bar_g(b), 1);
             mbar_init(bar_full(b), kProducers / 32);
-            mbar_init(bar_empty(b), 2);                              // one commit per issuer
+            mbar_init(bar_empty(b), kRegions);                       // one commit per issuer
         }
         mbar_fence_init();
         tma_bulk_load(smem, image, P::kImageBytes, bar_img);
@@ -229,106 +216,88 @@ __global__ void __launch_bounds__(kThreadsH, 1) learner_bwd_f16_kernel(const flo
     const int64_t n_stages = my_tiles * 8;
     float* dst = partials + (int64_t)cta * S::kParams;
 
-    // region / hidden half / stage parity this warp serves: issuer warp b, consumer group b (producers: unused)
-    const int b = tid >= kConsumers + kProducers ? warp - (kConsumers + kProducers) / 32 : (warp >> 3) & 1;
-    // MMA issue (the issuer warps, or with kSelfIssue the first warp of each consumer group), for region / hidden half b.
-    // Everything an MMA takes is computed BEFORE the barrier wait it follows and pinned there (pin()): after the wait
-    // only the register -> uniform-register moves and the tcgen05.mma themselves remain - the descriptor arithmetic
-    // (a dependent scalar chain of ~60 instructions) used to sit between the arrival and the first MMA of both groups.
+    // stage s of a CTA's stream: tile k = s >> 3; region r = s & 3 = (trunk << 1 | hidden half) - also the issuer warp, the
+    // consumer group and the accumulator pair of the stage; row half = (s >> 2) & 1.  A region sees the stages r, r + 4, ...
     const uint32_t n_st = (uint32_t)n_stages;
-    const uint32_t tile0 = smem_u32(smem + P::kTile);
-    const uint32_t d_h = tmem_base + P::kColH + (uint32_t)b * 64, rm = tmem_base + P::kColRM + (uint32_t)b * 64;
-    const uint64_t w1_desc = tcp::desc_sbo(smem_u32(smem) + b * (128 / 8) * P::kSbo1, P::kSbo1);
-    const uint64_t x_desc = tcp::desc_sbo(tile0 + P::kX, P::kSbo1);
-    const uint64_t g_desc = desc_lbo_sbo(tile0, P::kLboK, P::kSboN);
-    auto hand_over = [](int id) { asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(kConsumers / 2 + 32) : "memory"); };   // a consumer group + its issuer warp
-    auto pin32 = [](uint32_t& v) { asm volatile("" : "+r"(v)::"memory"); };
-    auto pin64 = [](uint64_t& v) { asm volatile("" : "+l"(v)::"memory"); };
-    uint32_t seen_full = 0xffffffffu;
-    auto need_tile = [&](uint32_t k) {      // (whole warp) the producers have written tile k's operands
-        if (k != seen_full) {
-            tcp::mbar_wait_c(bar_full((int)(k & 1)), (k >> 1) & 1u);
-            seen_full = k;
-        }
-    };
-    // first-layer operands of stage s: A = W1 of (trunk, hidden half b), B = the stage's 64 observation rows
-    auto recompute_ops = [&](uint32_t s, uint64_t& a, uint64_t& bb) {
-        const uint32_t trunk = (s >> 1) & 1u, rh = (s >> 2) & 1u, kb = (s >> 3) & 1u;
-        a = w1_desc + (uint64_t)((trunk * P::kTrunkBytes) >> 4);
-        bb = x_desc + (uint64_t)((kb * P::kTileBytes + rh * (64 / 8) * P::kSbo1) >> 4);
-        pin64(a);
-        pin64(bb);
-    };
-    auto recompute = [&](uint64_t a, uint64_t bb) {     // H^T of a stage into H region b (elected lane)
-#pragma unroll
-        for (int ks = 0; ks < KP / 16; ++ks) mma_ss_f16(d_h, a + (uint64_t)(ks * 16), bb + (uint64_t)(ks * 16), idesc_f16(64), ks > 0);
-        mma_commit(bar_h(b));
-    };
+    auto hand_over = [](int r) { asm volatile("bar.sync %0, %1;" ::"r"(1 + r), "n"(kGroupThreads) : "memory"); };   // consumer group r <-> issuer r
+
     if (tid >= kConsumers + kProducers) {
-        // ------------------------------------------------------------ issuers: warp b issues the stages with s & 1 == b
-        // stage s: tile k = s >> 3, hidden half = s & 1 (== region == issuer == consumer group), trunk = (s >> 1) & 1,
-        // row half = (s >> 2) & 1
-        if (!kSelfIssue) tcp::mbar_wait_c(bar_img, 0);
-        if (!kSelfIssue && (uint32_t)b < n_st) {               // fill the pipeline: stage b
-            uint64_t a, bb;
-            recompute_ops((uint32_t)b, a, bb);
+        // ------------------------------------------------------------ issuers: warp r issues the stages with s & 3 == r
+        // Everything an MMA takes is computed BEFORE the hand-over it follows and pinned there (pin()): behind it only the
+        // register -> uniform-register moves and the tcgen05.mma themselves remain.
+        const int r = warp - (kConsumers + kProducers) / 32;
+        const uint32_t trunk = (uint32_t)r >> 1, half = (uint32_t)r & 1u;
+        tcp::mbar_wait_c(bar_img, 0);
+        const uint32_t tile0 = smem_u32(smem + P::kTile);
+        const uint32_t region = tmem_base + P::kColStage + (uint32_t)r * 64;
+        const uint64_t w1_desc = tcp::desc_sbo(smem_u32(smem) + trunk * P::kTrunkBytes + half * (128 / 8) * P::kSbo1, P::kSbo1);
+        const uint64_t x_desc = tcp::desc_sbo(tile0 + P::kX, P::kSbo1);
+        const uint64_t g_desc = desc_lbo_sbo(tile0, P::kLboK, P::kSboN);
+        const uint32_t nx = trunk == 0 ? P::kNXV : P::kNXP;
+        const uint32_t acc1 = tmem_base + (trunk == 0 ? P::kAccV : P::kAccP) + half * nx;                 // D_w1 of (trunk, half)
+        const uint32_t acc2 = tmem_base + (trunk == 0 ? P::kAccV : P::kAccP) + 2 * nx + half * P::kNG;    // D_w2
+        const uint32_t idx = trunk == 0 ? idesc_f16(P::kNXV, true) : idesc_f16(P::kNXP, true);
+        auto pin64 = [](uint64_t& v) { asm volatile("" : "+l"(v)::"memory"); };
+        uint32_t seen_full = 0xffffffffu;
+        auto need_tile = [&](uint32_t k) {      // (whole warp) the producers have written tile k's operands
+            if (k != seen_full) {
+                tcp::mbar_wait_c(bar_full((int)(k & 1)), (k >> 1) & 1u);
+                seen_full = k;
+            }
+        };
+        // B operand of the first layers of stage s: the stage's 64 observation rows
+        auto x_of = [&](uint32_t s) {
+            const uint32_t rh = (s >> 2) & 1u, kb = (s >> 3) & 1u;
+            uint64_t d = x_desc + (uint64_t)((kb * P::kTileBytes + rh * (64 / 8) * P::kSbo1) >> 4);
+            pin64(d);
+            return d;
+        };
+        auto recompute = [&](uint64_t xb) {     // H^T of a stage into the region (elected lane)
+#pragma unroll
+            for (int ks = 0; ks < KP / 16; ++ks) mma_ss_f16(region, w1_desc + (uint64_t)(ks * 16), xb + (uint64_t)(ks * 16), idesc_f16(64), ks > 0);
+            mma_commit(bar_h(r));
+        };
+        if ((uint32_t)r < n_st) {               // fill the pipeline: stage r
+            const uint64_t xb = x_of((uint32_t)r);
             need_tile(0);
             tc_fence_after();
-            if (tcp::elect_one()) recompute(a, bb);
+            if (tcp::elect_one()) recompute(xb);
             __syncwarp();
         }
 #pragma unroll 1
-        for (uint32_t s = (uint32_t)b; !kSelfIssue && s < n_st; s += 2) {
-            const uint32_t trunk = (s >> 1) & 1u, rh = (s >> 2) & 1u, kb = (s >> 3) & 1u;
-            const uint32_t par = (s >> 1) & 1u;
-            const bool more = s + 2 < n_st;
+        for (uint32_t s = (uint32_t)r; s < n_st; s += kRegions) {
+            const uint32_t rh = (s >> 2) & 1u, kb = (s >> 3) & 1u;
+            const bool more = s + kRegions < n_st;
             // operands of grad(s): D_w2 += relu^T BG^T, D_w1 += M^T BX^T (K = the stage's 64 rows, 16 per MMA)
             const uint32_t t_off = kb * P::kTileBytes + rh * 8 * P::kLboK;
             uint64_t bx = g_desc + (uint64_t)((t_off + (trunk == 0 ? P::kBXV : P::kBXP)) >> 4);
             uint64_t bg = g_desc + (uint64_t)((t_off + P::kBG) >> 4);
-            const uint32_t nx = trunk == 0 ? P::kNXV : P::kNXP;
-            uint32_t acc1 = tmem_base + (trunk == 0 ? P::kAccV : P::kAccP) + (uint32_t)b * nx;
-            uint32_t acc2 = tmem_base + (trunk == 0 ? P::kAccV : P::kAccP) + 2 * nx + (uint32_t)b * P::kNG;
-            uint32_t idx = trunk == 0 ? idesc_f16(P::kNXV, true) : idesc_f16(P::kNXP, true);
             const uint32_t empty_bar = bar_empty((int)kb);
             pin64(bx);
             pin64(bg);
-            pin32(acc1);
-            pin32(acc2);
-            pin32(idx);
-            uint64_t a2 = 0, b2 = 0;
-            if (more) recompute_ops(s + 2, a2, b2);
-            HTR(2 + b, s, 0);
+            uint64_t xb = 0;
             if (more) {
-                need_tile((s + 2) >> 3);
-                if (kNamedBarriers) hand_over(1 + b);
-                else tcp::mbar_wait_c(bar_hl(b), par);                   // H^T of stage s is in the consumers' registers
-                tc_fence_after();
-                HTR(2 + b, s, 1);
-                if (tcp::elect_one()) recompute(a2, b2);
-                __syncwarp();
-                HTR(2 + b, s, 2);
+                xb = x_of(s + kRegions);
+                need_tile((s + kRegions) >> 3);
             }
-            if (kNamedBarriers) {
-                if (!more) hand_over(1 + b);                             // (every stage has both hand-overs, also the last ones)
-                hand_over(3 + b);
-            } else {
-                tcp::mbar_wait_c(bar_c(b), par);                         // relu^T | M^T of stage s are in RM region b
-            }
+            HTR(2, s, 0);
+            hand_over(r);                                               // relu^T | M^T of stage s are in the region
             tc_fence_after();
-            HTR(2 + b, s, 3);
+            HTR(2, s, 1);
             if (tcp::elect_one()) {
+                // rows 32p .. 32p + 31 of the stage sit at columns [32p, 32p + 16) (relu^T) and [32p + 16, 32p + 32) (M^T)
 #pragma unroll
                 for (int ks = 0; ks < 4; ++ks)
-                    mma_ts_f16(acc2, rm + ks * 8, bg + (uint64_t)((ks * 2 * P::kLboK) >> 4), idesc_f16(P::kNG, true), true);
+                    mma_ts_f16(acc2, region + (ks >> 1) * 32 + (ks & 1) * 8, bg + (uint64_t)((ks * 2 * P::kLboK) >> 4), idesc_f16(P::kNG, true), true);
 #pragma unroll
                 for (int ks = 0; ks < 4; ++ks)
-                    mma_ts_f16(acc1, rm + 32 + ks * 8, bx + (uint64_t)((ks * 2 * P::kLboK) >> 4), idx, true);
-                if ((s & 7) >= 6) mma_commit(empty_bar);                 // this issuer's last reads of the tile's shared-memory operands
-                mma_commit(bar_g(b));
+                    mma_ts_f16(acc1, region + (ks >> 1) * 32 + 16 + (ks & 1) * 8, bx + (uint64_t)((ks * 2 * P::kLboK) >> 4), idx, true);
+                if ((s & 7) >= 4) mma_commit(empty_bar);                // this issuer's last reads of the tile's shared-memory operands
+                if (more) recompute(xb);                                // (in order behind grad(s), which reads the region)
+                else mma_commit(bar_h(r));                              // the last gradient MMAs of the region
             }
             __syncwarp();
-            HTR(2 + b, s, 4);
+            HTR(2, s, 2);
         }
     } else if (tid >= kConsumers) {
         // ------------------------------------------------------------ producers: one thread per tile row
@@ -417,119 +386,48 @@ __global__ void __launch_bounds__(kThreadsH, 1) learner_bwd_f16_kernel(const flo
             if (lane32 == 0) s_red[pw * 8 + a] = v;
         }
     } else {
-        // ------------------------------------------------------------ consumers: thread = hidden unit x 32 rows of a stage
-        const int quad = warp & 3, cpart = warp >> 2;             // TMEM lane quadrant (hidden unit); (trunk, half) of the final read-out
-        // (b = warp >> 3: group == region == stage parity)
-        const bool leader = kSelfIssue && (warp & 7) == 0;          // issues the group's MMAs
-        auto group_sync = [&]() { asm volatile("bar.sync %0, %1;" ::"r"(1 + b), "n"(kConsumers / 2) : "memory"); };
-        tcp::mbar_wait_c(bar_img, 0);
-        if (leader && (uint32_t)b < n_st) {                        // fill the pipeline: stage b
-            uint64_t a, bb;
-            recompute_ops((uint32_t)b, a, bb);
-            need_tile(0);
-            tc_fence_after();
-            if (tcp::elect_one()) recompute(a, bb);
-            __syncwarp();
-        }
-        const int cw = cpart & 1;                                  // which 32 of the stage's 64 rows
+        // ------------------------------------------------------------ consumers: group r = warp >> 2 serves region r
+        // thread = hidden unit (TMEM lane) x the 64 rows of a stage, 32 at a time
+        const int quad = warp & 3, cpart = warp >> 2;             // TMEM lane quadrant (hidden unit); region == (trunk, half) of the final read-out
+        const int r = cpart;
         const int j_local = quad * 32 + lane32;
         const uint32_t tmem_lane = tmem_base + ((uint32_t)(quad * 32) << 16);
-        const uint32_t th = tmem_lane + P::kColH + b * 64 + cw * 32;
-        const uint32_t trm = tmem_lane + P::kColRM + b * 64 + cw * 16;
+        const uint32_t region = tmem_lane + P::kColStage + (uint32_t)r * 64;
         const __half2 zero2 = __float2half2_rn(0.f);
 #pragma unroll 1
-        for (uint32_t s = (uint32_t)b; s < n_st; s += 2) {
-            const uint32_t i = s >> 1;
-            const bool tr = (warp & 7) == 0;
-            const bool more = s + 2 < n_st;
-            // (leader) operands of grad(s) and recompute(s + 2), ahead of the waits
-            const uint32_t trunk = (s >> 1) & 1u, rh = (s >> 2) & 1u, kb = (s >> 3) & 1u;
-            const uint32_t t_off = kb * P::kTileBytes + rh * 8 * P::kLboK;
-            uint64_t bx = g_desc + (uint64_t)((t_off + (trunk == 0 ? P::kBXV : P::kBXP)) >> 4);
-            uint64_t bg = g_desc + (uint64_t)((t_off + P::kBG) >> 4);
-            const uint32_t nx = trunk == 0 ? P::kNXV : P::kNXP;
-            uint32_t acc1 = tmem_base + (trunk == 0 ? P::kAccV : P::kAccP) + (uint32_t)b * nx;
-            uint32_t acc2 = tmem_base + (trunk == 0 ? P::kAccV : P::kAccP) + 2 * nx + (uint32_t)b * P::kNG;
-            uint32_t idx = trunk == 0 ? idesc_f16(P::kNXV, true) : idesc_f16(P::kNXP, true);
-            const uint32_t empty_bar = bar_empty((int)kb);
-            uint64_t a2 = 0, b2 = 0;
-            if (leader) {
-                pin64(bx);
-                pin64(bg);
-                pin32(acc1);
-                pin32(acc2);
-                pin32(idx);
-                if (more) recompute_ops(s + 2, a2, b2);
-            }
-            if (tr) HTR(b, s, 0);
-            tcp::mbar_wait_c(bar_h(b), i & 1u);
+        for (uint32_t s = (uint32_t)r; s < n_st; s += kRegions) {
+            const uint32_t i = s >> 2;
+            const bool tr = quad == 0 && r == 0;
+            if (tr) HTR(0, s, 0);
+            tcp::mbar_wait_c(bar_h(r), i & 1u);                     // H^T of stage s is in the region (and grad(s - 4) has read it)
             tc_fence_after();
-            if (tr) HTR(b, s, 1);
-            uint32_t hr[32];
-            tmem_ld16(th, hr);
-            tmem_ld16(th + 16, hr + 16);
-            tmem_ld_wait();
-            if (tr) HTR(b, s, 2);
-            tc_fence_before();
-            if (kSelfIssue) {
-                group_sync();                                       // H^T of stage s is in the group's registers
-                if (leader && more) {
-                    need_tile((s + 2) >> 3);
-                    tc_fence_after();
-                    if (tcp::elect_one()) recompute(a2, b2);
-                    __syncwarp();
-                }
-            } else if (kNamedBarriers) {
-                hand_over(1 + b);                                   // the issuer may recompute stage s + 2 into the region
-            } else {
-                __syncwarp();
-                if (lane32 == 0) tcp::mbar_arrive(bar_hl(b));
-            }
-            // ---- rows (2c, 2c + 1) -> one packed column: relu^T, and next to it the 0/1 mask (of the ROUNDED value: a
-            // hidden unit whose positive pre-activation rounds to zero in fp16 counts as switched off in both)
-            uint32_t re[16], mk[16];
+            if (tr) HTR(0, s, 1);
 #pragma unroll
-            for (int c = 0; c < 16; ++c) {
-                re[c] = pack2_relu(__uint_as_float(hr[2 * c]), __uint_as_float(hr[2 * c + 1]));
-                const __half2 m = __hgt2(*reinterpret_cast<const __half2*>(&re[c]), zero2);
-                mk[c] = *reinterpret_cast<const uint32_t*>(&m);
+            for (int pass = 0; pass < 2; ++pass) {
+                uint32_t hr[32];
+                tmem_ld16(region + pass * 32, hr);
+                tmem_ld16(region + pass * 32 + 16, hr + 16);
+                tmem_ld_wait();
+                // rows (2c, 2c + 1) -> one packed column: relu^T, and next to it the 0/1 mask (of the ROUNDED value: a
+                // hidden unit whose positive pre-activation rounds to zero in fp16 counts as switched off in both)
+                uint32_t re[16], mk[16];
+#pragma unroll
+                for (int c = 0; c < 16; ++c) {
+                    re[c] = pack2_relu(__uint_as_float(hr[2 * c]), __uint_as_float(hr[2 * c + 1]));
+                    const __half2 m = __hgt2(*reinterpret_cast<const __half2*>(&re[c]), zero2);
+                    mk[c] = *reinterpret_cast<const uint32_t*>(&m);
+                }
+                tmem_st16(region + pass * 32, re);
+                tmem_st16(region + pass * 32 + 16, mk);
             }
-            if (i >= 1) {                                           // grad(s - 2) has read the region
-                tcp::mbar_wait_c(bar_g(b), (i - 1) & 1u);
-                tc_fence_after();
-            }
-            if (tr) HTR(b, s, 3);
-            tmem_st16(trm, re);
-            tmem_st16(trm + 32, mk);
             tcp::tmem_st_wait();
-            if (tr) HTR(b, s, 4);
+            if (tr) HTR(0, s, 2);
             tc_fence_before();
-            if (kSelfIssue) {
-                group_sync();                                       // relu^T | M^T of stage s are in RM region b
-                if (leader) {
-                    tc_fence_after();
-                    if (tcp::elect_one()) {
-#pragma unroll
-                        for (int ks = 0; ks < 4; ++ks)
-                            mma_ts_f16(acc2, rm + ks * 8, bg + (uint64_t)((ks * 2 * P::kLboK) >> 4), idesc_f16(P::kNG, true), true);
-#pragma unroll
-                        for (int ks = 0; ks < 4; ++ks)
-                            mma_ts_f16(acc1, rm + 32 + ks * 8, bx + (uint64_t)((ks * 2 * P::kLboK) >> 4), idx, true);
-                        if ((s & 7) >= 6) mma_commit(empty_bar);    // this group's last reads of the tile's shared-memory operands
-                        mma_commit(bar_g(b));
-                    }
-                    __syncwarp();
-                }
-            } else if (kNamedBarriers) {
-                hand_over(3 + b);                                   // relu^T | M^T of stage s are in RM region b
-            } else {
-                __syncwarp();
-                if (lane32 == 0) tcp::mbar_arrive(bar_c(b));
-            }
-            if (tr) HTR(b, s, 5);
+            hand_over(r);                                           // -> grad(s), recompute(s + 4)
+            if (tr) HTR(0, s, 3);
         }
-        // every gradient MMA complete: the last commit of the group's issuer; then the groups meet
-        if (n_stages >= 2) tcp::mbar_wait_c(bar_g(b), (uint32_t)((n_stages >> 1) - 1) & 1u);
+        // every gradient MMA of the region complete: its issuer's last commit; then the groups meet
+        if (n_st >= (uint32_t)kRegions) tcp::mbar_wait_c(bar_h(r), (n_st >> 2) & 1u);
         tc_fence_before();
         asm volatile("bar.sync 5, %0;" ::"n"(kConsumers) : "memory");
         tc_fence_after();

@@ -349,7 +349,7 @@ template <int A, int C, bool F16>
 __global__ void __launch_bounds__(kThreads, 1) rollout_tc2_kernel(RolloutArgs g) {
     using P = Plan<A, F16>;
     constexpr int KIN = P::KIN, KP = P::KP;
-    static_assert(!F16 || (kEpiWarps == 8 && !kEpiWide), "the fp16 epilogue exists for the default warp layout only");
+    static_assert(!F16 || kEpiWarps == 8, "the fp16 epilogue exists for eight epilogue warps (both layouts)");
     static_assert(A <= 4, "value + logits must fit the 8 useful columns of the second-layer accumulator");
     extern __shared__ __align__(1024) uint8_t smem[];
     const int tid = threadIdx.x;
