@@ -1,28 +1,21 @@
-// Learner-side net passes of RNaD.__learn, fused (SURVEY.md section 8 f#3):
+// Learner-side net passes of RNaD.__learn, fused (SURVEY.md section 8 f#3): the C-ABI entry points, the workspace
+// layout, and the one kernel still serving max_actions = 4.
 //
-//   rnad_learner_forward   the four forward_batch calls of rnad.py:373-380 in ONE pass
-//                          over the trajectory: learner (logit, pi, log_pi, v), target
-//                          net (v only), regularisation nets (log_pi only) = five trunk
-//                          evaluations per step instead of eight.  The engine in use is
-//                          learner_fwd_tc2.cu (both layers on tcgen05, fp16 operands); the
-//                          kernel in THIS file (first layers tcgen05 kind::tf32, second
-//                          layers on the CUDA cores) is the first build, kept for A/B runs
-//                          (RNAD_LEARNER_FWD_V1).
-//   rnad_learner_backward  parameter gradients of the learner net given d loss/d logit
-//   (_split)               and d loss/d v (from rnad_learner_targets).  Dispatch, newest
-//                          first:  split mode, max_actions <= 3 -> learner_bwd_f16.cu (fp16
-//                          operands, mask formulation, decoupled tensor-memory regions);
-//                          flat mode, max_actions <= 3 -> learner_bwd_tc3.cu (tf32, mask
-//                          formulation);  max_actions = 4 -> learner_bwd_tc2_kernel here:
-//                          the two trunks recomputed TRANSPOSED on the tensor core,
+//   rnad_learner_forward   the four forward_batch calls of rnad.py:373-380 in ONE pass over the trajectory: learner
+//                          (logit, pi, log_pi, v), target net (v only), regularisation nets (log_pi only) = five
+//                          trunk evaluations per step instead of eight -> learner_fwd_tc2.cu (both layers on
+//                          tcgen05, fp16 operands).
+//   rnad_learner_backward  parameter gradients of the learner net given d loss/d logit and d loss/d v (from
+//   (_split)               rnad_learner_targets).  Dispatch:  split mode, max_actions <= 3 -> learner_bwd_f16.cu
+//                          (fp16 operands, mask formulation, four in-place stage regions);  flat mode,
+//                          max_actions <= 3 -> learner_bwd_tc3.cu (tf32, mask formulation);  max_actions = 4 ->
+//                          learner_bwd_tc2_kernel here: the two trunks recomputed TRANSPOSED on the tensor core,
 //                              dW2 = g^T relu(h),  dh = (g W2) * [h > 0],  dW1 = dh^T x
-//                          with MMAs whose A operands (relu^T, dh^T) sit in tensor memory
-//                          and whose accumulators stay there across all tiles of a CTA.
-//                          A second kernel adds the per-CTA partials in a fixed order
-//                          (deterministic), per player in split mode.  learner_bwd_tc_kernel
-//                          (two CTAs per SM) and learner_bwd_kernel (reduction on the CUDA
-//                          cores) are earlier builds kept for A/B runs (RNAD_LEARNER_BWD_V1,
-//                          RNAD_LEARNER_BWD_CUDA_CORES).
+//                          with MMAs whose A operands (relu^T, dh^T) sit in tensor memory and whose accumulators
+//                          stay there across all tiles of a CTA.  A second kernel adds the per-CTA partials in a
+//                          fixed order (deterministic), per player in split mode.
+//   (Earlier builds - a forward with its second layers on the CUDA cores, a backward that reduced on the CUDA cores
+//    and one with two CTAs per SM - were removed at the end of round 2; `git log` has them.)
 //
 // Reference: nn/net.py:64-85 (forward_batch), learn/rnad.py:373-380, 424-425.
 // In the reference these are 8 x T small GEMMs + ~40 elementwise launches forward and
@@ -45,476 +38,6 @@ int learner_forward_tc2(const float* obs, int64_t N, int A, const rnad_mlp_weigh
 
 namespace tc {
 
-constexpr int kLearnThreads = 256;   // two threads per trajectory row
-constexpr int kFwdTrunks = 5;        // learner value, learner policy, target value, reg policy, reg_ policy
-
-// ------------------------------------------------------------------ forward
-
-template <int A>
-struct FwdPlan : Shape<A> {
-    using S = Shape<A>;
-    static constexpr int kB = 0;                                        // 5 first-layer operands
-    static constexpr int kW2v = kB + kFwdTrunks * S::kTrunkBytes;       // value_fc1.weight of learner, target
-    static constexpr int kW2p = kW2v + 2 * kHidden * 4;                 // policy_fc1.weight [j][4] of learner, reg, reg_
-    static constexpr int kB1 = kW2p + 3 * kHidden * 16;                 // first-layer biases, 5 x 256
-    static constexpr int kB2 = kB1 + kFwdTrunks * kHidden * 4;          // second-layer biases: 5 x 4 f32
-    static constexpr int kImageBytes = kB2 + kFwdTrunks * 16;
-    static constexpr int kA = kImageBytes;                              // A operand tile
-    static constexpr int kPart = kA + kTileM * S::KP * 4;               // upper-half partial sums: 128 x 5 x float4
-    static constexpr int kBar = kPart + kTileM * kFwdTrunks * 16;       // mbarriers: image, stage 0, stage 1
-    static constexpr int kTmem = kBar + 32;
-    static constexpr int kBytes = kTmem + 16;
-    static_assert(kImageBytes % 16 == 0 && kA % 16 == 0 && kPart % 16 == 0 && kBar % 8 == 0, "alignment");
-};
-
-struct FwdNets {
-    rnad_mlp_weights net, target, reg, reg_;
-};
-
-struct FwdOut {
-    float* logit;
-    float* pi;
-    float* log_pi;
-    float* v;
-    float* v_target;
-    float* log_pi_reg;
-    float* log_pi_reg_;
-};
-
-template <int A>
-__global__ void pack_fwd_image_kernel(FwdNets w, uint8_t* __restrict__ image) {
-    using P = FwdPlan<A>;
-    const int thread = blockIdx.x * blockDim.x + threadIdx.x, n_threads = gridDim.x * blockDim.x;
-    const float* w1[kFwdTrunks] = {w.net.value_fc0_w, w.net.policy_fc0_w, w.target.value_fc0_w, w.reg.policy_fc0_w,
-                                   w.reg_.policy_fc0_w};
-    const float* b1[kFwdTrunks] = {w.net.value_fc0_b, w.net.policy_fc0_b, w.target.value_fc0_b, w.reg.policy_fc0_b,
-                                   w.reg_.policy_fc0_b};
-#pragma unroll
-    for (int tr = 0; tr < kFwdTrunks; ++tr) {
-        pack_trunk_operand<P::KIN, P::KP, P::kBiasInK>(w1[tr], b1[tr], image + P::kB + tr * P::kTrunkBytes, thread,
-                                                       n_threads);
-        for (int j = thread; j < kHidden; j += n_threads) reinterpret_cast<float*>(image + P::kB1)[tr * kHidden + j] = b1[tr][j];
-    }
-    const float* w2v[2] = {w.net.value_fc1_w, w.target.value_fc1_w};
-    const float* w2p[3] = {w.net.policy_fc1_w, w.reg.policy_fc1_w, w.reg_.policy_fc1_w};
-    for (int j = thread; j < kHidden; j += n_threads) {
-#pragma unroll
-        for (int i = 0; i < 2; ++i) reinterpret_cast<float*>(image + P::kW2v)[i * kHidden + j] = w2v[i][j];
-#pragma unroll
-        for (int i = 0; i < 3; ++i) {
-            float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
-            p.x = w2p[i][j];
-            if (A > 1) p.y = w2p[i][1 * kHidden + j];
-            if (A > 2) p.z = w2p[i][2 * kHidden + j];
-            if (A > 3) p.w = w2p[i][3 * kHidden + j];
-            reinterpret_cast<float4*>(image + P::kW2p)[i * kHidden + j] = p;
-        }
-    }
-    if (thread < kFwdTrunks * 4) {
-        const int tr = thread >> 2, a = thread & 3;
-        const float* b2[kFwdTrunks] = {w.net.value_fc1_b, w.net.policy_fc1_b, w.target.value_fc1_b, w.reg.policy_fc1_b,
-                                       w.reg_.policy_fc1_b};
-        const int n = (tr == 0 || tr == 2) ? 1 : A;
-        reinterpret_cast<float*>(image + P::kB2)[thread] = a < n ? b2[tr][a] : 0.f;
-    }
-}
-
-template <int KP>
-__device__ __forceinline__ void issue_trunk_mma(uint32_t a_base, uint32_t b_trunk, uint32_t d_tmem, uint32_t mbar) {
-#pragma unroll
-    for (int s = 0; s < KP / 8; ++s) mma_tf32(d_tmem, make_desc<KP>(a_base + s * 256), make_desc<KP>(b_trunk + s * 256), s > 0);
-    mma_commit(mbar);
-}
-
-// net.py:76-80: masked softmax / log-softmax of one row
-template <int A>
-__device__ __forceinline__ void policy_heads(const float (&logit)[A], const bool (&mask)[A], float (&pi)[A],
-                                             float (&log_pi)[A]) {
-    float e[A];
-    float sum = 0.f;
-#pragma unroll
-    for (int a = 0; a < A; ++a) {
-        e[a] = mask[a] ? expf(logit[a]) : 0.f;
-        sum += e[a];
-    }
-    const float denom = fmaxf(sum, 1e-12f);
-    const float log_sum = logf(sum);
-#pragma unroll
-    for (int a = 0; a < A; ++a) {
-        pi[a] = e[a] / denom;
-        log_pi[a] = mask[a] ? logit[a] - log_sum : 0.f;
-    }
-}
-
-template <int A>
-__global__ void __launch_bounds__(kLearnThreads, 1) learner_fwd_kernel(const float* __restrict__ obs, int64_t N,
-                                                                        const uint8_t* __restrict__ image, FwdOut out) {
-    using P = FwdPlan<A>;
-    constexpr int KIN = P::KIN, KP = P::KP;
-    static_assert(A <= 4, "one float4 of second-layer weights per hidden unit");
-    extern __shared__ __align__(1024) uint8_t smem[];
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & (kTileM - 1), half = tid >> 7;
-    const uint32_t bar_img = smem_u32(smem + P::kBar), bar_stage[2] = {bar_img + 8, bar_img + 16};
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + P::kTmem);
-
-    if (warp == 0) tmem_alloc<512>(tmem_slot);
-    if (tid == 0) {
-        mbar_init(bar_img, 1);
-        mbar_init(bar_stage[0], 1);
-        mbar_init(bar_stage[1], 1);
-        mbar_fence_init();
-        tma_bulk_load(smem, image, P::kImageBytes, bar_img);
-    }
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    mbar_wait(bar_img, 0);
-    const uint32_t tmem_base = *tmem_slot;
-    const uint32_t tmem_mine = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(half * 128);
-    const uint32_t a_base = smem_u32(smem + P::kA), b_base = smem_u32(smem + P::kB);
-    const float* b1 = reinterpret_cast<const float*>(smem + P::kB1);
-    const float* b2 = reinterpret_cast<const float*>(smem + P::kB2);
-    const float* w2v = reinterpret_cast<const float*>(smem + P::kW2v);
-    const float4* w2p = reinterpret_cast<const float4*>(smem + P::kW2p);
-    float4* s_part = reinterpret_cast<float4*>(smem + P::kPart);
-
-    uint32_t phase[2] = {0u, 0u};
-    const int64_t num_tiles = (N + kTileM - 1) / kTileM;
-    for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int64_t row = tile * kTileM + lane;
-        const bool active = row < N;
-        bool mask[A];
-#pragma unroll
-        for (int a = 0; a < A; ++a) mask[a] = false;
-        if (half == 0) {
-            float x[KIN];
-            load_row<KIN>(obs, row, active, x);
-#pragma unroll
-            for (int a = 0; a < A; ++a) mask[a] = x[A * A + a * A] != 0.f;   // obs[:, 1, :, 0]
-            store_operand_row<KIN, KP, P::kBiasInK>(smem + P::kA, lane, x);
-            fence_async_smem();
-        }
-        tc_fence_before();
-        __syncthreads();
-        if (warp == 0) {           // converged warp, one elected lane issues (see learner_bwd_tc_kernel)
-            tc_fence_after();
-            if (tcp::elect_one()) {
-                issue_trunk_mma<KP>(a_base, b_base + 0 * P::kTrunkBytes, tmem_base + 0, bar_stage[0]);
-                issue_trunk_mma<KP>(a_base, b_base + 1 * P::kTrunkBytes, tmem_base + 256, bar_stage[1]);
-            }
-            __syncwarp();
-        }
-
-        float4 part[kFwdTrunks];
-#pragma unroll
-        for (int pass = 0; pass < kFwdTrunks; ++pass) {
-            constexpr int kNone = 0;
-            (void)kNone;
-            const int stage = pass & 1;
-            const bool value_pass = pass == 0 || pass == 2;
-            mbar_wait(bar_stage[stage], phase[stage]);
-            phase[stage] ^= 1u;
-            tc_fence_after();
-            float vacc[4] = {0.f, 0.f, 0.f, 0.f};
-            float lacc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
-            const float* b1p = b1 + pass * kHidden + half * 128;
-            const float* w2vp = w2v + (pass == 2 ? kHidden : 0) + half * 128;
-            const float4* w2pp = w2p + (pass == 1 ? 0 : pass == 3 ? kHidden : 2 * kHidden) + half * 128;
-            const uint32_t taddr = tmem_mine + stage * 256;
-            uint32_t ra[32], rb[32];
-            tmem_ld32(taddr, ra);
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                tmem_ld_wait();
-                if (c + 1 < 4) {
-                    if (c & 1) tmem_ld32(taddr + (c + 1) * 32, ra);
-                    else tmem_ld32(taddr + (c + 1) * 32, rb);
-                }
-                if (value_pass) {
-                    if (c & 1) consume_chunk<A, true, !P::kBiasInK>(rb, 0, b1p + c * 32, w2vp + c * 32, w2pp, vacc, lacc);
-                    else consume_chunk<A, true, !P::kBiasInK>(ra, 0, b1p + c * 32, w2vp + c * 32, w2pp, vacc, lacc);
-                } else {
-                    if (c & 1) consume_chunk<A, false, !P::kBiasInK>(rb, 0, b1p + c * 32, w2vp, w2pp + c * 32, vacc, lacc);
-                    else consume_chunk<A, false, !P::kBiasInK>(ra, 0, b1p + c * 32, w2vp, w2pp + c * 32, vacc, lacc);
-                }
-            }
-            part[pass] = value_pass ? make_float4((vacc[0] + vacc[1]) + (vacc[2] + vacc[3]), 0.f, 0.f, 0.f)
-                                    : make_float4(lacc[0][0] + lacc[1][0], lacc[0][1] + lacc[1][1],
-                                                  lacc[0][2] + lacc[1][2], lacc[0][3] + lacc[1][3]);
-            tc_fence_before();
-            if (pass + 2 < kFwdTrunks) {
-                __syncthreads();   // every thread has drained this accumulator stage
-                if (warp == 0) {
-                    tc_fence_after();
-                    if (tcp::elect_one())
-                        issue_trunk_mma<KP>(a_base, b_base + (pass + 2) * P::kTrunkBytes, tmem_base + stage * 256,
-                                            bar_stage[stage]);
-                    __syncwarp();
-                }
-            }
-        }
-        if (half == 1) {
-#pragma unroll
-            for (int pass = 0; pass < kFwdTrunks; ++pass) s_part[lane * kFwdTrunks + pass] = part[pass];
-        }
-        __syncthreads();
-        if (half == 0 && active) {
-            float4 tot[kFwdTrunks];
-#pragma unroll
-            for (int pass = 0; pass < kFwdTrunks; ++pass) {
-                const float4 o = s_part[lane * kFwdTrunks + pass];
-                const float4 bias = *reinterpret_cast<const float4*>(b2 + pass * 4);
-                tot[pass] = make_float4((part[pass].x + o.x) + bias.x, (part[pass].y + o.y) + bias.y,
-                                        (part[pass].z + o.z) + bias.z, (part[pass].w + o.w) + bias.w);
-            }
-            out.v[row] = tot[0].x;
-            out.v_target[row] = tot[2].x;
-            const float heads[3][4] = {{tot[1].x, tot[1].y, tot[1].z, tot[1].w},
-                                       {tot[3].x, tot[3].y, tot[3].z, tot[3].w},
-                                       {tot[4].x, tot[4].y, tot[4].z, tot[4].w}};
-            float* log_dst[3] = {out.log_pi, out.log_pi_reg, out.log_pi_reg_};
-#pragma unroll
-            for (int hnet = 0; hnet < 3; ++hnet) {
-                float logit[A], pi[A], log_pi[A];
-#pragma unroll
-                for (int a = 0; a < A; ++a) logit[a] = heads[hnet][a];
-                policy_heads<A>(logit, mask, pi, log_pi);
-#pragma unroll
-                for (int a = 0; a < A; ++a) {
-                    log_dst[hnet][row * A + a] = log_pi[a];
-                    if (hnet == 0) {
-                        out.logit[row * A + a] = logit[a];
-                        out.pi[row * A + a] = pi[a];
-                    }
-                }
-            }
-        }
-    }
-    tc_fence_before();
-    __syncthreads();
-    if (warp == 0) tmem_dealloc<512>(tmem_base);
-}
-
-// ----------------------------------------------------------------- backward
-
-template <int A>
-struct BwdPlan : Shape<A> {
-    using S = Shape<A>;
-    static constexpr int kHStride = kHidden + 1;                        // fp32 words per row of the activation tile
-    static constexpr int kB = 0;                                        // learner value, policy first layers
-    static constexpr int kB1 = kB + 2 * S::kTrunkBytes;                 // their biases, 2 x 256
-    static constexpr int kImageBytes = kB1 + 2 * kHidden * 4;
-    static constexpr int kA = kImageBytes;                              // A operand tile (tf32)
-    static constexpr int kG = kA + kTileM * S::KP * 4;                  // [128][8]: d_v, d_logit[0..A)
-    static constexpr int kH = kG + kTileM * 32;                         // relu(h) of one trunk, [128][257] f32
-    static constexpr int kXraw = kH + kTileM * kHStride * 4;            // exact fp32 inputs [128][KIN] (if they fit)
-    static constexpr bool kExactX = kXraw + kTileM * S::KIN * 4 + 64 <= 227 * 1024;
-    static constexpr int kBar = round_up(kXraw + (kExactX ? kTileM * S::KIN * 4 : 0), 16);
-    static constexpr int kTmem = kBar + 32;
-    static constexpr int kBytes = kTmem + 16;
-    static_assert(kBytes <= 227 * 1024, "backward tile does not fit in shared memory");
-};
-
-template <int A>
-__global__ void pack_bwd_image_kernel(rnad_mlp_weights w, uint8_t* __restrict__ image) {
-    using P = BwdPlan<A>;
-    const int thread = blockIdx.x * blockDim.x + threadIdx.x, n_threads = gridDim.x * blockDim.x;
-    pack_trunk_operand<P::KIN, P::KP, P::kBiasInK>(w.value_fc0_w, w.value_fc0_b, image + P::kB, thread, n_threads);
-    pack_trunk_operand<P::KIN, P::KP, P::kBiasInK>(w.policy_fc0_w, w.policy_fc0_b, image + P::kB + P::kTrunkBytes,
-                                                   thread, n_threads);
-    for (int j = thread; j < kHidden; j += n_threads) {
-        reinterpret_cast<float*>(image + P::kB1)[j] = w.value_fc0_b[j];
-        reinterpret_cast<float*>(image + P::kB1)[kHidden + j] = w.policy_fc0_b[j];
-    }
-}
-
-template <int A>
-__global__ void __launch_bounds__(kLearnThreads, 1) learner_bwd_kernel(const float* __restrict__ obs, int64_t N,
-                                                                        const uint8_t* __restrict__ image,
-                                                                        rnad_mlp_weights w,
-                                                                        const float* __restrict__ d_logit,
-                                                                        const float* __restrict__ d_v,
-                                                                        float* __restrict__ partials) {
-    using P = BwdPlan<A>;
-    constexpr int KIN = P::KIN, KP = P::KP, HS = P::kHStride;
-    extern __shared__ __align__(1024) uint8_t smem[];
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & (kTileM - 1), half = tid >> 7;
-    const uint32_t bar_img = smem_u32(smem + P::kBar), bar_stage[2] = {bar_img + 8, bar_img + 16};
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + P::kTmem);
-
-    if (warp == 0) tmem_alloc<512>(tmem_slot);
-    if (tid == 0) {
-        mbar_init(bar_img, 1);
-        mbar_init(bar_stage[0], 1);
-        mbar_init(bar_stage[1], 1);
-        mbar_fence_init();
-        tma_bulk_load(smem, image, P::kImageBytes, bar_img);
-    }
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    mbar_wait(bar_img, 0);
-    const uint32_t tmem_base = *tmem_slot;
-    const uint32_t tmem_mine = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(half * 128);
-    const uint32_t a_base = smem_u32(smem + P::kA), b_base = smem_u32(smem + P::kB);
-    const float* b1 = reinterpret_cast<const float*>(smem + P::kB1);
-    float* s_g = reinterpret_cast<float*>(smem + P::kG);
-    float* s_h = reinterpret_cast<float*>(smem + P::kH);
-    float* s_x = reinterpret_cast<float*>(smem + P::kXraw);
-
-    // thread j owns hidden unit j of both trunks in the reduction phase
-    const int j = tid;
-    const float w2v_j = w.value_fc1_w[j];
-    float w2p_j[A];
-#pragma unroll
-    for (int a = 0; a < A; ++a) w2p_j[a] = w.policy_fc1_w[a * kHidden + j];
-    float gw1[2][KIN], gb1[2] = {0.f, 0.f}, gw2v = 0.f, gw2p[A], gb2 = 0.f;
-#pragma unroll
-    for (int k = 0; k < KIN; ++k) gw1[0][k] = gw1[1][k] = 0.f;
-#pragma unroll
-    for (int a = 0; a < A; ++a) gw2p[a] = 0.f;
-
-    uint32_t phase[2] = {0u, 0u};
-    const int64_t num_tiles = (N + kTileM - 1) / kTileM;
-    for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int64_t row = tile * kTileM + lane;
-        const bool active = row < N;
-        if (half == 0) {
-            float x[KIN];
-            load_row<KIN>(obs, row, active, x);
-            store_operand_row<KIN, KP, P::kBiasInK>(smem + P::kA, lane, x);
-            if (P::kExactX) {
-#pragma unroll
-                for (int k = 0; k < KIN; ++k) s_x[lane * KIN + k] = x[k];
-            }
-            fence_async_smem();
-        } else {
-            float4 g0 = make_float4(0.f, 0.f, 0.f, 0.f), g1 = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (active) {
-                g0.x = d_v[row];
-                g0.y = d_logit[row * A + 0];
-                if (A > 1) g0.z = d_logit[row * A + 1];
-                if (A > 2) g0.w = d_logit[row * A + 2];
-                if (A > 3) g1.x = d_logit[row * A + 3];
-            }
-            reinterpret_cast<float4*>(s_g + lane * 8)[0] = g0;
-            reinterpret_cast<float4*>(s_g + lane * 8)[1] = g1;
-        }
-        tc_fence_before();
-        __syncthreads();
-        if (tid == 0) {
-            tc_fence_after();
-            issue_trunk_mma<KP>(a_base, b_base, tmem_base + 0, bar_stage[0]);
-            issue_trunk_mma<KP>(a_base, b_base + P::kTrunkBytes, tmem_base + 256, bar_stage[1]);
-        }
-#pragma unroll
-        for (int tr = 0; tr < 2; ++tr) {
-            // ---- activations of this trunk: TMEM -> relu -> shared [row][hidden]
-            mbar_wait(bar_stage[tr], phase[tr]);
-            phase[tr] ^= 1u;
-            tc_fence_after();
-            const uint32_t taddr = tmem_mine + tr * 256;
-            uint32_t ra[32], rb[32];
-            tmem_ld32(taddr, ra);
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                tmem_ld_wait();
-                if (c + 1 < 4) {
-                    if (c & 1) tmem_ld32(taddr + (c + 1) * 32, ra);
-                    else tmem_ld32(taddr + (c + 1) * 32, rb);
-                }
-                const int col = half * 128 + c * 32;
-#pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    float h = __uint_as_float((c & 1) ? rb[i] : ra[i]);
-                    if (!P::kBiasInK) h += b1[tr * kHidden + col + i];
-                    s_h[lane * HS + col + i] = fmaxf(h, 0.f);
-                }
-            }
-            tc_fence_before();
-            __syncthreads();
-            // ---- reduce over the 128 rows of the tile, hidden unit j per thread
-            {
-                float acc_w1[KIN], acc_b1 = 0.f, acc_w2[A];
-#pragma unroll
-                for (int k = 0; k < KIN; ++k) acc_w1[k] = 0.f;
-#pragma unroll
-                for (int a = 0; a < A; ++a) acc_w2[a] = 0.f;
-                float acc_b2 = 0.f;
-#pragma unroll 2
-                for (int n = 0; n < kTileM; ++n) {
-                    const float r = s_h[n * HS + j];
-                    const float4 g0 = reinterpret_cast<const float4*>(s_g + n * 8)[0];
-                    float s;
-                    if (tr == 0) {
-                        s = g0.x * w2v_j;
-                        acc_w2[0] = fmaf(g0.x, r, acc_w2[0]);
-                    } else {
-                        const float gl[4] = {g0.y, g0.z, g0.w, A > 3 ? s_g[n * 8 + 4] : 0.f};
-                        s = 0.f;
-#pragma unroll
-                        for (int a = 0; a < A; ++a) {
-                            s = fmaf(gl[a], w2p_j[a], s);
-                            acc_w2[a] = fmaf(gl[a], r, acc_w2[a]);
-                        }
-                    }
-                    if (tr == 0 && j <= A) acc_b2 += s_g[n * 8 + j];   // threads 0..A also sum the output-bias gradients
-                    const float dh = r > 0.f ? s : 0.f;
-                    acc_b1 += dh;
-                    if (P::kExactX) {
-                        const float2* xr = reinterpret_cast<const float2*>(s_x + n * KIN);
-#pragma unroll
-                        for (int k2 = 0; k2 < KIN / 2; ++k2) {
-                            const float2 xv = xr[k2];
-                            acc_w1[2 * k2] = fmaf(dh, xv.x, acc_w1[2 * k2]);
-                            acc_w1[2 * k2 + 1] = fmaf(dh, xv.y, acc_w1[2 * k2 + 1]);
-                        }
-                    } else {
-#pragma unroll
-                        for (int q = 0; q < KIN / 4; ++q) {   // tf32-rounded inputs straight from the operand tile
-                            const float4 xv = *reinterpret_cast<const float4*>(smem + P::kA + operand_offset<KP>(n, 4 * q));
-                            acc_w1[4 * q + 0] = fmaf(dh, xv.x, acc_w1[4 * q + 0]);
-                            acc_w1[4 * q + 1] = fmaf(dh, xv.y, acc_w1[4 * q + 1]);
-                            acc_w1[4 * q + 2] = fmaf(dh, xv.z, acc_w1[4 * q + 2]);
-                            acc_w1[4 * q + 3] = fmaf(dh, xv.w, acc_w1[4 * q + 3]);
-                        }
-                    }
-                }
-#pragma unroll
-                for (int k = 0; k < KIN; ++k) gw1[tr][k] += acc_w1[k];
-                gb1[tr] += acc_b1;
-                if (tr == 0) {
-                    gw2v += acc_w2[0];
-                    gb2 += acc_b2;
-                } else {
-#pragma unroll
-                    for (int a = 0; a < A; ++a) gw2p[a] += acc_w2[a];
-                }
-            }
-            __syncthreads();   // s_h (and after the second trunk: the operand tile, s_g, s_x) may be overwritten
-        }
-    }
-
-    // ---- this CTA's partial gradient, flat in state_dict order
-    float* dst = partials + (int64_t)blockIdx.x * P::kParams;
-#pragma unroll
-    for (int k = 0; k < KIN; ++k) {
-        dst[P::kOffV0w + j * KIN + k] = gw1[0][k];
-        dst[P::kOffP0w + j * KIN + k] = gw1[1][k];
-    }
-    dst[P::kOffV0b + j] = gb1[0];
-    dst[P::kOffP0b + j] = gb1[1];
-    dst[P::kOffV1w + j] = gw2v;
-#pragma unroll
-    for (int a = 0; a < A; ++a) dst[P::kOffP1w + a * kHidden + j] = gw2p[a];
-    if (j == 0) dst[P::kOffV1b] = gb2;
-    else if (j <= A) dst[P::kOffP1b + j - 1] = gb2;
-
-    tc_fence_before();
-    __syncthreads();
-    if (warp == 0) tmem_dealloc<512>(tmem_base);
-}
-
 // -------------------------------------------------------- backward on the tensor core
 //
 // dW1 = dh^T x, db1 = dh^T 1 and dW2 = relu(h)^T g are contractions over the ROWS of a tile, while tensor memory
@@ -527,7 +50,6 @@ __global__ void __launch_bounds__(kLearnThreads, 1) learner_bwd_kernel(const flo
 // whose accumulators stay in tensor memory over all tiles of the CTA.  No activation ever leaves the SM and the
 // CUDA cores do ~9 instructions per (row, hidden unit) instead of ~40.  Deterministic (fixed order everywhere).
 
-constexpr int kBwdTcThreads = 256;   // two threads per hidden unit (TMEM lane), 32 rows (columns) of a 64-row stage each
 
 // Two CTAs share an SM, one per trunk (256 TMEM columns each): while one waits for its MMAs the other runs its
 // elementwise stage.  A stage is (128-unit half of the trunk) x (64-row half of the tile).
@@ -581,253 +103,6 @@ __global__ void pack_bwd_tc_image_kernel(rnad_mlp_weights w, uint8_t* __restrict
         if (trunk == 1 && k >= 1 && k <= A) v = w.policy_fc1_w[(k - 1) * kHidden + j];
         *reinterpret_cast<float*>(image + P::kW2T + trunk * kHidden * 32 + operand_offset<8>(j, k)) = to_tf32(v);
     }
-}
-
-template <int A>
-__global__ void __launch_bounds__(kBwdTcThreads, 2) learner_bwd_tc_kernel(const float* __restrict__ obs, int64_t N,
-                                                                           int T_split, int64_t B_split,
-                                                                           const uint8_t* __restrict__ image,
-                                                                           const float* __restrict__ d_logit,
-                                                                           const float* __restrict__ d_v,
-                                                                           float* __restrict__ partials) {
-    using P = BwdTcPlan<A>;
-    constexpr int KIN = P::KIN, KP = P::KP;
-    constexpr int kSbo1 = (KP / 4) * 128;
-    static_assert(A <= 4, "g[n] is staged as 8 floats");
-    extern __shared__ __align__(1024) uint8_t smem[];
-    const int tid = threadIdx.x, warp = tid >> 5, lane32 = tid & 31;
-    const int trunk = blockIdx.x & 1;                         // 0: value trunk, 1: policy trunk
-    const int cta = blockIdx.x >> 1, n_ctas = gridDim.x >> 1; // the two CTAs of a pair walk the same tiles
-    const int quad = warp & 3, cpart = warp >> 2;             // TMEM lane quadrant (hidden units), 32-column (row) part of a stage
-    const int j_local = quad * 32 + lane32;                   // hidden unit of the current 128-unit half == TMEM lane
-    const uint32_t bar_img = smem_u32(smem + P::kBar), bar_mma = bar_img + 8;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + P::kTmem);
-
-    if (warp == 0) tmem_alloc<256>(tmem_slot);
-    if (tid == 0) {
-        mbar_init(bar_img, 1);
-        mbar_init(bar_mma, 1);
-        mbar_fence_init();
-        // this trunk's slices of the weight image: three bulk copies counted on one barrier
-        constexpr uint32_t kBytesIn = P::kTrunkBytes + kHidden * 4 + kHidden * 32;
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_img), "r"(kBytesIn) : "memory");
-        auto bulk = [&](int dst, const uint8_t* src, uint32_t bytes) {
-            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                             smem_u32(smem + dst)),
-                         "l"(src), "r"(bytes), "r"(bar_img)
-                         : "memory");
-        };
-        bulk(P::kSW1, image + P::kB + trunk * P::kTrunkBytes, P::kTrunkBytes);
-        bulk(P::kSB1, image + P::kB1 + trunk * kHidden * 4, kHidden * 4);
-        bulk(P::kSW2T, image + P::kW2T + trunk * kHidden * 32, kHidden * 32);
-    }
-    // operand rows that are never written stay zero
-    for (int i = tid; i < ((P::kNX + P::kNG) / 8) * P::kSboT / 4; i += kBwdTcThreads) reinterpret_cast<uint32_t*>(smem + P::kBX)[i] = 0u;
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    mbar_wait(bar_img, 0);
-    const uint32_t tmem_base = *tmem_slot;
-    const uint32_t tmem_lane = tmem_base + ((uint32_t)(quad * 32) << 16);
-    {   // clear the gradient accumulators: columns [128, 256), 64 per thread of a lane
-        uint32_t zero[32];
-#pragma unroll
-        for (int i = 0; i < 32; ++i) zero[i] = 0u;
-#pragma unroll
-        for (int q = 0; q < 2; ++q) tcp::tmem_st32(tmem_lane + 128 + cpart * 64 + q * 32, zero);
-        tcp::tmem_st_wait();
-    }
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-
-    const float* b1 = reinterpret_cast<const float*>(smem + P::kSB1);
-    auto off_t = [](int c, int n) { return (c >> 3) * P::kSboT + (n >> 2) * P::kLbo + (c & 7) * 16 + (n & 3) * 4; };
-    float gsum[1 + A];
-#pragma unroll
-    for (int a = 0; a <= A; ++a) gsum[a] = 0.f;
-    // this lane's hidden units (one per 128-unit half): first-layer bias where it does not ride in K
-    float bias_j[2];
-#pragma unroll
-    for (int half = 0; half < 2; ++half) bias_j[half] = P::kBiasInK ? 0.f : b1[half * 128 + j_local];
-
-    uint32_t phase = 0;
-    // Which tiles this CTA pair walks.  Flat mode (T_split == 0): tile u = rows [128 u, 128 u + 128) of the N rows, pair
-    // `cta` takes u = cta, cta + n_ctas, ...  Split mode (the rows are a (T_split, B_split) trajectory): tiles never
-    // straddle a half-move - half-move t has ceil(B / 128) tiles, the last one short - and pairs with an even index walk
-    // the tiles of even t (player 0's steps), pairs with an odd index those of odd t (player 1's): the per-pair partial
-    // sums then add up to one UNNORMALISED gradient per player (reduce_partials_kernel), which the caller divides by the
-    // global step counts after the exchange.
-    const bool split = T_split > 0;
-    const int player = split ? (cta & 1) : 0;
-    const int64_t tiles_per_t = split ? (B_split + kTileM - 1) / kTileM : 0;
-    const int64_t my_first = split ? (cta >> 1) : cta, my_stride = split ? (n_ctas >> 1) : n_ctas;
-    const int64_t num_tiles = split ? (int64_t)((T_split - player + 1) / 2) * tiles_per_t : (N + kTileM - 1) / kTileM;
-    // threads 0..127 own one row of every tile; its observation and output gradients, one tile ahead
-    float x_next[KIN], g_next[1 + A];
-    auto load_tile_row = [&](int64_t u) {
-        int64_t row = u * kTileM + tid;
-        bool active = u < num_tiles && row < N;
-        if (split) {
-            const int64_t tt = 2 * (u / tiles_per_t) + player, j = (u % tiles_per_t) * kTileM + tid;
-            row = tt * B_split + j;
-            active = u < num_tiles && j < B_split;
-        }
-        load_row<KIN>(obs, active ? row : 0, active, x_next);
-        g_next[0] = active ? __ldg(d_v + row) : 0.f;
-#pragma unroll
-        for (int a = 0; a < A; ++a) g_next[1 + a] = active ? __ldg(d_logit + row * A + a) : 0.f;
-    };
-    if (tid < kTileM) load_tile_row(my_first);
-    for (int64_t tile = my_first; tile < num_tiles; tile += my_stride) {
-        // ---- the tile's operands: observation tile (B of the recompute), x^T | 1 and g^T (B of the gradient MMAs);
-        //      the row's data was loaded one tile ahead, the next tile's loads are issued right after it is consumed
-        if (tid < kTileM) {
-            const int n = tid;
-            float x[KIN], g[1 + A];
-#pragma unroll
-            for (int k = 0; k < KIN; ++k) x[k] = x_next[k];
-#pragma unroll
-            for (int a = 0; a <= A; ++a) g[a] = g_next[a];
-            load_tile_row(tile + my_stride);
-            store_operand_row<KIN, KP, P::kBiasInK>(smem + P::kX, n, x);
-#pragma unroll
-            for (int k = 0; k < KIN; ++k) *reinterpret_cast<float*>(smem + P::kBX + off_t(k, n)) = to_tf32_fast(x[k]);
-            *reinterpret_cast<float*>(smem + P::kBX + off_t(KIN, n)) = 1.f;
-            float g8[8];
-#pragma unroll
-            for (int a = 0; a < 8; ++a) g8[a] = a <= A ? to_tf32_fast(g[a < 1 + A ? a : 0]) : 0.f;
-#pragma unroll
-            for (int a = 0; a <= A; ++a) {
-                *reinterpret_cast<float*>(smem + P::kBG + off_t(a, n)) = g8[a];
-                gsum[a] += g[a];
-            }
-            // the same values row-major, as the B operand of S^T = W2^T . G^T
-            *reinterpret_cast<float4*>(smem + P::kG + operand_offset<8>(n, 0)) = make_float4(g8[0], g8[1], g8[2], g8[3]);
-            *reinterpret_cast<float4*>(smem + P::kG + operand_offset<8>(n, 4)) = make_float4(g8[4], g8[5], g8[6], g8[7]);
-            fence_async_smem();
-        }
-        tc_fence_before();
-        __syncthreads();
-
-        // stage st = (hidden half, row half).  H^T = W1[half] . X^T[rows]  (M = hidden units, N = 64 rows, K = inputs)
-        // into columns [0, 64);  S^T = W2^T[half] . G^T[rows] = (g W2)^T (K = the 1 + A outputs) into columns [64, 128)
-        auto recompute = [&](int st) {
-            const int half = st >> 1, rh = st & 1;
-            const uint32_t a_base = smem_u32(smem + P::kSW1) + half * (128 / 8) * kSbo1;
-            const uint32_t b_base = smem_u32(smem + P::kX) + rh * (64 / 8) * kSbo1;
-#pragma unroll
-            for (int ks = 0; ks < KP / 8; ++ks)
-                mma_ss_n(tmem_base, make_desc<KP>(a_base + ks * 256), make_desc<KP>(b_base + ks * 256), idesc_tf32(64), ks > 0);
-            mma_ss_n(tmem_base + 64, make_desc<8>(smem_u32(smem + P::kSW2T) + half * 128 * 32),
-                     make_desc<8>(smem_u32(smem + P::kG) + rh * 64 * 32), idesc_tf32(64), false);
-        };
-        // (the whole warp runs this converged and one ELECTED lane issues: behind an `if (tid == 0)` ptxas wraps every
-        //  UTCHMMA in a waterfall loop and the issue rate drops to one MMA per ~75 cycles)
-        if (warp == 0) {
-            tc_fence_after();
-            if (tcp::elect_one()) {
-                recompute(0);
-                mma_commit(bar_mma);
-            }
-            __syncwarp();
-        }
-#pragma unroll 1
-        for (int st = 0; st < 4; ++st) {
-            const int half = st >> 1, rh = st & 1;
-            const float bias = half ? bias_j[1] : bias_j[0];
-            mbar_wait(bar_mma, phase);                        // H^T, S^T of this stage (and the gradient MMAs of the previous one)
-            phase ^= 1u;
-            tc_fence_after();
-            // ---- this thread's 32 rows of its hidden unit: relu^T over H^T, dh^T = S^T where h > 0, both in place
-            //      (the tensor core truncates these fp32 A operands to tf32)
-            uint32_t hr[32], dh[32];
-            tmem_ld32(tmem_lane + cpart * 32, hr);
-            tmem_ld32(tmem_lane + 64 + cpart * 32, dh);
-            tmem_ld_wait();
-#pragma unroll
-            for (int i = 0; i < 32; ++i) {
-                const float h = __uint_as_float(hr[i]) + bias;
-                const bool on = h > 0.f;
-                hr[i] = on ? __float_as_uint(h) : 0u;
-                dh[i] = on ? dh[i] : 0u;
-            }
-            tcp::tmem_st32(tmem_lane + cpart * 32, hr);
-            tcp::tmem_st32(tmem_lane + 64 + cpart * 32, dh);
-            tcp::tmem_st_wait();
-            tc_fence_before();
-            __syncthreads();
-            // ---- D_w2[half] += relu^T BG^T, D_w1[half] += dh^T BX^T (K = the stage's 64 rows), then the next stage's
-            //      H^T / S^T: the tensor core executes one thread's MMAs in order, so the recompute may overwrite the
-            //      columns right behind the MMAs that read them, and one commit covers the three groups
-            if (warp == 0) {
-                tc_fence_after();
-                const uint64_t bx = desc_lbo_sbo(smem_u32(smem + P::kBX) + rh * 16 * P::kLbo, P::kLbo, P::kSboT);
-                const uint64_t bg = desc_lbo_sbo(smem_u32(smem + P::kBG) + rh * 16 * P::kLbo, P::kLbo, P::kSboT);
-                if (tcp::elect_one()) {
-#pragma unroll
-                    for (int ks = 0; ks < 8; ++ks)
-                        tcp::mma_ts(tmem_base + P::kColW2 + half * P::kNG, tmem_base + ks * 8, bg + (uint64_t)((ks * 2 * P::kLbo) >> 4),
-                                    idesc_tf32(P::kNG), true);
-#pragma unroll
-                    for (int ks = 0; ks < 8; ++ks)
-                        tcp::mma_ts(tmem_base + P::kColW1 + half * P::kNX, tmem_base + 64 + ks * 8,
-                                    bx + (uint64_t)((ks * 2 * P::kLbo) >> 4), idesc_tf32(P::kNX), true);
-                    if (st < 3) recompute(st + 1);
-                    mma_commit(bar_mma);
-                }
-                __syncwarp();
-            }
-        }
-        mbar_wait(bar_mma, phase);                            // the last gradient MMAs have read the tile's operands
-        phase ^= 1u;
-        tc_fence_after();
-        __syncthreads();
-    }
-
-    // ---- this CTA's share of the pair's partial gradient, flat in state_dict order
-    float* dst = partials + (int64_t)cta * P::kParams;
-    if (cpart == 0) {
-#pragma unroll 1
-        for (int half = 0; half < 2; ++half) {
-            const int j = half * 128 + j_local;
-            uint32_t acc[P::kNX];
-#pragma unroll
-            for (int q = 0; q < P::kNX / 16; ++q) tmem_ld16(tmem_lane + P::kColW1 + half * P::kNX + q * 16, acc + q * 16);
-            tmem_ld_wait();
-            float* w1_dst = dst + (trunk == 0 ? P::kOffV0w : P::kOffP0w) + j * KIN;
-#pragma unroll
-            for (int k = 0; k < KIN; ++k) w1_dst[k] = __uint_as_float(acc[k]);
-            dst[(trunk == 0 ? P::kOffV0b : P::kOffP0b) + j] = __uint_as_float(acc[KIN]);
-            uint32_t acc2[16];
-            tmem_ld16(tmem_lane + P::kColW2 + half * P::kNG, acc2);
-            tmem_ld_wait();
-            if (trunk == 0) {
-                dst[P::kOffV1w + j] = __uint_as_float(acc2[0]);
-            } else {
-#pragma unroll
-                for (int a = 0; a < A; ++a) dst[P::kOffP1w + a * kHidden + j] = __uint_as_float(acc2[1 + a]);
-            }
-        }
-    }
-    // output-bias gradients: sums of g over the CTA's rows (threads 0..127 each own one row of every tile)
-    float* s_red = reinterpret_cast<float*>(smem + P::kRed);
-    if (tid < kTileM) {
-#pragma unroll
-        for (int a = 0; a <= A; ++a) {
-            const float v = warp_sum(gsum[a]);
-            if (lane32 == 0) s_red[warp * 8 + a] = v;
-        }
-    }
-    __syncthreads();
-    if (tid <= A) {
-        const float v = (s_red[0 * 8 + tid] + s_red[1 * 8 + tid]) + (s_red[2 * 8 + tid] + s_red[3 * 8 + tid]);
-        if (tid == 0 && trunk == 0) dst[P::kOffV1b] = v;
-        if (tid > 0 && trunk == 1) dst[P::kOffP1b + tid - 1] = v;
-    }
-    tc_fence_before();
-    __syncthreads();
-    if (warp == 0) tmem_dealloc<256>(tmem_base);
 }
 
 // -------------------------------------------------------- backward, software-pipelined
@@ -1200,11 +475,10 @@ __global__ void reduce_partials_kernel(const float* __restrict__ partials, int n
 }
 
 
-// the forward kernels' weight image sits at the start of the workspace: room for the larger of the two builds
+// the forward kernel's weight image (learner_fwd_tc2.cu) sits at the start of the workspace
 template <int A>
 int64_t fwd_image_reserve() {
-    const int64_t v1 = FwdPlan<A>::kImageBytes, v2 = learner_forward_tc2_image_bytes(A);
-    return round_up((int)(v1 > v2 ? v1 : v2), 256);
+    return round_up((int)learner_forward_tc2_image_bytes(A), 256);
 }
 
 // then the backward's images: the tf32 one (pack_bwd_tc_image_kernel) and, where that engine exists, the fp16 one
@@ -1226,109 +500,61 @@ int prepare(Kernel kernel, size_t smem, const char* what) {
                                            cudaSharedmemCarveoutMaxShared), what);
 }
 
-template <int A>
-int launch_forward(const float* obs, int64_t N, const FwdNets& nets, const FwdOut& out, uint8_t* workspace,
-                   cudaStream_t st) {
-    using P = FwdPlan<A>;
-    static_assert(P::kBytes <= 227 * 1024, "forward image does not fit in shared memory");
-    pack_fwd_image_kernel<A><<<48, 256, 0, st>>>(nets, workspace);
-    RNAD_CHECK_LAUNCH("pack_fwd_image_kernel");
-    int rc = prepare<A>(learner_fwd_kernel<A>, P::kBytes, "cudaFuncSetAttribute(learner_fwd)");
-    if (rc) return rc;
-    int64_t blocks = (N + kTileM - 1) / kTileM;
-    if (blocks > sm_count()) blocks = sm_count();
-    learner_fwd_kernel<A><<<(int)blocks, kLearnThreads, P::kBytes, st>>>(obs, N, workspace, out);
-    RNAD_CHECK_LAUNCH("learner_fwd_kernel");
-    return RNAD_OK;
-}
-
 // T_split > 0: the rows are a (T_split, B_split) trajectory and flat_grad receives TWO unnormalised gradients,
-// player 0's (rows of even t) then player 1's (see learner_bwd_tc_kernel).
+// player 0's (rows of even t) then player 1's.  mode (as in learner_fwd_tc2.cu): 0 pack + run, 1 prepacked, 2 pack only.
 template <int A>
 int launch_backward(const float* obs, int64_t N, int T_split, int64_t B_split, const rnad_mlp_weights& w,
                     const float* d_logit, const float* d_v, float* flat_grad, uint8_t* workspace, cudaStream_t st,
                     int mode = 0) {
-    using P = BwdPlan<A>;
+    using P = Shape<A>;
     using PT = BwdTcPlan<A>;
-    static_assert(PT::kImageBytes >= P::kImageBytes, "the workspace reserves the larger image");
     uint8_t* image = workspace + fwd_image_reserve<A>();
     uint8_t* image_f16 = image + round_up(PT::kImageBytes, 256);
     float* partials = reinterpret_cast<float*>(image + bwd_image_reserve<A>());
     int64_t blocks = (N + kTileM - 1) / kTileM;
     const int cap = sm_count() < kMaxBwdCtas ? sm_count() : kMaxBwdCtas;
     if (T_split > 0) {
-        // an even number of CTA pairs, half of them per player; at least one pair each (a player without rows writes zeros)
+        // an even number of CTAs, half of them per player; at least one each (a player without rows writes zeros)
         const int64_t per_player = (int64_t)((T_split + 1) / 2) * ((B_split + kTileM - 1) / kTileM);
         blocks = 2 * (per_player < cap / 2 ? per_player : cap / 2);
     } else if (blocks > cap) {
         blocks = cap;
     }
-    static const bool cuda_core_reduction = getenv("RNAD_LEARNER_BWD_CUDA_CORES") != nullptr;   // the previous kernel, for A/B runs
-    if (cuda_core_reduction && T_split == 0 && mode == 0) {
-        pack_bwd_image_kernel<A><<<24, 256, 0, st>>>(w, image);
-        RNAD_CHECK_LAUNCH("pack_bwd_image_kernel");
-        int rc = prepare<A>(learner_bwd_kernel<A>, P::kBytes, "cudaFuncSetAttribute(learner_bwd)");
+    const dim3 reduce_grid((P::kParams * 8 + 255) / 256, T_split > 0 ? 2 : 1);
+    // split mode (one UNNORMALISED gradient per player: the learner step) runs on the fp16-operand engine
+    // (learner_bwd_f16.cu) where it exists; RNAD_LEARNER_BWD_TF32 keeps the tf32 kernels there too, for A/B runs
+    static const bool v2 = getenv("RNAD_LEARNER_BWD_V2") != nullptr;         // the S^T formulation where the mask one fits, for A/B runs
+    static const bool tf32_only = getenv("RNAD_LEARNER_BWD_TF32") != nullptr || v2;
+    const bool f16_engine = !tf32_only && learner_backward_f16_supported(A);
+    if (f16_engine && (T_split > 0 || mode == 2)) {
+        int rc = learner_backward_f16(A, obs, N, T_split, B_split, w, d_logit, d_v, image_f16, partials, (int)blocks, st, mode);
         if (rc) return rc;
-        learner_bwd_kernel<A><<<(int)blocks, kLearnThreads, P::kBytes, st>>>(obs, N, image, w, d_logit, d_v, partials);
-        RNAD_CHECK_LAUNCH("learner_bwd_kernel");
-    } else {
-        // split mode (one UNNORMALISED gradient per player: the learner step) runs on the fp16-operand engine
-        // (learner_bwd_f16.cu) where it exists; RNAD_LEARNER_BWD_TF32 keeps the tf32 kernels there too, for A/B runs
-        static const bool tf32_only = getenv("RNAD_LEARNER_BWD_TF32") != nullptr || getenv("RNAD_LEARNER_BWD_V1") != nullptr ||
-                                      getenv("RNAD_LEARNER_BWD_V2") != nullptr;
-        const bool f16_engine = !tf32_only && learner_backward_f16_supported(A);
-        if (f16_engine && (T_split > 0 || mode == 2)) {
-            int rc = learner_backward_f16(A, obs, N, T_split, B_split, w, d_logit, d_v, image_f16, partials, (int)blocks, st, mode);
-            if (rc) return rc;
-            if (mode != 2) {
-                reduce_partials_kernel<<<dim3((P::kParams * 8 + 255) / 256, 2), 256, 0, st>>>(partials, (int)blocks, P::kParams, flat_grad);
-                RNAD_CHECK_LAUNCH("reduce_partials_kernel");
-            }
-            return RNAD_OK;      // (pack only: the prepacked entry point is the split one, which this engine serves)
-        }
-        if (mode != 1) {      // (mode as in learner_fwd_tc2.cu: 0 pack + run, 1 prepacked, 2 pack only)
-            pack_bwd_tc_image_kernel<A><<<32, 256, 0, st>>>(w, image);
-            RNAD_CHECK_LAUNCH("pack_bwd_tc_image_kernel");
-            if (mode == 2) return RNAD_OK;
-        }
-        static const bool two_ctas = getenv("RNAD_LEARNER_BWD_V1") != nullptr;   // the first kernel (two CTAs per SM), for A/B runs
-        static const bool v2 = getenv("RNAD_LEARNER_BWD_V2") != nullptr;         // the S^T formulation where the mask one fits, for A/B runs
-        static_assert(PT::kB == 0 && PT::kB1 == 2 * PT::kTrunkBytes, "learner_bwd_tc3.cu reads the head of this image");
-        if (!two_ctas && !v2 && learner_backward_tc3_supported(A)) {
-            int rc = learner_backward_tc3(A, obs, N, T_split, B_split, w, d_logit, d_v, image, partials, (int)blocks, st);
-            if (rc) return rc;
-            reduce_partials_kernel<<<dim3((P::kParams * 8 + 255) / 256, T_split > 0 ? 2 : 1), 256, 0, st>>>(
-                partials, (int)blocks, P::kParams, flat_grad);
+        if (mode != 2) {
+            reduce_partials_kernel<<<reduce_grid, 256, 0, st>>>(partials, (int)blocks, P::kParams, flat_grad);
             RNAD_CHECK_LAUNCH("reduce_partials_kernel");
-            return RNAD_OK;
         }
-        if (!two_ctas) {
-            using P2 = BwdTc2Plan<A>;
-            // one CTA per SM (all 512 tensor-memory columns): more than half of the shared memory keeps a second one out
-            const size_t smem2 = P2::kBytes > 116 * 1024 ? P2::kBytes : 116 * 1024;
-            int rc = prepare<A>(learner_bwd_tc2_kernel<A>, smem2, "cudaFuncSetAttribute(learner_bwd_tc2)");
-            if (rc) return rc;
-            learner_bwd_tc2_kernel<A><<<(int)blocks, kBwd2Threads, smem2, st>>>(obs, N, T_split, B_split, image, d_logit, d_v,
-                                                                               partials);
-            RNAD_CHECK_LAUNCH("learner_bwd_tc2_kernel");
-            reduce_partials_kernel<<<dim3((P::kParams * 8 + 255) / 256, T_split > 0 ? 2 : 1), 256, 0, st>>>(
-                partials, (int)blocks, P::kParams, flat_grad);
-            RNAD_CHECK_LAUNCH("reduce_partials_kernel");
-            return RNAD_OK;
-        }
-        // two CTAs per SM (one per trunk, 256 TMEM columns each): pad the shared-memory request so that a third can
-        // never become resident and spin inside tcgen05.alloc
-        size_t smem = PT::kBytes;
-        const size_t floor_two_per_sm = 227 * 1024 / 3 + 1024;
-        if (smem < floor_two_per_sm) smem = floor_two_per_sm;
-        int rc = prepare<A>(learner_bwd_tc_kernel<A>, smem, "cudaFuncSetAttribute(learner_bwd_tc)");
-        if (rc) return rc;
-        learner_bwd_tc_kernel<A><<<2 * (int)blocks, kBwdTcThreads, smem, st>>>(obs, N, T_split, B_split, image, d_logit,
-                                                                               d_v, partials);
-        RNAD_CHECK_LAUNCH("learner_bwd_tc_kernel");
+        return RNAD_OK;      // (pack only: the prepacked entry point is the split one, which this engine serves)
     }
-    reduce_partials_kernel<<<dim3((P::kParams * 8 + 255) / 256, T_split > 0 ? 2 : 1), 256, 0, st>>>(
-        partials, (int)blocks, P::kParams, flat_grad);
+    if (mode != 1) {
+        pack_bwd_tc_image_kernel<A><<<32, 256, 0, st>>>(w, image);
+        RNAD_CHECK_LAUNCH("pack_bwd_tc_image_kernel");
+        if (mode == 2) return RNAD_OK;
+    }
+    static_assert(PT::kB == 0 && PT::kB1 == 2 * PT::kTrunkBytes, "learner_bwd_tc3.cu reads the head of this image");
+    if (!v2 && learner_backward_tc3_supported(A)) {
+        int rc = learner_backward_tc3(A, obs, N, T_split, B_split, w, d_logit, d_v, image, partials, (int)blocks, st);
+        if (rc) return rc;
+    } else {
+        using P2 = BwdTc2Plan<A>;
+        // one CTA per SM (all 512 tensor-memory columns): more than half of the shared memory keeps a second one out
+        const size_t smem2 = P2::kBytes > 116 * 1024 ? P2::kBytes : 116 * 1024;
+        int rc = prepare<A>(learner_bwd_tc2_kernel<A>, smem2, "cudaFuncSetAttribute(learner_bwd_tc2)");
+        if (rc) return rc;
+        learner_bwd_tc2_kernel<A><<<(int)blocks, kBwd2Threads, smem2, st>>>(obs, N, T_split, B_split, image, d_logit, d_v,
+                                                                           partials);
+        RNAD_CHECK_LAUNCH("learner_bwd_tc2_kernel");
+    }
+    reduce_partials_kernel<<<reduce_grid, 256, 0, st>>>(partials, (int)blocks, P::kParams, flat_grad);
     RNAD_CHECK_LAUNCH("reduce_partials_kernel");
     return RNAD_OK;
 }
@@ -1380,20 +606,12 @@ static int learner_forward_impl(const float* observations, int64_t N, int A, con
     }
     RNAD_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "rnad_learner_forward: workspace must be 256-byte aligned");
     if (N == 0) return RNAD_OK;
-    static const bool v1 = getenv("RNAD_LEARNER_FWD_V1") != nullptr;   // the previous kernel, for A/B runs
-    if (!v1 && learner_forward_tc2_supported(A, net->width))
-        return learner_forward_tc2(observations, N, A, net, target, reg, reg_, out, workspace, (cudaStream_t)stream,
-                                   prepacked ? 1 : 0, others_only != 0);
-    RNAD_REQUIRE(!prepacked && !others_only, "rnad_learner_forward_prepacked: not available with RNAD_LEARNER_FWD_V1");
-    tc::FwdNets nets{*net, *target, *reg, *reg_};
-    tc::FwdOut o{out->logit, out->pi, out->log_pi, out->v, out->v_target, out->log_pi_reg, out->log_pi_reg_};
-    cudaStream_t st = (cudaStream_t)stream;
-    switch (A) {
-        case 2: return tc::launch_forward<2>(observations, N, nets, o, (uint8_t*)workspace, st);
-        case 3: return tc::launch_forward<3>(observations, N, nets, o, (uint8_t*)workspace, st);
-        case 4: return tc::launch_forward<4>(observations, N, nets, o, (uint8_t*)workspace, st);
+    if (!learner_forward_tc2_supported(A, net->width)) {
+        set_error("rnad_learner_forward: no forward engine for max_actions %d, width %d", A, net->width);
+        return RNAD_EUNSUPPORTED;
     }
-    return RNAD_EINVAL;
+    return learner_forward_tc2(observations, N, A, net, target, reg, reg_, out, workspace, (cudaStream_t)stream,
+                               prepacked ? 1 : 0, others_only != 0);
 }
 
 int rnad_learner_forward(const float* observations, int64_t N, int A, const rnad_mlp_weights* net,
