@@ -241,23 +241,28 @@ class RolloutRunner:
 
 
 def timed_steps(fn, steps, warmup, flush, barrier):
-    """W warm-up calls, then K calls each bracketed by CUDA events on the current stream, L2 flushed in between."""
+    """
+    W warm-up calls, then K calls each bracketed by its own pair of CUDA events on the current stream, the L2 flushed
+    in between (outside the brackets).  The events exist before the loop and nothing synchronises inside it (unless
+    `fn` itself does, as the end-to-end step must): the flush keeps the GPU busy while the host enqueues the next
+    bracket, so a bracket holds device time only - not the host's launch latency, which grows when eight ranks share
+    the box's cores.
+    """
     for _ in range(warmup):
         fn()
     torch.cuda.synchronize()
     barrier()
     torch.cuda.synchronize()
-    total_ms = 0.0
+    starts = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
+    stops = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
     wall0 = time.perf_counter()
-    for _ in range(steps):
+    for start, stop in zip(starts, stops):
         flush()
-        start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         start.record()
         fn()
         stop.record()
-        stop.synchronize()
-        total_ms += start.elapsed_time(stop)
     torch.cuda.synchronize()
+    total_ms = sum(start.elapsed_time(stop) for start, stop in zip(starts, stops))
     barrier()
     torch.cuda.synchronize()
     return total_ms, time.perf_counter() - wall0

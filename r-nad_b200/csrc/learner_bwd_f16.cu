@@ -219,7 +219,18 @@ __global__ void __launch_bounds__(kThreadsH, 1) learner_bwd_f16_kernel(const flo
     // stage s of a CTA's stream: tile k = s >> 3; region r = s & 3 = (trunk << 1 | hidden half) - also the issuer warp, the
     // consumer group and the accumulator pair of the stage; row half = (s >> 2) & 1.  A region sees the stages r, r + 4, ...
     const uint32_t n_st = (uint32_t)n_stages;
-    auto hand_over = [](int r) { asm volatile("bar.sync %0, %1;" ::"r"(1 + r), "n"(kGroupThreads) : "memory"); };   // consumer group r <-> issuer r
+    // consumer group r -> issuer r: a hardware named barrier of kGroupThreads threads; the consumers ARRIVE (they do not
+    // wait for the issuer), the issuer SYNCs.  (.aligned: the warp must be converged - the compiler does not know that
+    // about inline PTX, and a polling loop may have left it diverged, hence the __syncwarp.)  The barrier is free for the
+    // group's next stage in time: that stage's H^T only exists once the issuer is past this sync.
+    auto hand_over_arrive = [](int r) {
+        __syncwarp();
+        asm volatile("bar.arrive %0, %1;" ::"r"(1 + r), "n"(kGroupThreads) : "memory");
+    };
+    auto hand_over_sync = [](int r) {
+        __syncwarp();
+        asm volatile("bar.sync %0, %1;" ::"r"(1 + r), "n"(kGroupThreads) : "memory");
+    };
 
     if (tid >= kConsumers + kProducers) {
         // ------------------------------------------------------------ issuers: warp r issues the stages with s & 3 == r
@@ -281,7 +292,7 @@ __global__ void __launch_bounds__(kThreadsH, 1) learner_bwd_f16_kernel(const flo
                 need_tile((s + kRegions) >> 3);
             }
             HTR(2, s, 0);
-            hand_over(r);                                               // relu^T | M^T of stage s are in the region
+            hand_over_sync(r);                                          // relu^T | M^T of stage s are in the region
             tc_fence_after();
             HTR(2, s, 1);
             if (tcp::elect_one()) {
@@ -423,12 +434,13 @@ __global__ void __launch_bounds__(kThreadsH, 1) learner_bwd_f16_kernel(const flo
             tcp::tmem_st_wait();
             if (tr) HTR(0, s, 2);
             tc_fence_before();
-            hand_over(r);                                           // -> grad(s), recompute(s + 4)
+            hand_over_arrive(r);                                    // -> grad(s), recompute(s + 4)
             if (tr) HTR(0, s, 3);
         }
         // every gradient MMA of the region complete: its issuer's last commit; then the groups meet
         if (n_st >= (uint32_t)kRegions) tcp::mbar_wait_c(bar_h(r), (n_st >> 2) & 1u);
         tc_fence_before();
+        __syncwarp();
         asm volatile("bar.sync 5, %0;" ::"n"(kConsumers) : "memory");
         tc_fence_after();
 

@@ -302,6 +302,7 @@ __global__ void __launch_bounds__(kThreads3, 1) learner_bwd_tc3_kernel(const flo
         if (kGroups == 2) {
             if (n_stages >= 2) tcp::mbar_wait_c(bar_r(group), (uint32_t)(n_stages >> 1) & 1u);
             tc_fence_before();
+            __syncwarp();
             asm volatile("bar.sync 1, %0;" ::"n"(kConsumers) : "memory");
         } else if (n_stages >= 2) {
             tcp::mbar_wait_c(bar_r(0), (uint32_t)(n_stages >> 1) & 1u);
