@@ -168,6 +168,25 @@ __global__ void __cluster_dims__(kTailCtas, 1, 1) __launch_bounds__(kTailThreads
         for (int r = 0; r < a.world; ++r) acc += __ldcg(a.xchg[a.rank] + ((int64_t)slot * a.world + r) * row_floats + i);
         return acc;
     };
+    // ---- pass 1: the gradient (vtrace.py:370-374, 387-389: each player's sum over its own step count) and its norm.
+    //      Everything pass 2 needs is fetched here as well, and BEFORE the block waits for the step counts and Adam's
+    //      scalars (two double-precision pow on one thread): one round of independent loads per thread, in flight
+    //      under that arithmetic.
+    constexpr int kMaxPer = 4;                   // up to 32,768 parameters
+    float g[kMaxPer], g1[kMaxPer], m[kMaxPer], v[kMaxPer], p[kMaxPer], t[kMaxPer];
+#pragma unroll
+    for (int u = 0; u < kMaxPer; ++u) {
+        const int i = gtid + u * n_threads;
+        g[u] = g1[u] = m[u] = v[u] = p[u] = t[u] = 0.f;
+        if (i < P) {
+            g[u] = total(i);
+            g1[u] = total(P + i);
+            m[u] = a.exp_avg[i];
+            v[u] = a.exp_avg_sq[i];
+            p[u] = a.params[i];
+            t[u] = a.target_params[i];
+        }
+    }
     if (tid < 8) s_stats[tid] = total(2 * P + tid);
     if (tid == 32) {     // Adam's scalars, once per CTA, in double like torch's host-side arithmetic
         const double step = (double)a.ctrl->adam_step + 1.0;
@@ -178,24 +197,9 @@ __global__ void __cluster_dims__(kTailCtas, 1, 1) __launch_bounds__(kTailThreads
     }
     __syncthreads();
     const float n0 = fmaxf(s_stats[0] * 4096.f + s_stats[1], 1.f), n1 = fmaxf(s_stats[2] * 4096.f + s_stats[3], 1.f);
-
-    // ---- pass 1: the gradient (vtrace.py:370-374, 387-389: each player's sum over its own step count) and its norm.
-    //      Everything pass 2 needs is fetched here as well: one round of independent loads per thread.
-    constexpr int kMaxPer = 4;                   // up to 32,768 parameters
-    float g[kMaxPer], m[kMaxPer], v[kMaxPer], p[kMaxPer], t[kMaxPer];
     float sq = 0.f;
 #pragma unroll
-    for (int u = 0; u < kMaxPer; ++u) {
-        const int i = gtid + u * n_threads;
-        g[u] = m[u] = v[u] = p[u] = t[u] = 0.f;
-        if (i < P) {
-            g[u] = total(i) / n0 + total(P + i) / n1;
-            m[u] = a.exp_avg[i];
-            v[u] = a.exp_avg_sq[i];
-            p[u] = a.params[i];
-            t[u] = a.target_params[i];
-        }
-    }
+    for (int u = 0; u < kMaxPer; ++u) g[u] = g[u] / n0 + g1[u] / n1;      // (0 / n + 0 / n = 0 beyond the last parameter)
 #pragma unroll
     for (int u = 0; u < kMaxPer; ++u) sq = fmaf(g[u], g[u], sq);
     sq = warp_sum(sq);
@@ -236,15 +240,17 @@ __global__ void __cluster_dims__(kTailCtas, 1, 1) __launch_bounds__(kTailThreads
     cluster_sync();                              // every CTA has read ctrl and its peers' partial sums
     if (cta == 0 && tid == 0) {
         // loss = sum over players of (its numerator / its step count); the NeuRD loss carries a minus sign (vtrace.py:429)
-        a.losses[0] = s_stats[4] / n0 + s_stats[5] / n1;
-        a.losses[1] = -(s_stats[6] / n0 + s_stats[7] / n1);
+        const float loss_v = s_stats[4] / n0 + s_stats[5] / n1, loss_nerd = -(s_stats[6] / n0 + s_stats[7] / n1);
+        const float err = (float)a.ctrl->error;
+        a.losses[0] = loss_v;
+        a.losses[1] = loss_nerd;
         a.losses[2] = norm;
-        a.losses[3] = (float)a.ctrl->error;
+        a.losses[3] = err;
         if (a.losses_host != nullptr) {
-            a.losses_host[0] = a.losses[0];
-            a.losses_host[1] = a.losses[1];
+            a.losses_host[0] = loss_v;
+            a.losses_host[1] = loss_nerd;
             a.losses_host[2] = norm;
-            a.losses_host[3] = a.losses[3];
+            a.losses_host[3] = err;
         }
         a.ctrl->seq = seq + 1u;
         a.ctrl->adam_step = s_adam[2];
