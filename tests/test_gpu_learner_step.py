@@ -256,6 +256,35 @@ def test_on_policy_step_reuses_the_rollouts_own_net_outputs():
     close(step.loss_sums, sums, rtol=1e-5, atol=1e-4)
 
 
+def test_step_engine_follows_changes_of_what_it_captured():
+    """The captured step bakes hyper-parameters, nets and the optimizer in.  RNaD compares a cheap fingerprint every step
+    (no walk over the modules) and must build a new engine when any of it changes - and keep the old one otherwise."""
+    from nn.net import MLP
+
+    tree = seeded_tree()
+    trial = fresh_trial(tree, 1024, "pytest_step_key", "graph")
+    for i in range(3):
+        torch.manual_seed(40 + i)
+        trial.learner_step(alpha=0.5)
+    first = trial._step
+    assert first is not None and first.graph is not None
+    trial.learner_step(alpha=0.5)
+    assert trial._step is first                                  # nothing changed: the same engine, the fast path
+    trial.eta = 0.3                                              # a hyper-parameter the targets kernel takes by value
+    trial.learner_step(alpha=0.5)
+    second = trial._step
+    assert second is not first and abs(second._params.eta - 0.3) < 1e-7
+    trial.optimizer.param_groups[0]["lr"] = 5e-4                 # the tail kernel's learning rate
+    trial.learner_step(alpha=0.5)
+    third = trial._step
+    assert third is not second and abs(third._tail.lr - 5e-4) < 1e-10
+    trial.net_reg = MLP(3, 256, device=torch.device(DEV))        # another regularisation net (as at the end of an eta)
+    trial.learner_step(alpha=0.5)
+    assert trial._step is not third
+    torch.cuda.synchronize()
+    assert bool(torch.isfinite(flat(trial.net)).all())
+
+
 def test_logging_step_in_between_keeps_the_optimizer_state_consistent():
     """A step on the step-by-step path (as wandb logging takes) between graph steps shares params, moments and step count."""
     tree = seeded_tree()
