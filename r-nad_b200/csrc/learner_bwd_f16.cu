@@ -132,8 +132,8 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* r) {
 }
 
 #ifdef RNAD_TRACE_BWD
-// development aid (scripts/trace_bwd_f16.py): cycle stamps of CTA 0, stages 16..79: [role][stage - 16][event]; role 0 / 1 =
-// first warp of consumer group 0 / 1, 2 / 3 = issuer 0 / 1, 4 = producer warp 0 (per tile, at its first stage)
+// development aid (scripts/trace_bwd_f16.py): cycle stamps of CTA 0, stages 16..79: [role][stage - 16][event]; role 0 =
+// first warp of consumer group 0 (its stages only), 2 = the stage's issuer, 4 = producer warp 0 (per tile, at its first stage)
 __device__ long long g_bwdh_trace[5][64][8];
 #define HTR(role, s, ev) do { if (blockIdx.x == 0 && (s) >= 16 && (s) < 80 && lane32 == 0) g_bwdh_trace[role][(s) - 16][ev] = clock64(); } while (0)
 #else

@@ -27,14 +27,15 @@ torch.cuda.synchronize()
 buf = np.zeros((5, 64, 8), dtype=np.int64)
 L.rnad_debug_bwdh_trace.argtypes = [ctypes.c_void_p]
 assert L.rnad_debug_bwdh_trace(buf.ctypes.data) == 0
-t0 = buf[0, 0, 0]
+t0 = buf[0, 0, 0]      # consumer group 0, stage 16, wait start
 np.set_printoptions(linewidth=250)
-print("stage | consumer group (s&1), first warp: wait start, H seen, loads back, packed + RM free, stores done, arrived | issuer (s&1): loop top, H free seen, recompute issued, RM seen, grads issued")
+print("stage (region = s & 3) | issuer of the region: loop top, hand-over passed, grads + next recompute issued | "
+      "region 0 only - first consumer warp: wait start, H seen, stored, arrived at the hand-over")
 for j in range(48):
     s = j + 16
-    c0 = " ".join(f"{x - t0:7d}" for x in buf[s & 1, j, :6])
-    iss = " ".join(f"{x - t0:7d}" for x in buf[2 + (s & 1), j, :5])
-    print(f"{s:4d} | {c0} | {iss}")
+    iss = " ".join(f"{x - t0:7d}" for x in buf[2, j, :3])
+    con = " ".join(f"{x - t0:7d}" for x in buf[0, j, :4]) if s % 4 == 0 else ""
+    print(f"{s:4d} ({s & 3}) | {iss} | {con}")
 print("producer warp 0 per tile: loop top, buffer free, operands written")
 for j in range(0, 64, 8):
     print(f"tile {(j + 16) // 8}: " + " ".join(f"{x - t0:7d}" for x in buf[4, j, :3]))
