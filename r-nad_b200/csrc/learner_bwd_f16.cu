@@ -26,7 +26,8 @@
 // prefetch the tile after it into registers.
 // [History at cfg2: tf32, S^T formulation 128 us -> tf32 mask formulation 106 -> fp16 with H^T and relu^T | M^T in
 //  separate regions, two stages in flight (recompute issued as soon as a stage is loaded) 87 -> named-barrier
-//  hand-overs 84.6 -> this cut.]
+//  hand-overs 84.6 -> four in-place regions 64 -> consumers arrive / issuer syncs 60 (bench.py's per-call time, which
+//  includes the 5 us reduction of the per-CTA partials; the kernel alone: 53 us under ncu, tensor pipe 53 % active).]
 // Reference: loss.backward() of rnad.py:425 through nn/net.py:37-51.
 #include <cuda_fp16.h>
 
