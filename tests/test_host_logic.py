@@ -162,3 +162,34 @@ def test_product_path_fails_loudly_without_cuda(golden):
         States(tree, 4).observations()
     with pytest.raises(_b200.RnadError):
         Episodes(tree, 4).generate(mlp_from_golden(g, "net"))
+
+
+def test_step_engine_fingerprint_sees_what_a_captured_step_bakes_in():
+    """`LearnerStep.quick_key_of` (what RNaD compares every step instead of walking the modules) is stable while nothing
+    changes and differs as soon as a hyper-parameter, the optimizer's settings, a net or a parameter tensor does."""
+    import learn.fused as fused
+    from learn.rnad import RNaD
+    from nn.net import MLP
+
+    tree = seeded_tree(3, max_actions=2, max_transitions=1, depth_bound=2)
+    trial = RNaD(tree=tree, device=torch.device("cpu"), directory_name="pytest_quick_key", batch_size=64, eta=0.2, lr=1e-3,
+                 net_params={"type": "MLP", "max_actions": 2, "width": 256})
+    trial.net, trial.net_target, trial.net_reg, trial.net_reg_ = (MLP(2, 256) for _ in range(4))
+    trial.optimizer = torch.optim.Adam(trial.net.parameters(), lr=1e-3, betas=(0.0, 0.999), eps=1e-8)
+    key = fused.LearnerStep.quick_key_of
+    k0 = key(trial)
+    assert key(trial) == k0 and hash(k0) is not None
+    trial.eta = 0.3
+    k1 = key(trial)
+    assert k1 != k0
+    trial.optimizer.param_groups[0]["lr"] = 5e-4
+    k2 = key(trial)
+    assert k2 != k1
+    trial.net_reg_ = MLP(2, 256)                                   # another module object
+    k3 = key(trial)
+    assert k3 != k2
+    trial.net.value_fc0.weight.data = trial.net.value_fc0.weight.data.clone()     # same Parameter, another storage
+    k4 = key(trial)
+    assert k4 != k3
+    trial.optimizer = torch.optim.Adam(trial.net.parameters(), lr=5e-4, betas=(0.0, 0.999), eps=1e-8)
+    assert key(trial) != k4
