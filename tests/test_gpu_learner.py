@@ -333,7 +333,7 @@ def test_fused_learner_forward_vs_oracle(a, T, B):
     print(f"fused forward A={a}: max |logit error| = {err:.2e} vs fp32 net, {err_tc:.2e} vs fp16-aware oracle")
 
 
-@pytest.mark.parametrize("a,T,B", [(2, 4, 300), (3, 8, 4099), (4, 5, 2048), (3, 2, 77)])
+@pytest.mark.parametrize("a,T,B", [(2, 4, 300), (3, 8, 4099), (4, 5, 2048), (3, 2, 77), (3, 8, 20011), (4, 6, 20011)])
 def test_fused_learner_backward_vs_autograd(a, T, B):
     import learn.fused as fused
     from nn.net import MLP
@@ -392,7 +392,8 @@ def test_fused_learner_backward_vs_autograd(a, T, B):
         assert torch.equal(again, first)
 
 
-@pytest.mark.parametrize("a,T,B", [(2, 4, 300), (3, 8, 4099), (3, 3, 130), (4, 5, 2048)])
+# (the last case gives every CTA eight or nine tiles: the double-buffered tile operands and every barrier parity wrap around)
+@pytest.mark.parametrize("a,T,B", [(2, 4, 300), (3, 8, 4099), (3, 3, 130), (4, 5, 2048), (3, 8, 20011)])
 def test_fused_learner_backward_split_vs_autograd(a, T, B):
     """
     The learner step's backward (`rnad_learner_backward_split`): one UNNORMALISED gradient per player, rows of even t
