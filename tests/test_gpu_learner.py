@@ -276,7 +276,8 @@ def _random_observations(a, T, B, seed):
     return torch.stack([ev * legal, legal], dim=2).contiguous()
 
 
-@pytest.mark.parametrize("a,T,B", [(2, 4, 300), (3, 8, 4099), (4, 5, 2048), (3, 1, 1), (4, 12, 4100)])
+# (the last case: eight or nine tiles per CTA - observation and accumulator double buffers and the barrier ring wrap around)
+@pytest.mark.parametrize("a,T,B", [(2, 4, 300), (3, 8, 4099), (4, 5, 2048), (3, 1, 1), (4, 12, 4100), (3, 8, 20011)])
 def test_fused_learner_forward_vs_oracle(a, T, B):
     import learn.fused as fused
 
